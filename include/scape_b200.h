@@ -1,0 +1,179 @@
+/* libscape_b200.so -- C ABI of the B200-native `scape infer_pa` hot path.
+ *
+ * The reference (chengl7-lab/scape, SCAPE-APA 1.0.4) has no FFI of its own: its hot path sits behind
+ * Python seams.  The entry points below are what a binding of that path
+ * needs; each one names the reference interface it replaces.  The reference-side ctypes stub a
+ * maintainer would add is shown in INTEGRATION.md; the in-repo binding is scape_b200/_lib.py.
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure
+ * (scape_b200_last_error() describes the last failure on the calling thread); all pointers are
+ * caller-owned, contiguous host memory, read-only unless documented as output; the library never
+ * keeps a caller pointer past the call; one handle per device, a handle is not re-entrant.
+ * There is no CPU fallback: without a CUDA device scape_b200_create fails.
+ */
+#ifndef SCAPE_B200_H
+#define SCAPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCAPE_B200_KCAP 15     /* max pA components of one chain (columns = KCAP + 1 with the uniform one) */
+#define SCAPE_B200_NROUND 50   /* apa_core.py:422  nround  */
+#define SCAPE_B200_NTRIAL 10   /* apa_core.py:847  n_trial */
+#define SCAPE_B200_MAX_BETA 64
+#define SCAPE_B200_MAX_S 32
+#define SCAPE_B200_MAX_SMOOTH 1024
+
+/* Model parameters: the TOML keys of `scape infer_pa` (tutorial/default_config.toml,
+ * ApaModel.__init__ apa_core.py:333-363) plus the small tables the Python host derives from them
+ * with numpy so that they are bit-identical to the reference's (apa_core.py:394-396, 684-686, 942). */
+typedef struct scape_b200_params {
+  int32_t n_max_apa, n_min_apa;
+  int64_t utr_length;
+  double min_LA, max_LA, mu_f, sigma_f;
+  double min_pa_gap, max_beta;
+  int32_t theta_step, beta_step;
+  double min_ws, max_unif_ws;
+  int32_t re_run_mode;          /* subsample_run(re_run_mode=...), apa_core.py:984,1023 */
+  int32_t fixed_run_mode;       /* --pre_para_pkl_file, apa_core.py:94-99, 999-1017      */
+  int32_t pre_K;                /* fixed mode: first Parameters object of the pre_para file */
+  int32_t _pad0;
+  int64_t pre_L;
+  double pre_alpha[SCAPE_B200_KCAP];
+  double pre_beta[SCAPE_B200_KCAP];
+  int32_t n_beta, n_s, n_smooth, _pad1;
+  double betas[SCAPE_B200_MAX_BETA];      /* predef_beta_arr (apa_core.py:942 / :896)              */
+  double s_dis[SCAPE_B200_MAX_S];         /* polyA length grid (apa_core.py:394)                   */
+  double pmf_s[SCAPE_B200_MAX_S];         /* its pmf (apa_core.py:395-396)                         */
+  double smooth_w[SCAPE_B200_MAX_SMOOTH]; /* exp(-arange(-3bw,3bw+1)^2 / (2 bw^2)) (apa_core.py:684-685) */
+} scape_b200_params;
+
+/* One batch of UTRs = what `infer` streams out of chunk pickles (apa_core.py:1117-1132), with the
+ * DataFrame columns x, l, r, pa concatenated over UTRs (CSR by read_off).  Each UTR belongs to one
+ * RNG stream; a stream is seeded once (np.random.seed(1) per chunk file, apa_core.py:125) and its
+ * UTRs are consumed in batch order. */
+typedef struct scape_b200_batch {
+  int64_t n_utr;
+  const int64_t* read_off;     /* [n_utr + 1] */
+  const double* x;             /* [read_off[n_utr]]  read start (integer valued)            */
+  const double* l;             /*                     UTR part length of the read            */
+  const double* r;             /*                     polyA length, NaN = unknown            */
+  const double* pa;            /*                     junction pA site, NaN = not a junction */
+  int32_t n_streams;
+  int32_t _pad0;
+  const int32_t* stream_id;    /* [n_utr], values in [0, n_streams) */
+  const uint32_t* stream_seed; /* [n_streams] */
+} scape_b200_batch;
+
+/* Per-UTR results = the fields of scape.apa_core.Parameters (apa_core.py:236-258) that `infer`
+ * pickles.  All arrays are caller-allocated. */
+typedef struct scape_b200_results {
+  int32_t* status;   /* [n_utr] 0 = ok, <0 = the reference would have raised (see host_prep.hpp)  */
+  int32_t* K;        /* [n_utr]                                                                   */
+  int64_t* L;        /* [n_utr]                                                                   */
+  double* alpha;     /* [n_utr * KCAP]       sorted pA sites (bp from the UTR 5' end)             */
+  double* beta;      /* [n_utr * KCAP]                                                            */
+  double* ws;        /* [n_utr * (KCAP + 1)] last used entry = uniform component                  */
+  double* bic;       /* [n_utr]                                                                   */
+  int32_t* n_lb;     /* [n_utr]              length of lb_arr                                     */
+  double* lb_arr;    /* [n_utr * NROUND]                                                          */
+  int64_t* label;    /* [read_off[n_utr]]    per-read hard label, K = noise (apa_core.py:873-881,976) */
+  int32_t* n_frag;   /* [n_utr]              number of bins N (apa_core.py:379)                   */
+  int32_t* n_theta;  /* [n_utr]              theta grid size T                                    */
+  int32_t* path;     /* [n_utr * 4]          sweeps run, K selected by BIC, K after pruning, chains run */
+  double* em_work;   /* [n_utr * 2]          sum over chains/iterations of N*(K+1); total EM iterations */
+} scape_b200_results;
+
+/* Device-side timing of the last fit_batch, CUDA events on the library's stream. */
+typedef struct scape_b200_timing {
+  double table_ms, tensor_ms, em_ms, label_ms;    /* summed kernel durations                  */
+  double host_prep_ms, host_rng_ms, h2d_ms, d2h_ms, total_ms; /* wall clock                    */
+  int64_t launches;                               /* kernels launched by this library          */
+  int64_t waves;
+  double em_grid_bytes;                           /* algorithmic tensor bytes read by the EM grid search */
+  double em_grid_flops;
+  double tensor_exp;                              /* exp() evaluations of the marginal kernel  */
+  double h2d_bytes, d2h_bytes;
+} scape_b200_timing;
+
+typedef struct scape_b200_handle scape_b200_handle;
+
+const char* scape_b200_last_error(void);
+int scape_b200_version(void);
+int scape_b200_device_count(void);
+
+/* ApaModel(**kwargs) lifetime: parameters are fixed per handle. */
+int scape_b200_create(int device, const scape_b200_params* params, scape_b200_handle** out);
+int scape_b200_destroy(scape_b200_handle* h);
+
+/* Replaces the body of `infer` (apa_core.py:1104-1137): subsample_run (+ run / fixed_run,
+ * rm_component, re-run loop, get_label) for every UTR of the batch. */
+int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch* batch, scape_b200_results* out);
+int scape_b200_get_timing(scape_b200_handle* h, scape_b200_timing* out);
+
+/* ---- kernel-seam entry points (parity tests; reference seam B3, apa_core.py:23) ------------- */
+
+/* loglik_xlr_t over a theta list (apa_core.py:620-640, taichi_core.py:183-215):
+ * fragments in, table[n_frag * n_theta] (row-major [n][t]) out. */
+int scape_b200_loglik_table(scape_b200_handle* h, int64_t n_frag, const double* x, const double* l,
+                            const double* r, const double* pa, int64_t n_theta, const double* theta,
+                            double* table_out);
+
+/* get_loglik_marginal_tensor (taichi_core.py:237-246): table[n][t] in, tensor[t][b][n] out. */
+int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, int64_t n_theta, const double* theta,
+                               int64_t n_beta, const double* betas, const double* table,
+                               double* tensor_out);
+
+/* em_algo for explicit initial chains on one UTR's tensor (apa_core.py:714-779): inputs are the
+ * init_para blobs; outputs per chain: alpha/beta grid indices, ws, bic, lb_arr, n_iter and the
+ * per-iteration trace (alpha idx, beta idx, ws after each iteration). */
+typedef struct scape_b200_chain_io {
+  int32_t K;
+  int32_t weights_only;                 /* fixed_inference_flag (apa_core.py:735-736) */
+  int32_t a_idx[SCAPE_B200_KCAP];
+  int32_t b_idx[SCAPE_B200_KCAP];
+  double ws[SCAPE_B200_KCAP + 1];
+  uint8_t k_order[SCAPE_B200_NROUND + 6];
+  /* outputs */
+  int32_t n_iter;
+  int32_t _pad;
+  double bic;
+  double lb_arr[SCAPE_B200_NROUND];
+} scape_b200_chain_io;
+
+int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_t n_theta, int64_t n_beta,
+                         const double* tensor, const double* cnt, double unif_loglik,
+                         int64_t n_chains, scape_b200_chain_io* chains,
+                         int32_t* trace_a, int32_t* trace_b, double* trace_ws /* optional, may be NULL */);
+
+/* ---- host pre-pass entry points (no GPU needed; CPU tests) --------------------------------- */
+
+/* bin_data (apa_core.py:285-327).  Outputs sized n_reads; returns the number of bins in *n_bins. */
+int scape_b200_bin_reads(int64_t n_reads, const double* x, const double* l, const double* r, const double* pa,
+                         double* bx, double* bl, double* br, double* bpa, double* cnt, int32_t* read_to_bin,
+                         int64_t* n_bins);
+
+/* Model set-up + coverage profile + peaks for one UTR (apa_core.py:365-462, 681-700, 784-794).
+ * prof_y must hold L + 200 doubles (query with prof_y == NULL first: *L_out is still written). */
+int scape_b200_profile(const scape_b200_params* params, int64_t n_reads, const double* x, const double* l,
+                       const double* r, const double* pa, int64_t* L_out, int64_t* n_theta, double* theta,
+                       double* prof_y, int64_t* n_peaks, int64_t* peak_idx, double* peak_w, int64_t cap);
+
+/* Replay of the reference's initialisation draws on one UTR (apa_core.py:817-829, 720):
+ * n_chains chains with K = ks[i] drawn back to back from a stream seeded with `seed`,
+ * after skipping `skip_u32` 32-bit draws. */
+int scape_b200_draw_chains(const scape_b200_params* params, int64_t n_reads, const double* x, const double* l,
+                           const double* r, const double* pa, uint32_t seed, int64_t n_chains,
+                           const int32_t* ks, scape_b200_chain_io* out);
+
+/* Raw generator access for the RNG tests: fills out[n] with RandomState(seed).random_sample(n)
+ * (kind 0), .randint(0, arg, n) (kind 1), .permutation(arg) (kind 2, n == arg). */
+int scape_b200_rng_draw(uint32_t seed, int kind, int64_t arg, int64_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAPE_B200_H */

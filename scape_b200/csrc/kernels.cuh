@@ -1,0 +1,90 @@
+// sm_100a CUDA kernels of the infer_pa path.  All arithmetic is FP64 like the reference
+// (taichi_core.py:11 `default_fp=ti.f64`); no tensor cores (the path is not a dense contraction).
+//
+//   table_kernel    K2  loglik_xlr_t for every (fragment, theta)         apa_core.py:620-640, taichi_core.py:101-157
+//   tensor_kernel   K3  marginal log-likelihood tensor[t][b][n]          taichi_core.py:160-179, 218-246
+//   em_chain_kernel K4  one coordinate-wise EM chain per CTA, resident   apa_core.py:473-573, 702-779
+//   label_kernel    K5  full E-step + row arg-max                        apa_core.py:873-881
+//
+// HBM layout (per wave of UTRs, one arena):
+//   frag columns x,l,r,pa,cnt  double[sum N]            CSR by UtrDev.frag_off
+//   theta grids                double[sum T]            CSR by UtrDev.theta_off
+//   table                      double[sum T*Npad]       [t][n]  (transposed w.r.t. the reference so that n is contiguous)
+//   tensor                     double[sum T*B*Npad]     [t][b][n], Npad = N rounded up to 4 (32-byte rows)
+//   log_zmat scratch           double[sum_chains (K+1)*Npad]  [k][n]
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/scape_b200.h"
+
+namespace scape {
+
+#define SCAPE_SENTINEL (-3.4028234663852886e38)
+#define SCAPE_PI 3.141592653589793
+
+struct UtrDev {
+  int32_t N, Npad, T, B;
+  int64_t frag_off;
+  int64_t theta_off;
+  int64_t table_off;
+  int64_t tensor_off;
+  double unif_loglik;
+};
+
+struct ModelConst {
+  double mu_f, sigma_f, max_unif_ws;
+  int32_t n_s, n_beta;
+  double s_dis[SCAPE_B200_MAX_S];
+  double pmf_s[SCAPE_B200_MAX_S];
+  double logpmf_s[SCAPE_B200_MAX_S];
+  double betas[SCAPE_B200_MAX_BETA];
+};
+
+struct ChainDev {
+  int32_t utr;
+  int32_t K;
+  int32_t weights_only;
+  int32_t n_iter;                 // out
+  int64_t lz_off;                 // into the log_zmat scratch
+  int64_t v_off;                  // into the global v scratch (only used when v does not fit in smem)
+  int64_t trace_off;              // into the trace buffers, or -1
+  int32_t a_idx[SCAPE_B200_KCAP];
+  int32_t b_idx[SCAPE_B200_KCAP];
+  double ws[SCAPE_B200_KCAP + 1];
+  uint8_t k_order[SCAPE_B200_NROUND + 6];
+  double bic;                     // out
+  double lb_arr[SCAPE_B200_NROUND];  // out
+  double grid_rows;               // out: sum over iterations of candidate rows scanned (W*B)
+};
+
+struct LabelDev {
+  int32_t utr;
+  int32_t K;
+  int64_t out_off;                // into the label buffer (per fragment)
+  int32_t a_idx[SCAPE_B200_KCAP];
+  int32_t b_idx[SCAPE_B200_KCAP];
+  double ws[SCAPE_B200_KCAP + 1];
+};
+
+// (utr, theta index) rows of a wave, flattened for the table / tensor launches
+struct RowRef {
+  int32_t utr;
+  int32_t t;
+};
+
+void launch_table(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, const double* fx,
+                  const double* fl, const double* fr, const double* fpa, const double* theta, double* table,
+                  cudaStream_t st);
+void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, int n_beta, int max_win,
+                   const double* theta, const double* table, double* tensor, cudaStream_t st);
+// returns the number of kernel launches made
+int launch_em(ChainDev* chains, int64_t n_chains, const UtrDev* utrs, const double* tensor, const double* cnt,
+              double* lz, double* vbuf, int max_npad, int32_t* trace_a, int32_t* trace_b, double* trace_ws,
+              cudaStream_t st);
+void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const double* tensor,
+                   const double* cnt, int32_t* labels, cudaStream_t st);
+cudaError_t upload_model_const(const ModelConst& mc);
+
+}  // namespace scape
