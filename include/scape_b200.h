@@ -65,7 +65,10 @@ typedef struct scape_b200_batch {
   int32_t n_streams;
   int32_t _pad0;
   const int32_t* stream_id;    /* [n_utr], values in [0, n_streams) */
-  const uint32_t* stream_seed; /* [n_streams] */
+  const uint32_t* stream_seed; /* [n_streams] np.random.seed(seed) per stream; ignored if stream_state != NULL */
+  uint32_t* stream_state;      /* optional in/out [n_streams * 625]: MT19937 key[624] + pos, i.e.
+                                  np.random.get_state()[1:3]; on return holds the state the reference
+                                  would have left behind, so callers can np.random.set_state() it */
 } scape_b200_batch;
 
 /* Per-UTR results = the fields of scape.apa_core.Parameters (apa_core.py:236-258) that `infer`
@@ -168,6 +171,13 @@ int scape_b200_profile(const scape_b200_params* params, int64_t n_reads, const d
 int scape_b200_draw_chains(const scape_b200_params* params, int64_t n_reads, const double* x, const double* l,
                            const double* r, const double* pa, uint32_t seed, int64_t n_chains,
                            const int32_t* ks, scape_b200_chain_io* out);
+
+/* Process-wide hook: order of np.argsort(values) as the installed numpy computes it.  Called (from
+ * worker threads) only when two candidate coverage peaks have exactly equal height, because
+ * scipy.signal.find_peaks ranks peaks with an unstable np.argsort whose tie order is build / CPU
+ * specific (apa_core.py:784).  NULL (default) = stable order. */
+typedef void (*scape_b200_argsort_fn)(const double* values, int64_t n, int64_t* order_out);
+int scape_b200_set_argsort_callback(scape_b200_argsort_fn fn);
 
 /* Raw generator access for the RNG tests: fills out[n] with RandomState(seed).random_sample(n)
  * (kind 0), .randint(0, arg, n) (kind 1), .permutation(arg) (kind 2, n == arg). */

@@ -1,0 +1,398 @@
+"""Host-side mirror of the reference's `scape.apa_core` for the infer_pa path.
+
+Same names, arguments and error behaviour as the reference module (apa_core.py:40-184, 236-258,
+984-1137) so that the `scape infer_pa` CLI, the TOML parameters, `--pre_para_pkl_file` mode and the
+result pickles are unchanged -- but the per-UTR work (binning, likelihood table, marginal tensor,
+EM chains, BIC selection, pruning, re-run, labels) happens in libscape_b200.so on the GPU.  There
+is no CPU / Taichi fallback: if the library or a CUDA device is missing, these functions raise.
+
+The module also keeps `exp_pa_len` / `cal_exp_pa_len_by_cluster` importable (the reference's
+`utils.py:3` imports them from `scape.apa_core`; they are small numpy helpers outside the hot path).
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import pickle
+import time
+import tomllib
+from multiprocessing import Event, Process
+from pathlib import Path
+from timeit import default_timer as timer
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+try:  # the CLI decorators need click (a reference dependency); the Python API works without it
+    import click
+except Exception:  # pragma: no cover
+    click = None
+
+
+class Parameters:
+    """Result record, attribute-for-attribute the reference's (apa_core.py:236-258).  Pickled under
+    the class path `scape.apa_core.Parameters` so `merge_pa` / `cal_exp_pa_len` / `ex_pa_cnt_mat`
+    load the results untouched (junction_handler.py:7,76)."""
+
+    def __init__(self, title='', alpha_arr=None, beta_arr=None, ws=None, L=None, cb_id_arr=None, readID_arr=None,
+                 K=None):
+        self.title = title
+        self.alpha_arr = alpha_arr
+        self.beta_arr = beta_arr
+        self.ws = ws
+        self.K = len(self.alpha_arr)
+        self.L = L
+        self.cb_id_arr = cb_id_arr
+        self.readID_arr = readID_arr
+
+    def __str__(self):
+        outstr = '-' * 10 + f'{self.title} K={self.K}' + '-' * 10 + '\n'
+        if hasattr(self, 'gene_info_str'):
+            outstr += f'gene info: {self.gene_info_str}\n'
+        outstr += f'K={self.K} L={self.L} Last component is uniform component.\n'
+        outstr += f'alpha_arr={self.alpha_arr}\n'
+        outstr += f'beta_arr={self.beta_arr}\n'
+        outstr += f'ws={np.around(self.ws, decimals=2)}\n'
+        if hasattr(self, 'bic'):
+            outstr += f'bic={np.around(self.bic, decimals=2)}\n'
+        outstr += '-' * 30 + '\n'
+        return outstr
+
+
+Parameters.__module__ = "scape.apa_core"
+
+STATUS_MESSAGES = {
+    -1: "AssertionError: read start outside [0, utr_length) (apa_core.py:388)",
+    -2: "read coordinates exceed the supported bin range",
+    -3: "UTR without reads",
+    -4: f"re-run would need more than {_lib.KCAP} pA components",
+    -5: "invalid parameters",
+    -6: "ValueError: Fewer non-zero entries in p than size (np.random.choice in sample_alpha, apa_core.py:797)",
+}
+
+
+def _result_class():
+    """The class object pickles must reference: whatever `scape.apa_core.Parameters` resolves to
+    (this repo's shim, or the reference package when this path is grafted into it)."""
+    try:
+        import importlib
+        mod = importlib.import_module("scape.apa_core")
+        return getattr(mod, "Parameters", Parameters)
+    except Exception:
+        return Parameters
+
+
+# ------------------------------------------------------------------------------------------------
+# batch driver (new API: many chunks at once)
+# ------------------------------------------------------------------------------------------------
+class ChunkBatch:
+    """UTRs of one or more chunk files packed as CSR read columns."""
+
+    def __init__(self):
+        self.gene_info: List[str] = []
+        self.frames = []          # (cb_id, read_id) per UTR
+        self.cols = [[], [], [], []]
+        self.n_reads: List[int] = []
+        self.stream: List[int] = []
+
+    def add(self, gene_info_str, df, stream: int):
+        self.gene_info.append(gene_info_str)
+        for c, name in zip(self.cols, ("x", "l", "r", "pa")):
+            c.append(np.asarray(df[name], dtype=np.float64))
+        self.frames.append((np.array(df["cb_id"]), np.array(df["read_id"])))
+        self.n_reads.append(len(self.cols[0][-1]))
+        self.stream.append(stream)
+
+    def __len__(self):
+        return len(self.gene_info)
+
+    def packed(self):
+        off = np.zeros(len(self) + 1, np.int64)
+        np.cumsum(self.n_reads, out=off[1:])
+        cat = [np.concatenate(c) if c else np.zeros(0) for c in self.cols]
+        return off, cat[0], cat[1], cat[2], cat[3], np.asarray(self.stream, np.int32)
+
+
+def read_chunk_file(path) -> list:
+    """All (gene_info_str, DataFrame) tuples of a prepare_input chunk (apa_core.py:1117-1132)."""
+    out = []
+    with open(path, 'rb') as fh:
+        while True:
+            try:
+                out.append(pickle.load(fh))
+            except EOFError:
+                return out
+
+
+def results_to_parameters(batch: ChunkBatch, out, fixed_run_mode: bool) -> list:
+    """FitOutput -> list of Parameters (one per UTR, input order)."""
+    cls = _result_class()
+    off = np.zeros(len(batch) + 1, np.int64)
+    np.cumsum(batch.n_reads, out=off[1:])
+    res = []
+    for u in range(len(batch)):
+        if out.status[u] != 0:
+            msg = STATUS_MESSAGES.get(int(out.status[u]), f"status {int(out.status[u])}")
+            if out.status[u] == -1:
+                raise AssertionError(f"{batch.gene_info[u]}: {msg}")
+            raise Exception(f"{batch.gene_info[u]}: {msg}")
+        K = int(out.K[u])
+        para = cls(title='Final Result (subsample run)' if fixed_run_mode else 'Final Result',
+                   alpha_arr=out.alpha[u, :K].astype('int'), beta_arr=out.beta[u, :K].copy(),
+                   ws=out.ws[u, :K + 1].copy(), L=int(out.L[u]),
+                   cb_id_arr=batch.frames[u][0], readID_arr=batch.frames[u][1])
+        para.bic = np.float64(out.bic[u])
+        para.lb_arr = [np.float64(v) for v in out.lb_arr[u, :int(out.n_lb[u])]]
+        para.label_arr = out.label[off[u]:off[u + 1]].copy()
+        para.gene_info_str = batch.gene_info[u]
+        res.append(para)
+    return res
+
+
+def _load_pre_para(kwargs):
+    assert kwargs["pre_para_pkl_file"]
+    assert os.path.exists(kwargs["pre_para_pkl_file"])
+    with open(kwargs["pre_para_pkl_file"], 'rb') as fh:
+        return pickle.load(fh)          # first object only (apa_core.py:1002-1003)
+
+
+def fit_chunks(chunks: Sequence[Sequence[tuple]], seeds: Optional[Sequence[int]] = None, device: int = 0,
+               engine: Optional[_lib.Engine] = None, return_raw: bool = False, stream_state=None, **kwargs):
+    """Fit every UTR of several in-memory chunks in ONE library call.  Each chunk is one RNG stream
+    (seed 1 by default, like `_infer_pa`), so results equal running `infer` per file.  Returns a
+    list (per chunk) of lists of Parameters."""
+    fixed = bool(kwargs.get("fixed_run_mode", False))
+    pre_para = _load_pre_para(kwargs) if fixed else None
+    batch = ChunkBatch()
+    for s, chunk in enumerate(chunks):
+        for gene_info_str, df in chunk:
+            batch.add(gene_info_str, df, s)
+    if seeds is None:
+        seeds = [1] * len(chunks)
+    own = engine is None
+    if own:
+        engine = _lib.Engine(_lib.make_params(pre_para=pre_para, **kwargs), device=device)
+    try:
+        off, x, l, r, pa, sid = batch.packed()
+        out = engine.fit(off, x, l, r, pa, sid, np.asarray(seeds, np.uint32), stream_state=stream_state)
+    finally:
+        if own:
+            engine.close()
+    paras = results_to_parameters(batch, out, fixed)
+    per_chunk, pos = [], 0
+    for chunk in chunks:
+        per_chunk.append(paras[pos:pos + len(chunk)])
+        pos += len(chunk)
+    return (per_chunk, out) if return_raw else per_chunk
+
+
+# ------------------------------------------------------------------------------------------------
+# reference API (same signatures)
+# ------------------------------------------------------------------------------------------------
+def subsample_run(return_model=False, re_run_mode=True, gene_info_str="None", fixed_run_mode=False, **kwargs):
+    """apa_core.py:984-1035 for one UTR (`data=DataFrame`).  Consumes and advances the global numpy
+    legacy RNG exactly like the reference."""
+    if return_model:
+        raise NotImplementedError("return_model=True exposes the reference's ApaModel object; not part of the hot path")
+    tbl = kwargs.pop('data')
+    state = np.random.get_state()
+    ss = np.empty((1, 625), np.uint32)
+    ss[0, :624] = state[1]
+    ss[0, 624] = state[2]
+    res = fit_chunks([[(gene_info_str, tbl)]], re_run_mode=re_run_mode, fixed_run_mode=fixed_run_mode,
+                     stream_state=ss, **kwargs)[0][0]
+    np.random.set_state((state[0], ss[0, :624].copy(), int(ss[0, 624]), 0, 0.0))
+    return res
+
+
+def infer(pickle_input_file, pickle_output_file, **kwargs):
+    """apa_core.py:1104-1137: fit every UTR of a chunk pickle, then dump the Parameters objects in
+    input order.  The whole file is one library call; the global numpy RNG is consumed and advanced
+    as the reference would."""
+    print(f"start inferring APA events from input pickle file = {pickle_input_file}. Output file = {pickle_input_file}")
+    start_t = timer()
+    chunk = read_chunk_file(pickle_input_file)
+    state = np.random.get_state()
+    ss = np.empty((1, 625), np.uint32)
+    ss[0, :624] = state[1]
+    ss[0, 624] = state[2]
+    res_lst = fit_chunks([chunk], stream_state=ss, **kwargs)[0]
+    np.random.set_state((state[0], ss[0, :624].copy(), int(ss[0, 624]), 0, 0.0))
+    end_t = timer()
+    print(f"Done {len(res_lst)} UTR regions in {(end_t - start_t) / 60} min.")
+    with open(pickle_output_file, 'wb') as fh:
+        for res in res_lst:
+            print(f"save result of {res.gene_info_str}")
+            pickle.dump(res, fh)
+
+
+def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0, **kwargs) -> List[str]:
+    """Multi-file entry point: same per-file seeding and output naming as
+    `_infer_pa`, but all files share one library call so their UTRs run concurrently."""
+    os.makedirs(os.path.join(output_dir, "pkl_output"), exist_ok=True)
+    names, outs = [], []
+    for f in pkl_input_files:
+        if not os.path.exists(f):
+            raise Exception("Given input file does not exists")
+        name = os.path.basename(f)[:-10]
+        if ".tmp." in name:
+            raise Exception("The input file " + name + " is incomplete. Please re-run prepare_input() on " +
+                            name.split(".")[0] + ".bam")
+        names.append(name)
+        outs.append(os.path.join(output_dir, "pkl_output", name + ".res.pkl"))
+    for o in outs:
+        if os.path.exists(o):
+            os.remove(o)
+    chunks = [read_chunk_file(f) for f in pkl_input_files]
+    results = fit_chunks(chunks, seeds=[1] * len(chunks), device=device, **kwargs)
+    for o, res_lst in zip(outs, results):
+        with open(o, 'wb') as fh:
+            for res in res_lst:
+                pickle.dump(res, fh)
+    return outs
+
+
+def _infer_pa(pkl_input_file: str, output_dir: str, **kwargs):
+    """apa_core.py:107-147."""
+    if not (os.path.exists(pkl_input_file)):
+        raise Exception("Given input file does not exists")
+    if not (os.path.exists(os.path.join(output_dir, "pkl_output"))):
+        os.makedirs(os.path.join(output_dir, "pkl_output"))
+    np.random.seed(1)
+    filename = os.path.basename(pkl_input_file)[:-10]
+    if ".tmp." in filename:
+        raise Exception("The input file " + filename + " is incomplete. Please re-run prepare_input() on " +
+                        filename.split(".")[0] + ".bam")
+    out_pkl_file = os.path.join(output_dir, "pkl_output", filename + ".res.pkl")
+    if os.path.exists(out_pkl_file):
+        os.remove(out_pkl_file)
+    watch_dog_flag = kwargs.get("watch_dog_flag", False)
+    if watch_dog_flag:
+        exit_event = Event()
+        log_file = os.path.join(output_dir, "pkl_output", filename + "log.txt")
+        infer_with_watchdog = watch_dog(log_file, exit_event)(infer)
+        infer_with_watchdog(pkl_input_file, out_pkl_file, **kwargs)
+    else:
+        infer(pkl_input_file, out_pkl_file, **kwargs)
+
+
+def run_infer_pa(pkl_input_file: str, output_dir: str, toml_para_file: str = None, pre_para_pkl_file=None):
+    """Body of the `infer_pa` click command (apa_core.py:67-104)."""
+    assert Path(output_dir).exists()
+    para_dict = {"n_max_apa": 5, "pre_para_pkl_file": pre_para_pkl_file}
+
+    if toml_para_file is None:
+        toml_para_file = Path(output_dir) / "parameters.toml"
+
+    if toml_para_file:
+        assert os.path.exists(toml_para_file)
+        with open(toml_para_file, "rb") as fh:
+            user_para_dict = tomllib.load(fh)
+            para_dict.update(user_para_dict)
+        print(f"Parameter file {toml_para_file} loaded.")
+        for k, v in user_para_dict.items():
+            print(f"{k} = {v}")
+        print()
+
+    if pre_para_pkl_file:
+        assert os.path.exists(pre_para_pkl_file)
+        para_dict["fixed_run_mode"] = True
+        para_dict["pre_para_pkl_file"] = pre_para_pkl_file
+        import tomli_w
+        with open(toml_para_file, 'wb') as fh:
+            tomli_w.dump(para_dict, fh)
+
+    if "output_dir" in para_dict:
+        del para_dict["output_dir"]
+
+    _infer_pa(pkl_input_file, output_dir, **para_dict)
+
+
+if click is not None:
+    @click.command(name="infer_pa")
+    @click.option('--pkl_input_file', type=str, help='input pickle file (result of prepare_input)', required=True)
+    @click.option('--output_dir', type=str, help='output directory', required=True)
+    @click.option('--toml_para_file', type=str, help='a TOML file specifies user-defined parameters', default=None,
+                  required=False)
+    @click.option('--pre_para_pkl_file', type=str,
+                  help='a pickle file with pre-specified pA sites and utr length, result file of scape analysis',
+                  default=None, required=False)
+    def infer_pa(pkl_input_file: str, output_dir: str, toml_para_file: str = None, pre_para_pkl_file=None):
+        """
+        INPUT:
+        - pkl_input_file: file path (pickle) including information for each UTR region
+        - output_dir: path to output_dir folder
+        - toml_para_file: a TOML file specifies user-defined parameters
+
+        OUTPUT:
+        - Pickle file including Parameters for each UTR region
+        """
+        run_infer_pa(pkl_input_file, output_dir, toml_para_file, pre_para_pkl_file)
+else:  # pragma: no cover
+    infer_pa = run_infer_pa
+
+
+# ---- helpers the reference's downstream stages import from scape.apa_core (utils.py:3) ------------
+def exp_pa_len(apamix_res, label_arr):
+    """Expected pA length statistic (apa_core.py:1038-1052)."""
+    if apamix_res.K == 1:
+        return 1.0
+    if len(label_arr) == 0:
+        return np.nan
+    is_pa = label_arr < apamix_res.K
+    if not np.any(is_pa):
+        return np.nan
+    labs, cnt = np.unique(label_arr[is_pa], return_counts=True)
+    ws = np.zeros(apamix_res.K)
+    ws[labs] = cnt
+    ws = ws / np.sum(ws)
+    a = apamix_res.alpha_arr
+    return np.sum(ws * (1.0 + 9.0 * (a - a[0]) / (a[-1] - a[0])))
+
+
+def cal_exp_pa_len_by_cluster(apamix_res, partition):
+    """apa_core.py:1055-1063."""
+    partition = np.array(partition)
+    clusters = np.unique(partition)
+    out = np.zeros(len(clusters))
+    for i, c in enumerate(clusters):
+        out[i] = exp_pa_len(apamix_res, apamix_res.label_arr[partition == c])
+    return clusters, out
+
+
+# ---- watchdog (apa_core.py:1066-1101) -------------------------------------------------------------
+def _watch_dog(log_file: str, exit_event):
+    import psutil
+    gib = 1024.0 ** 3
+    with open(log_file, "w") as fh:
+        while not exit_event.is_set():
+            mem = psutil.virtual_memory()
+            used, avail, total = round(mem.used / gib, 2), round(mem.available / gib, 2), round(mem.total / gib, 2)
+            fh.write(datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S") + "\n")
+            fh.write(f'The CPU usage is: {psutil.cpu_percent(4)}%\n')
+            fh.write(f"Memory usage: used = {used} GB ({round(used / total * 100, 2)}%);  "
+                     f"available={avail} GB ({round(avail / total * 100, 2)}%); total={total} GB\n")
+            fh.write(str(mem))
+            fh.write("\n\n")
+            fh.flush()
+            exit_event.wait(60)
+
+
+def watch_dog(log_file: str, exit_event):
+    def decorate(task_func):
+        def wrapper(*args, **kwargs):
+            print(f"Launching watch dog. log_file = {log_file}")
+            proc = Process(target=_watch_dog, args=(log_file, exit_event))
+            proc.start()
+            start_t = timer()
+            try:
+                return task_func(*args, **kwargs)
+            finally:
+                print(f"Task takes {(timer() - start_t) / 60} minutes.")
+                print("Task finished, terminating watch dog process.")
+                exit_event.set()
+                proc.join()
+        return wrapper
+    return decorate

@@ -1,0 +1,832 @@
+// libscape_b200.so: C ABI (include/scape_b200.h) + the wave scheduler that drives the kernels.
+//
+// Replaces the body of the reference's `infer` loop (apa_core.py:1104-1137): for every UTR of a
+// batch it does what subsample_run -> ApaModel.run / fixed_run do (apa_core.py:883-1035), with the
+// likelihood phases and every EM chain on the GPU and the (tiny, serial) model-selection logic and
+// the numpy-legacy RNG replay on the host.
+//
+// Scheduling: the reference seeds the global RNG once per chunk file and the amount of randomness
+// a UTR consumes depends on its own result (rm_component :843, re-run loop :1023-1030), so the
+// UTRs of one stream form a serial chain at the RNG level.  A *wave* therefore takes the next
+// unfinished UTR of every stream; all chains of all UTRs of a wave run concurrently.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <functional>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "host_prep.hpp"
+#include "kernels.cuh"
+
+namespace scape {
+int launch_em_groups(ChainDev* chains_dev, const ChainDev* chains_host, int64_t n_chains, const UtrDev* utrs_host,
+                     const UtrDev* utrs_dev, const double* tensor, const double* cnt, double* lz, double* vbuf,
+                     int32_t* order_dev, int32_t* order_host, int32_t* trace_a, int32_t* trace_b,
+                     double* trace_ws, cudaStream_t st);
+}
+
+using namespace scape;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(-100, std::string(#call) + ": " + cudaGetErrorString(e__));                      \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc((void**)&p, cap * sizeof(T));
+    if (e != cudaSuccess) cap = 0;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct scape_b200_handle {
+  int device = 0;
+  scape_b200_params P;
+  ModelConst mc;
+  cudaStream_t st = nullptr;
+  DevBuf<double> d_fx, d_fl, d_fr, d_fpa, d_cnt, d_theta, d_table, d_tensor, d_lz, d_v, d_trace_ws;
+  DevBuf<UtrDev> d_utrs;
+  DevBuf<RowRef> d_rows;
+  DevBuf<ChainDev> d_chains;
+  DevBuf<int32_t> d_order, d_labels, d_trace_a, d_trace_b;
+  DevBuf<LabelDev> d_jobs;
+  cudaEvent_t ev[8];
+  scape_b200_timing tm;
+  double wave_budget_bytes = 24e9;
+  int host_threads = 0;
+};
+
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+static int pad4(int64_t n) { return int((n + 3) / 4 * 4); }
+
+static void fill_model_const(const scape_b200_params& P, ModelConst& mc) {
+  memset(&mc, 0, sizeof(mc));
+  mc.mu_f = P.mu_f;
+  mc.sigma_f = P.sigma_f;
+  mc.max_unif_ws = P.max_unif_ws;
+  mc.n_s = P.n_s;
+  mc.n_beta = P.n_beta;
+  for (int i = 0; i < P.n_s; i++) {
+    mc.s_dis[i] = P.s_dis[i];
+    mc.pmf_s[i] = P.pmf_s[i];
+    mc.logpmf_s[i] = std::log(P.pmf_s[i]);
+  }
+  for (int i = 0; i < P.n_beta; i++) mc.betas[i] = P.betas[i];
+}
+
+static int check_params(const scape_b200_params& P) {
+  if (P.n_beta <= 0 || P.n_beta > SCAPE_B200_MAX_BETA) return fail(-5, "n_beta out of range");
+  if (P.n_s <= 0 || P.n_s > SCAPE_B200_MAX_S) return fail(-5, "n_s out of range");
+  if (P.n_smooth <= 0 || P.n_smooth > SCAPE_B200_MAX_SMOOTH || P.n_smooth % 2 == 0)
+    return fail(-5, "n_smooth out of range");
+  if (P.theta_step <= 0 || P.beta_step <= 0) return fail(-5, "theta_step / beta_step must be positive");
+  if (P.n_max_apa > SCAPE_B200_KCAP || P.n_min_apa < 1)
+    return fail(-5, "n_max_apa above SCAPE_B200_KCAP or n_min_apa < 1");
+  if (P.fixed_run_mode && (P.pre_K < 1 || P.pre_K > SCAPE_B200_KCAP)) return fail(-5, "pre_K out of range");
+  return 0;
+}
+
+// widest marginal window (in grid points) any (alpha, beta) of this parameter set can have
+static int max_window(const scape_b200_params& P) {
+  double bmax = 0;
+  for (int i = 0; i < P.n_beta; i++) bmax = std::max(bmax, P.betas[i]);
+  return 2 * int(std::floor(3 * bmax / P.theta_step)) + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* scape_b200_last_error(void) { return g_err.c_str(); }
+int scape_b200_version(void) { return 100; }
+
+int scape_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int scape_b200_create(int device, const scape_b200_params* params, scape_b200_handle** out) {
+  if (!params || !out) return fail(-5, "null argument");
+  if (int rc = check_params(*params)) return rc;
+  int n = scape_b200_device_count();
+  if (n <= 0) return fail(-101, "no CUDA device: libscape_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail(-101, "device index out of range");
+  CU(cudaSetDevice(device));
+  scape_b200_handle* h = new scape_b200_handle();
+  h->device = device;
+  h->P = *params;
+  fill_model_const(h->P, h->mc);
+  CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  memset(&h->tm, 0, sizeof(h->tm));
+  if (const char* s = getenv("SCAPE_B200_WAVE_GB")) h->wave_budget_bytes = atof(s) * 1e9;
+  if (const char* s = getenv("SCAPE_B200_THREADS")) h->host_threads = atoi(s);
+  *out = h;
+  return 0;
+}
+
+int scape_b200_destroy(scape_b200_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  h->d_fx.release(); h->d_fl.release(); h->d_fr.release(); h->d_fpa.release(); h->d_cnt.release();
+  h->d_theta.release(); h->d_table.release(); h->d_tensor.release(); h->d_lz.release(); h->d_v.release();
+  h->d_trace_ws.release(); h->d_utrs.release(); h->d_rows.release(); h->d_chains.release();
+  h->d_order.release(); h->d_labels.release(); h->d_trace_a.release(); h->d_trace_b.release();
+  h->d_jobs.release();
+  for (auto& e : h->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+int scape_b200_get_timing(scape_b200_handle* h, scape_b200_timing* out) {
+  if (!h || !out) return fail(-5, "null argument");
+  *out = h->tm;
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// wave machinery
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct WaveUtr {
+  int64_t u;          // index into the batch
+  int k_max, k_min;   // current sweep range
+  int sweeps = 0, chains_run = 0, k_selected = 0;
+  bool done = false;
+  ChainDev best;      // current result chain (a_idx/b_idx/ws/bic/lb_arr/n_iter)
+  double work = 0, iters = 0;
+};
+
+int np_argmin(const std::vector<double>& v) {
+  int best = 0;
+  for (int i = 0; i < (int)v.size(); i++) {
+    if (std::isnan(v[size_t(i)])) return i;
+    if (v[size_t(i)] < v[size_t(best)]) best = i;
+  }
+  return best;
+}
+
+// Upload chains, run them, bring them back.  `utrs_host` is the wave's UtrDev array.
+int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::vector<UtrDev>& utrs_host,
+               bool want_trace = false) {
+  if (chains.empty()) return 0;
+  int64_t lz = 0, vsz = 0, tr = 0;
+  for (auto& c : chains) {
+    const UtrDev& u = utrs_host[size_t(c.utr)];
+    c.lz_off = lz;
+    lz += int64_t(c.K + 1) * u.Npad;
+    c.v_off = vsz;
+    if (u.Npad > 24576) vsz += u.Npad;
+    c.trace_off = want_trace ? tr : -1;
+    tr += int64_t(SCAPE_B200_NROUND) * (SCAPE_B200_KCAP + 1);
+    c.n_iter = 0;
+  }
+  CU(h->d_lz.ensure(size_t(lz)));
+  CU(h->d_v.ensure(size_t(std::max<int64_t>(vsz, 1))));
+  CU(h->d_chains.ensure(chains.size()));
+  CU(h->d_order.ensure(chains.size()));
+  if (want_trace) {
+    CU(h->d_trace_a.ensure(size_t(tr)));
+    CU(h->d_trace_b.ensure(size_t(tr)));
+    CU(h->d_trace_ws.ensure(size_t(tr)));
+  }
+  std::vector<int32_t> order(chains.size());
+  double t0 = now_ms();
+  CU(cudaMemcpyAsync(h->d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, h->st));
+  h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size());
+  CU(cudaEventRecord(h->ev[4], h->st));
+  int nl = launch_em_groups(h->d_chains.p, chains.data(), int64_t(chains.size()), utrs_host.data(), h->d_utrs.p,
+                            h->d_tensor.p, h->d_cnt.p, h->d_lz.p, h->d_v.p, h->d_order.p, order.data(),
+                            h->d_trace_a.p, h->d_trace_b.p, h->d_trace_ws.p, h->st);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev[5], h->st));
+  CU(cudaMemcpyAsync(chains.data(), h->d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  h->tm.d2h_bytes += double(sizeof(ChainDev) * chains.size());
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+  h->tm.em_ms += ms;
+  h->tm.launches += nl;
+  (void)t0;
+  for (auto& c : chains) {
+    const UtrDev& u = utrs_host[size_t(c.utr)];
+    h->tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;
+    h->tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
+  }
+  return 0;
+}
+
+void parallel_for(int64_t n, int threads, const std::function<void(int64_t)>& fn) {
+  if (threads <= 0) threads = int(std::thread::hardware_concurrency());
+  threads = int(std::max<int64_t>(1, std::min<int64_t>(threads, n)));
+  if (threads == 1) {
+    for (int64_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::vector<std::thread> pool;
+  std::atomic<int64_t> next(0);
+  for (int t = 0; t < threads; t++)
+    pool.emplace_back([&]() {
+      for (;;) {
+        int64_t i = next.fetch_add(1);
+        if (i >= n) break;
+        fn(i);
+      }
+    });
+  for (auto& th : pool) th.join();
+}
+}  // namespace
+
+extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch* bt, scape_b200_results* out) {
+  if (!h || !bt || !out) return fail(-5, "null argument");
+  CU(cudaSetDevice(h->device));
+  const scape_b200_params& P = h->P;
+  const int64_t U = bt->n_utr;
+  memset(&h->tm, 0, sizeof(h->tm));
+  const double t_begin = now_ms();
+  CU(upload_model_const(h->mc));
+
+  // ---- host pre-pass (RNG free), parallel over UTRs -------------------------------------------
+  std::vector<UtrPrep> prep(static_cast<size_t>(U));
+  double t0 = now_ms();
+  parallel_for(U, h->host_threads, [&](int64_t u) {
+    const int64_t a = bt->read_off[u], n = bt->read_off[u + 1] - a;
+    UtrPrep& p = prep[size_t(u)];
+    if (bin_reads(bt->x + a, bt->l + a, bt->r + a, bt->pa + a, n, p) != kOk) return;
+    if (setup_model(P, bt->x + a, bt->l + a, n, p) != kOk) return;
+    coverage_and_peaks(P, p);
+  });
+  h->tm.host_prep_ms += now_ms() - t0;
+
+  // ---- streams --------------------------------------------------------------------------------
+  const int S = bt->n_streams;
+  std::vector<std::vector<int64_t>> stream_utrs(static_cast<size_t>(S));
+  for (int64_t u = 0; u < U; u++) {
+    int s = bt->stream_id[u];
+    if (s < 0 || s >= S) return fail(-5, "stream_id out of range");
+    stream_utrs[size_t(s)].push_back(u);
+  }
+  std::vector<NpRandomState> rng;
+  rng.reserve(size_t(S));
+  for (int s = 0; s < S; s++) {
+    if (bt->stream_state) {
+      rng.emplace_back(0u);
+      memcpy(rng.back().key, bt->stream_state + size_t(s) * 625, 624 * sizeof(uint32_t));
+      rng.back().pos = int(bt->stream_state[size_t(s) * 625 + 624]);
+      if (rng.back().pos < 0 || rng.back().pos > 624) return fail(-5, "stream_state: bad MT19937 position");
+    } else {
+      rng.emplace_back(bt->stream_seed[s]);
+    }
+  }
+  std::vector<size_t> cursor(size_t(S), 0);
+
+  for (int64_t u = 0; u < U; u++) {
+    out->status[u] = prep[size_t(u)].status;
+    out->K[u] = 0;
+    out->L[u] = prep[size_t(u)].L;
+    out->n_frag[u] = int32_t(prep[size_t(u)].n());
+    out->n_theta[u] = int32_t(prep[size_t(u)].T());
+    out->n_lb[u] = 0;
+    out->bic[u] = NAN;
+    for (int i = 0; i < 4; i++) out->path[u * 4 + i] = 0;
+    out->em_work[u * 2] = out->em_work[u * 2 + 1] = 0;
+  }
+
+  const int maxwin = max_window(P);
+  std::vector<int32_t> stream_of(static_cast<size_t>(U));
+  for (int64_t u = 0; u < U; u++) stream_of[size_t(u)] = bt->stream_id[u];
+
+  for (;;) {
+    // ---- pick the wave: next UTR of every stream, within the memory budget ---------------------
+    std::vector<WaveUtr> wave;
+    double bytes = 0;
+    for (int s = 0; s < S; s++) {
+      while (cursor[size_t(s)] < stream_utrs[size_t(s)].size()) {
+        int64_t u = stream_utrs[size_t(s)][cursor[size_t(s)]];
+        if (prep[size_t(u)].status != kOk) { cursor[size_t(s)]++; continue; }   // the reference would have raised
+        const UtrPrep& p = prep[size_t(u)];
+        double need = double(p.T()) * p.B() * pad4(p.n()) * 8.0 * 1.1;
+        if (!wave.empty() && bytes + need > h->wave_budget_bytes) break;
+        bytes += need;
+        WaveUtr w;
+        w.u = u;
+        w.k_max = P.fixed_run_mode ? P.pre_K : P.n_max_apa;
+        w.k_min = P.fixed_run_mode ? P.pre_K : P.n_min_apa;
+        memset(&w.best, 0, sizeof(ChainDev));
+        wave.push_back(w);
+        cursor[size_t(s)]++;
+        break;
+      }
+    }
+    if (wave.empty()) break;
+    h->tm.waves++;
+
+    // ---- device layout of the wave --------------------------------------------------------------
+    const size_t W = wave.size();
+    std::vector<UtrDev> ud(W);
+    std::vector<RowRef> rows;
+    int64_t nf = 0, nt = 0, ntab = 0, nten = 0;
+    int max_n = 0;
+    for (size_t i = 0; i < W; i++) {
+      const UtrPrep& p = prep[size_t(wave[i].u)];
+      UtrDev& d = ud[i];
+      d.N = int32_t(p.n()); d.Npad = pad4(p.n()); d.T = int32_t(p.T()); d.B = int32_t(p.B());
+      d.frag_off = nf; d.theta_off = nt; d.table_off = ntab; d.tensor_off = nten;
+      d.unif_loglik = p.unif_loglik;
+      nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += int64_t(d.T) * d.B * d.Npad;
+      max_n = std::max(max_n, d.Npad);
+      for (int t = 0; t < d.T; t++) rows.push_back({int32_t(i), t});
+    }
+    std::vector<double> hx(size_t(nf), 0.0), hl(size_t(nf), 0.0), hr(size_t(nf), 0.0), hpa(size_t(nf), 0.0),
+        hc(size_t(nf), 0.0), hth(static_cast<size_t>(nt));
+    for (size_t i = 0; i < W; i++) {
+      const UtrPrep& p = prep[size_t(wave[i].u)];
+      std::copy(p.x.begin(), p.x.end(), hx.begin() + ud[i].frag_off);
+      std::copy(p.l.begin(), p.l.end(), hl.begin() + ud[i].frag_off);
+      std::copy(p.r.begin(), p.r.end(), hr.begin() + ud[i].frag_off);
+      std::copy(p.pa.begin(), p.pa.end(), hpa.begin() + ud[i].frag_off);
+      std::copy(p.cnt.begin(), p.cnt.end(), hc.begin() + ud[i].frag_off);
+      std::copy(p.theta.begin(), p.theta.end(), hth.begin() + ud[i].theta_off);
+    }
+    CU(h->d_fx.ensure(size_t(nf))); CU(h->d_fl.ensure(size_t(nf))); CU(h->d_fr.ensure(size_t(nf)));
+    CU(h->d_fpa.ensure(size_t(nf))); CU(h->d_cnt.ensure(size_t(nf))); CU(h->d_theta.ensure(size_t(nt)));
+    CU(h->d_table.ensure(size_t(ntab))); CU(h->d_tensor.ensure(size_t(nten)));
+    CU(h->d_utrs.ensure(W)); CU(h->d_rows.ensure(rows.size()));
+    const size_t fb = sizeof(double) * size_t(nf);
+    CU(cudaMemcpyAsync(h->d_fx.p, hx.data(), fb, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_fl.p, hl.data(), fb, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_fr.p, hr.data(), fb, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_fpa.p, hpa.data(), fb, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_cnt.p, hc.data(), fb, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_theta.p, hth.data(), sizeof(double) * size_t(nt), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_utrs.p, ud.data(), sizeof(UtrDev) * W, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, h->st));
+    h->tm.h2d_bytes += double(5 * fb + sizeof(double) * size_t(nt) + sizeof(UtrDev) * W + sizeof(RowRef) * rows.size());
+
+    // ---- likelihood phases ----------------------------------------------------------------------
+    CU(cudaEventRecord(h->ev[0], h->st));
+    launch_table(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), max_n, h->d_fx.p, h->d_fl.p, h->d_fr.p,
+                 h->d_fpa.p, h->d_theta.p, h->d_table.p, h->st);
+    CU(cudaEventRecord(h->ev[1], h->st));
+    launch_tensor(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), max_n, P.n_beta, maxwin, h->d_theta.p,
+                  h->d_table.p, h->d_tensor.p, h->st);
+    CU(cudaEventRecord(h->ev[2], h->st));
+    CU(cudaGetLastError());
+    h->tm.launches += 2;
+    for (size_t i = 0; i < W; i++) {
+      // exp() evaluations = N * sum over (t, beta) of the clipped window sizes (regular grid)
+      const UtrDev& d = ud[i];
+      double win = 0;
+      for (int j = 0; j < P.n_beta; j++) {
+        const int half = int(std::floor(3 * P.betas[j] / P.theta_step));
+        for (int t = 0; t < d.T; t++) win += std::min(d.T - 1, t + half) - std::max(0, t - half) + 1;
+      }
+      h->tm.tensor_exp += double(d.N) * win;
+    }
+    bool timed_lik = false;
+
+    // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
+    for (;;) {
+      std::vector<ChainDev> chains;
+      std::vector<size_t> owner;       // wave index of each chain
+      double tr0 = now_ms();
+      for (size_t i = 0; i < W; i++) {
+        WaveUtr& w = wave[i];
+        if (w.done) continue;
+        const UtrPrep& p = prep[size_t(w.u)];
+        NpRandomState& g = rng[size_t(stream_of[size_t(w.u)])];
+        const size_t first_chain = chains.size();
+        for (int K = w.k_max; K >= w.k_min && !w.done; K--)
+          for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++) {
+            ChainInit ci;
+            int32_t rc = draw_chain(g, P, p, K, ci);
+            if (rc != kOk) {       // numpy's choice() would have raised inside the reference
+              out->status[w.u] = rc;
+              w.done = true;
+              chains.resize(first_chain);
+              owner.resize(first_chain);
+              break;
+            }
+            ChainDev c;
+            memset(&c, 0, sizeof(c));
+            c.utr = int32_t(i); c.K = K; c.weights_only = 0;
+            memcpy(c.a_idx, ci.a_idx, sizeof(ci.a_idx));
+            memcpy(c.b_idx, ci.b_idx, sizeof(ci.b_idx));
+            memcpy(c.ws, ci.ws, sizeof(ci.ws));
+            memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
+            chains.push_back(c);
+            owner.push_back(i);
+          }
+      }
+      h->tm.host_rng_ms += now_ms() - tr0;
+      if (chains.empty()) break;
+      if (int rc = run_chains(h, chains, ud)) return rc;
+      if (!timed_lik) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+        CU(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+        h->tm.table_ms += a;
+        h->tm.tensor_ms += b;
+        timed_lik = true;
+      }
+      // ---- selection (em_optim0 :865, run :972) + pruning (rm_component :832-844) -----------------
+      std::vector<ChainDev> refits;
+      std::vector<size_t> refit_owner;
+      tr0 = now_ms();
+      size_t pos = 0;
+      for (size_t i = 0; i < W; i++) {
+        WaveUtr& w = wave[i];
+        if (w.done) continue;
+        const int nK = w.k_max - w.k_min + 1;
+        std::vector<double> bic_k(static_cast<size_t>(nK));
+        std::vector<size_t> best_k(static_cast<size_t>(nK));
+        for (int ik = 0; ik < nK; ik++) {
+          std::vector<double> b(SCAPE_B200_NTRIAL);
+          for (int t = 0; t < SCAPE_B200_NTRIAL; t++) {
+            const ChainDev& c = chains[pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(t)];
+            b[size_t(t)] = c.bic;
+            w.work += double(c.n_iter) * ud[i].N * (c.K + 1);
+            w.iters += c.n_iter;
+          }
+          int m = np_argmin(b);
+          best_k[size_t(ik)] = pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(m);
+          bic_k[size_t(ik)] = b[size_t(m)];
+        }
+        pos += size_t(nK) * SCAPE_B200_NTRIAL;
+        w.chains_run += nK * SCAPE_B200_NTRIAL;
+        w.sweeps++;
+        w.best = chains[best_k[size_t(np_argmin(bic_k))]];
+        w.k_selected = w.best.K;
+        if (!P.fixed_run_mode) {
+          int keep[SCAPE_B200_KCAP], nk = 0;
+          for (int k = 0; k < w.best.K; k++)
+            if (!(w.best.ws[k] < P.min_ws)) keep[nk++] = k;
+          if (nk < w.best.K) {
+            ChainDev c;
+            memset(&c, 0, sizeof(c));
+            c.utr = int32_t(i); c.K = nk; c.weights_only = 1;
+            for (int k = 0; k < nk; k++) { c.a_idx[k] = w.best.a_idx[keep[k]]; c.b_idx[k] = w.best.b_idx[keep[k]]; }
+            ChainInit ci;
+            ci.K = nk;
+            draw_refit(rng[size_t(stream_of[size_t(w.u)])], P, ci);
+            memcpy(c.ws, ci.ws, sizeof(ci.ws));
+            memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
+            refits.push_back(c);
+            refit_owner.push_back(i);
+          }
+        }
+      }
+      h->tm.host_rng_ms += now_ms() - tr0;
+      if (int rc = run_chains(h, refits, ud)) return rc;
+      for (size_t j = 0; j < refits.size(); j++) {
+        WaveUtr& w = wave[refit_owner[j]];
+        w.best = refits[j];
+        w.chains_run += 1;
+        w.work += double(refits[j].n_iter) * ud[refit_owner[j]].N * (refits[j].K + 1);
+        w.iters += refits[j].n_iter;
+      }
+      bool again = false;
+      for (size_t i = 0; i < W; i++) {
+        WaveUtr& w = wave[i];
+        if (w.done) continue;
+        if (!P.fixed_run_mode && P.re_run_mode && w.best.K == w.k_max) {
+          if (w.k_max + 2 > SCAPE_B200_KCAP) {
+            out->status[w.u] = kErrKcap;
+            w.done = true;
+          } else {
+            w.k_min = w.k_max;
+            w.k_max += 2;
+            again = true;
+          }
+        } else {
+          w.done = true;
+        }
+      }
+      if (!again) break;
+    }
+
+    // ---- labels (get_label :873-881) + per-read expansion (:976) --------------------------------
+    std::vector<LabelDev> jobs(W);
+    int64_t nl = 0;
+    for (size_t i = 0; i < W; i++) {
+      LabelDev& j = jobs[i];
+      memset(&j, 0, sizeof(j));
+      j.utr = int32_t(i); j.K = wave[i].best.K; j.out_off = nl;
+      memcpy(j.a_idx, wave[i].best.a_idx, sizeof(j.a_idx));
+      memcpy(j.b_idx, wave[i].best.b_idx, sizeof(j.b_idx));
+      memcpy(j.ws, wave[i].best.ws, sizeof(j.ws));
+      nl += ud[i].N;
+    }
+    CU(h->d_jobs.ensure(W));
+    CU(h->d_labels.ensure(size_t(nl)));
+    CU(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), sizeof(LabelDev) * W, cudaMemcpyHostToDevice, h->st));
+    CU(cudaEventRecord(h->ev[6], h->st));
+    launch_labels(h->d_jobs.p, int64_t(W), max_n, h->d_utrs.p, h->d_tensor.p, h->d_cnt.p, h->d_labels.p, h->st);
+    CU(cudaEventRecord(h->ev[7], h->st));
+    CU(cudaGetLastError());
+    h->tm.launches += 1;
+    std::vector<int32_t> lab(static_cast<size_t>(nl));
+    CU(cudaMemcpyAsync(lab.data(), h->d_labels.p, sizeof(int32_t) * size_t(nl), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->tm.h2d_bytes += double(sizeof(LabelDev) * W);
+    h->tm.d2h_bytes += double(sizeof(int32_t) * size_t(nl));
+    {
+      float a = 0;
+      CU(cudaEventElapsedTime(&a, h->ev[6], h->ev[7]));
+      h->tm.label_ms += a;
+    }
+    for (size_t i = 0; i < W; i++) {
+      const WaveUtr& w = wave[i];
+      const UtrPrep& p = prep[size_t(w.u)];
+      const int64_t u = w.u;
+      const ChainDev& c = w.best;
+      out->K[u] = c.K;
+      for (int k = 0; k < c.K; k++) {
+        out->alpha[u * SCAPE_B200_KCAP + k] = std::nearbyint(p.theta[size_t(c.a_idx[k])]);   // np.rint (:770)
+        out->beta[u * SCAPE_B200_KCAP + k] = p.betas[size_t(c.b_idx[k])];
+      }
+      for (int k = 0; k <= c.K; k++) out->ws[u * (SCAPE_B200_KCAP + 1) + k] = c.ws[k];
+      out->bic[u] = c.bic;
+      out->n_lb[u] = c.n_iter;
+      for (int k = 0; k < c.n_iter; k++) out->lb_arr[u * SCAPE_B200_NROUND + k] = c.lb_arr[k];
+      out->path[u * 4 + 0] = w.sweeps; out->path[u * 4 + 1] = w.k_selected;
+      out->path[u * 4 + 2] = c.K; out->path[u * 4 + 3] = w.chains_run;
+      out->em_work[u * 2] = w.work; out->em_work[u * 2 + 1] = w.iters;
+      const int32_t* lb = lab.data() + jobs[i].out_off;
+      int64_t* dst = out->label + bt->read_off[u];
+      for (int64_t r = 0; r < p.n_reads; r++) dst[r] = lb[p.read_to_bin[size_t(r)]];
+    }
+  }
+  if (bt->stream_state)
+    for (int s = 0; s < S; s++) {
+      memcpy(bt->stream_state + size_t(s) * 625, rng[size_t(s)].key, 624 * sizeof(uint32_t));
+      bt->stream_state[size_t(s) * 625 + 624] = uint32_t(rng[size_t(s)].pos);
+    }
+  h->tm.total_ms = now_ms() - t_begin;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-seam entry points for the parity tests
+// ------------------------------------------------------------------------------------------------
+extern "C" int scape_b200_loglik_table(scape_b200_handle* h, int64_t n_frag, const double* x, const double* l,
+                                       const double* r, const double* pa, int64_t n_theta, const double* theta,
+                                       double* table_out) {
+  if (!h) return fail(-5, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(upload_model_const(h->mc));
+  UtrDev d;
+  memset(&d, 0, sizeof(d));
+  d.N = int32_t(n_frag); d.Npad = pad4(n_frag); d.T = int32_t(n_theta); d.B = h->P.n_beta;
+  std::vector<RowRef> rows;
+  for (int t = 0; t < d.T; t++) rows.push_back({0, t});
+  const size_t np_ = size_t(d.Npad);
+  std::vector<double> px(np_, 0.0), pl(np_, 0.0), pr(np_, 0.0), ppa(np_, 0.0);
+  std::copy(x, x + n_frag, px.begin()); std::copy(l, l + n_frag, pl.begin());
+  std::copy(r, r + n_frag, pr.begin()); std::copy(pa, pa + n_frag, ppa.begin());
+  CU(h->d_fx.ensure(np_)); CU(h->d_fl.ensure(np_)); CU(h->d_fr.ensure(np_)); CU(h->d_fpa.ensure(np_));
+  CU(h->d_theta.ensure(size_t(n_theta))); CU(h->d_table.ensure(size_t(n_theta) * np_));
+  CU(h->d_utrs.ensure(1)); CU(h->d_rows.ensure(rows.size()));
+  CU(cudaMemcpyAsync(h->d_fx.p, px.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_fl.p, pl.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_fr.p, pr.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_fpa.p, ppa.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_theta.p, theta, 8 * size_t(n_theta), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, h->st));
+  launch_table(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), d.Npad, h->d_fx.p, h->d_fl.p, h->d_fr.p, h->d_fpa.p,
+               h->d_theta.p, h->d_table.p, h->st);
+  CU(cudaGetLastError());
+  std::vector<double> tt(size_t(n_theta) * np_);
+  CU(cudaMemcpyAsync(tt.data(), h->d_table.p, 8 * tt.size(), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int64_t n = 0; n < n_frag; n++)
+    for (int64_t t = 0; t < n_theta; t++) table_out[n * n_theta + t] = tt[size_t(t) * np_ + size_t(n)];
+  return 0;
+}
+
+extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, int64_t n_theta, const double* theta,
+                                          int64_t n_beta, const double* betas, const double* table,
+                                          double* tensor_out) {
+  if (!h) return fail(-5, "null handle");
+  if (n_beta > SCAPE_B200_MAX_BETA) return fail(-5, "n_beta too large");
+  CU(cudaSetDevice(h->device));
+  ModelConst mc = h->mc;
+  mc.n_beta = int32_t(n_beta);
+  double bmax = 0;
+  for (int i = 0; i < n_beta; i++) { mc.betas[i] = betas[i]; bmax = std::max(bmax, betas[i]); }
+  CU(upload_model_const(mc));
+  // widest window for an arbitrary sorted theta list
+  int maxwin = 1;
+  for (int64_t i = 0; i < n_theta; i++) {
+    const double* lo = std::lower_bound(theta, theta + n_theta, theta[i] - 3 * bmax);
+    const double* hi = std::upper_bound(theta, theta + n_theta, theta[i] + 3 * bmax);
+    maxwin = std::max(maxwin, int(hi - lo));
+  }
+  UtrDev d;
+  memset(&d, 0, sizeof(d));
+  d.N = int32_t(n_frag); d.Npad = pad4(n_frag); d.T = int32_t(n_theta); d.B = int32_t(n_beta);
+  const size_t np_ = size_t(d.Npad);
+  std::vector<RowRef> rows;
+  for (int t = 0; t < d.T; t++) rows.push_back({0, t});
+  std::vector<double> tt(size_t(n_theta) * np_, 0.0);
+  for (int64_t n = 0; n < n_frag; n++)
+    for (int64_t t = 0; t < n_theta; t++) tt[size_t(t) * np_ + size_t(n)] = table[n * n_theta + t];
+  CU(h->d_theta.ensure(size_t(n_theta))); CU(h->d_table.ensure(tt.size()));
+  CU(h->d_tensor.ensure(size_t(n_theta) * size_t(n_beta) * np_));
+  CU(h->d_utrs.ensure(1)); CU(h->d_rows.ensure(rows.size()));
+  CU(cudaMemcpyAsync(h->d_theta.p, theta, 8 * size_t(n_theta), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_table.p, tt.data(), 8 * tt.size(), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, h->st));
+  launch_tensor(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), d.Npad, int(n_beta), maxwin, h->d_theta.p,
+                h->d_table.p, h->d_tensor.p, h->st);
+  CU(cudaGetLastError());
+  std::vector<double> ten(size_t(n_theta) * size_t(n_beta) * np_);
+  CU(cudaMemcpyAsync(ten.data(), h->d_tensor.p, 8 * ten.size(), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int64_t tb = 0; tb < n_theta * n_beta; tb++)
+    memcpy(tensor_out + tb * n_frag, ten.data() + size_t(tb) * np_, 8 * size_t(n_frag));
+  CU(upload_model_const(h->mc));
+  return 0;
+}
+
+extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_t n_theta, int64_t n_beta,
+                                    const double* tensor, const double* cnt, double unif_loglik, int64_t n_chains,
+                                    scape_b200_chain_io* io, int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
+  if (!h) return fail(-5, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(upload_model_const(h->mc));
+  UtrDev d;
+  memset(&d, 0, sizeof(d));
+  d.N = int32_t(n_frag); d.Npad = pad4(n_frag); d.T = int32_t(n_theta); d.B = int32_t(n_beta);
+  d.unif_loglik = unif_loglik;
+  const size_t np_ = size_t(d.Npad);
+  std::vector<double> ten(size_t(n_theta) * size_t(n_beta) * np_, 0.0), pc(np_, 0.0);
+  for (int64_t tb = 0; tb < n_theta * n_beta; tb++)
+    memcpy(ten.data() + size_t(tb) * np_, tensor + tb * n_frag, 8 * size_t(n_frag));
+  std::copy(cnt, cnt + n_frag, pc.begin());
+  CU(h->d_tensor.ensure(ten.size())); CU(h->d_cnt.ensure(np_)); CU(h->d_utrs.ensure(1));
+  CU(cudaMemcpyAsync(h->d_tensor.p, ten.data(), 8 * ten.size(), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_cnt.p, pc.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
+  std::vector<UtrDev> ud(1, d);
+  std::vector<ChainDev> chains(static_cast<size_t>(n_chains));
+  for (int64_t i = 0; i < n_chains; i++) {
+    ChainDev& c = chains[size_t(i)];
+    memset(&c, 0, sizeof(c));
+    if (io[i].K < 1 || io[i].K > SCAPE_B200_KCAP) return fail(-5, "chain K out of range");
+    c.utr = 0; c.K = io[i].K; c.weights_only = io[i].weights_only;
+    memcpy(c.a_idx, io[i].a_idx, sizeof(c.a_idx));
+    memcpy(c.b_idx, io[i].b_idx, sizeof(c.b_idx));
+    memcpy(c.ws, io[i].ws, sizeof(c.ws));
+    memcpy(c.k_order, io[i].k_order, SCAPE_B200_NROUND);
+  }
+  const bool want_trace = trace_a && trace_b && trace_ws;
+  if (int rc = run_chains(h, chains, ud, want_trace)) return rc;
+  for (int64_t i = 0; i < n_chains; i++) {
+    const ChainDev& c = chains[size_t(i)];
+    memcpy(io[i].a_idx, c.a_idx, sizeof(c.a_idx));
+    memcpy(io[i].b_idx, c.b_idx, sizeof(c.b_idx));
+    memcpy(io[i].ws, c.ws, sizeof(c.ws));
+    io[i].n_iter = c.n_iter;
+    io[i].bic = c.bic;
+    memcpy(io[i].lb_arr, c.lb_arr, sizeof(c.lb_arr));
+  }
+  if (want_trace) {
+    const size_t tr = size_t(n_chains) * SCAPE_B200_NROUND * (SCAPE_B200_KCAP + 1);
+    CU(cudaMemcpy(trace_a, h->d_trace_a.p, 4 * tr, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(trace_b, h->d_trace_b.p, 4 * tr, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(trace_ws, h->d_trace_ws.p, 8 * tr, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host pre-pass entry points (CPU only)
+// ------------------------------------------------------------------------------------------------
+extern "C" int scape_b200_bin_reads(int64_t n_reads, const double* x, const double* l, const double* r,
+                                    const double* pa, double* bx, double* bl, double* br, double* bpa, double* cnt,
+                                    int32_t* read_to_bin, int64_t* n_bins) {
+  UtrPrep p;
+  int32_t rc = bin_reads(x, l, r, pa, n_reads, p);
+  if (rc != kOk) return fail(rc, "bin_reads failed");
+  *n_bins = p.n();
+  std::copy(p.x.begin(), p.x.end(), bx); std::copy(p.l.begin(), p.l.end(), bl);
+  std::copy(p.r.begin(), p.r.end(), br); std::copy(p.pa.begin(), p.pa.end(), bpa);
+  std::copy(p.cnt.begin(), p.cnt.end(), cnt);
+  std::copy(p.read_to_bin.begin(), p.read_to_bin.end(), read_to_bin);
+  return 0;
+}
+
+static int prep_one(const scape_b200_params* P, int64_t n, const double* x, const double* l, const double* r,
+                    const double* pa, UtrPrep& p) {
+  if (int rc = check_params(*P)) return rc;
+  if (bin_reads(x, l, r, pa, n, p) != kOk) return fail(p.status, "bin_reads failed");
+  if (setup_model(*P, x, l, n, p) != kOk) return fail(p.status, "model set-up failed (reference would raise)");
+  coverage_and_peaks(*P, p);
+  return 0;
+}
+
+extern "C" int scape_b200_profile(const scape_b200_params* P, int64_t n_reads, const double* x, const double* l,
+                                  const double* r, const double* pa, int64_t* L_out, int64_t* n_theta,
+                                  double* theta, double* prof_y, int64_t* n_peaks, int64_t* peak_idx,
+                                  double* peak_w, int64_t cap) {
+  UtrPrep p;
+  if (int rc = prep_one(P, n_reads, x, l, r, pa, p)) return rc;
+  *L_out = p.L;
+  *n_theta = p.T();
+  *n_peaks = int64_t(p.peak_idx.size());
+  if (!prof_y) return 0;
+  if (cap < p.L + 200 || cap < p.T()) return fail(-5, "output capacity too small");
+  std::copy(p.theta.begin(), p.theta.end(), theta);
+  std::copy(p.prof_y.begin(), p.prof_y.end(), prof_y);
+  std::copy(p.peak_idx.begin(), p.peak_idx.end(), peak_idx);
+  std::copy(p.peak_w.begin(), p.peak_w.end(), peak_w);
+  return 0;
+}
+
+extern "C" int scape_b200_draw_chains(const scape_b200_params* P, int64_t n_reads, const double* x, const double* l,
+                                      const double* r, const double* pa, uint32_t seed, int64_t n_chains,
+                                      const int32_t* ks, scape_b200_chain_io* out) {
+  UtrPrep p;
+  if (int rc = prep_one(P, n_reads, x, l, r, pa, p)) return rc;
+  NpRandomState g(seed);
+  for (int64_t i = 0; i < n_chains; i++) {
+    ChainInit ci;
+    if (ks[i] < 0) {           // negative K: a prune refit draw (init_ws + gen_k_arr only)
+      ci.K = -ks[i];
+      draw_refit(g, *P, ci);
+    } else {
+      int32_t rc = draw_chain(g, *P, p, ks[i], ci);
+      if (rc != kOk) return fail(rc, "draw_chain failed");
+    }
+    memset(&out[i], 0, sizeof(out[i]));
+    out[i].K = ci.K;
+    memcpy(out[i].a_idx, ci.a_idx, sizeof(ci.a_idx));
+    memcpy(out[i].b_idx, ci.b_idx, sizeof(ci.b_idx));
+    memcpy(out[i].ws, ci.ws, sizeof(ci.ws));
+    memcpy(out[i].k_order, ci.k_order, SCAPE_B200_NROUND);
+  }
+  return 0;
+}
+
+extern "C" int scape_b200_set_argsort_callback(scape_b200_argsort_fn fn) {
+  argsort_callback() = fn;
+  return 0;
+}
+
+extern "C" int scape_b200_rng_draw(uint32_t seed, int kind, int64_t arg, int64_t n, double* out) {
+  NpRandomState g(seed);
+  if (kind == 0) {
+    for (int64_t i = 0; i < n; i++) out[i] = g.next_double();
+  } else if (kind == 1) {
+    for (int64_t i = 0; i < n; i++) out[i] = double(g.randint_below(arg));
+  } else if (kind == 2) {
+    std::vector<int64_t> p;
+    g.permutation(arg, p);
+    for (int64_t i = 0; i < n && i < arg; i++) out[i] = double(p[size_t(i)]);
+  } else {
+    return fail(-5, "unknown kind");
+  }
+  return 0;
+}

@@ -54,6 +54,17 @@ inline double np_pairwise_sum(const double* a, int64_t n) {
   return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
 }
 
+// np.argsort(priority) as the *installed numpy* does it.  scipy's _select_by_peak_distance ranks
+// peaks with an unstable np.argsort, whose order among exactly equal heights depends on the
+// numpy build / CPU dispatch (AVX-512 sorting networks on this image).  Equal heights are common
+// (isolated noise reads of equal length give identical bumps), so when -- and only when -- two
+// candidate peaks tie, the host binding is asked for the order.  Without a callback: stable sort.
+typedef void (*argsort_fn)(const double* values, int64_t n, int64_t* order_out);
+inline argsort_fn& argsort_callback() {
+  static argsort_fn fn = nullptr;
+  return fn;
+}
+
 struct UtrPrep {
   int32_t status = kOk;
   int64_t n_reads = 0;
@@ -223,6 +234,14 @@ inline void coverage_and_peaks(const scape_b200_params& P, UtrPrep& u) {
   for (size_t i = 0; i < order.size(); i++) order[i] = int64_t(i);
   std::stable_sort(order.begin(), order.end(),
                    [&](int64_t a, int64_t b) { return s[size_t(cand[size_t(a)])] < s[size_t(cand[size_t(b)])]; });
+  bool tie = false;
+  for (size_t i = 1; i < order.size() && !tie; i++)
+    tie = s[size_t(cand[size_t(order[i])])] == s[size_t(cand[size_t(order[i - 1])])];
+  if (tie && argsort_callback()) {
+    std::vector<double> pri(cand.size());
+    for (size_t i = 0; i < cand.size(); i++) pri[i] = s[size_t(cand[i])];
+    argsort_callback()(pri.data(), int64_t(pri.size()), order.data());
+  }
   std::vector<char> keep(cand.size(), 1);
   for (int64_t i = int64_t(order.size()) - 1; i >= 0; i--) {
     int64_t j = order[size_t(i)];
