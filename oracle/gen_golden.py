@@ -16,7 +16,7 @@ Cases (every one is `np.random.seed(1)` once per chunk, like `_infer_pa`, apa_co
   toy, chr17, chr19    shipped chunks, default TOML            (cfg-1 of BASELINE.json)
   synth8               synthetic UTRs 0..7 x 300 reads          (serial RNG stream with prunes)
   synth_rerun          UTRs 0, 22, 31 with n_max_apa=3          (re-run loop, apa_core.py:1023-1030)
-  synth_fixed          UTRs 3, 6, 8 with pre_para = result of UTR 3   (fixed_run, apa_core.py:883-928)
+  synth_fixed          UTRs 3, 6, 15 with pre_para = result of UTR 3   (fixed_run, apa_core.py:883-928)
 """
 from __future__ import annotations
 
@@ -46,7 +46,7 @@ EXAMPLES = {
 SYNTH_CASES = {
     "synth8": dict(utrs=list(range(8)), reads=300, params={}),
     "synth_rerun": dict(utrs=[0, 22, 31], reads=300, params={"n_max_apa": 3}),
-    "synth_fixed": dict(utrs=[3, 6, 8], reads=300, params={}, fixed_from=3),
+    "synth_fixed": dict(utrs=[3, 6, 15], reads=300, params={}, fixed_from=3),
 }
 
 
@@ -88,8 +88,19 @@ def main():
     sys.modules.setdefault("scape", sys.modules["scape_ref"])          # shipped pickles name scape.apa_core
     sys.modules.setdefault("scape.apa_core", ref)
     results, labels, inputs = {}, {}, {}
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:   # refresh selected cases, keep the rest of the committed fixtures
+        with open(os.path.join(GOLD, "reference_results.json")) as fh:
+            results = json.load(fh)["cases"]
+        labels = dict(np.load(os.path.join(GOLD, "reference_labels.npz")))
+        inputs = dict(np.load(os.path.join(GOLD, "example_inputs.npz")))
+        for name in only:
+            for k in [k for k in labels if k.startswith(name + "/")]:
+                del labels[k]
 
     for name, pat in EXAMPLES.items():
+        if only and name not in only:
+            continue
         chunk = _load_stream(pat.format("input", "input"))
         shipped = _load_stream(pat.format("output", "res"))
         t0 = time.time()
@@ -111,6 +122,8 @@ def main():
             labels[key] = np.asarray(r.label_arr, dtype=np.int8)
 
     for name, spec in SYNTH_CASES.items():
+        if only and name not in only:
+            continue
         utrs = [synth.make_utr(u, spec["reads"]) for u in spec["utrs"]]
         chunk = [(u.gene_info_str, synth.to_dataframe(u)) for u in utrs]
         pre_file = None

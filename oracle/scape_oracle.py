@@ -147,6 +147,18 @@ def loglik_marginal_lxr(alpha, beta, all_theta, table):
     return _lse_rows(table[:, lo:hi + 1] + logp[None, :] - logp_sum)
 
 
+def loglik_marginal_lxr_scipy(alpha, beta, all_theta, table):
+    """The numpy/scipy variant fixed_run uses instead of the Taichi kernel (apa_core.py:642-651):
+    same window and the same mathematics, rounded by scipy's logpdf / logsumexp."""
+    from scipy.special import logsumexp
+    sel = np.where(np.logical_and(all_theta >= alpha - 3 * beta, all_theta <= alpha + 3 * beta))[0]
+    logp = _sp_stats.norm(loc=alpha, scale=beta).logpdf(all_theta[sel])
+    res = np.zeros((table.shape[0], len(sel))) + SENTINEL
+    for i, t in enumerate(sel):
+        res[:, i] = table[:, t] + logp[i]
+    return logsumexp(res, axis=1) - logsumexp(logp)
+
+
 def get_loglik_marginal_tensor(all_theta, predef_beta_arr, table):
     """tensor[i, j, n] (taichi_core.py:237-246)."""
     out = np.empty((len(all_theta), len(predef_beta_arr), table.shape[0]))
@@ -492,8 +504,8 @@ def run_chain(m: UtrModel, ch: Chain, rng, weights_only: bool = False) -> Chain:
 
 def best_of_restarts(m: UtrModel, k: int, rng) -> Chain:
     """em_optim0 (apa_core.py:846-871): 10 restarts, first arg-min BIC."""
-    bic = np.full(N_TRIAL, POS_SENTINEL)
-    runs = []
+    bic = np.full(N_TRIAL, np.finfo("f").max)   # NB float32 array (:427, :849): BICs are compared after
+    runs = []                                    # rounding to float32, first of the tied minima wins
     for i in range(N_TRIAL):
         runs.append(run_chain(m, draw_chain(m, k, rng), rng))
         bic[i] = runs[i].bic
@@ -560,7 +572,10 @@ def _sweep(m: UtrModel, k_max: int, k_min: int, rng) -> Chain:
         raise Exception("max_beta has to be greater than beta_step_size!")
     ks = list(range(k_max, k_min - 1, -1))
     best = [best_of_restarts(m, k, rng) for k in ks]
-    pick = best[int(np.argmin(np.array([c.bic for c in best])))]
+    bic_k = np.full(len(ks), np.finfo("f").max)  # float32 again (:945)
+    for i, c in enumerate(best):
+        bic_k[i] = c.bic
+    pick = best[int(np.argmin(bic_k))]
     k_sel = pick.K
     out = prune_and_refit(m, pick, rng)
     m.path.append((k_max, k_sel, out.K))
@@ -617,7 +632,10 @@ def fit_utr_fixed(x, l, r, pa, rng, pre_alpha, pre_beta, pre_L, trace=None, **pa
     m.table = theta_table(m, m.theta)
     m.prof_x, m.prof_y = coverage_profile(m)
     m.peak_idx, m.peak_w = find_profile_peaks(m)
-    m.tensor = get_loglik_marginal_tensor(m.theta, m.betas, m.table)    # same maths as :642-651
+    m.tensor = np.zeros((len(m.theta), len(m.betas), m.n))              # :910-914
+    for i, a in enumerate(m.theta):
+        for j, b in enumerate(m.betas):
+            m.tensor[i][j] = loglik_marginal_lxr_scipy(a, b, m.theta, m.table)
     ch = best_of_restarts(m, len(pre_alpha), rng)                       # :920
     res = _finish(m, ch, "Final Result (subsample run)")
     res.chains_run = N_TRIAL

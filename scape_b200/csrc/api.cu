@@ -196,11 +196,14 @@ struct WaveUtr {
   double work = 0, iters = 0;
 };
 
+// np.argmin over the reference's bic_arr.  That array is created with np.full(n, np.finfo('f').max)
+// (apa_core.py:427, 849, 945) and is therefore FLOAT32: BICs are compared after rounding to float32
+// and the first of the tied minima wins.
 int np_argmin(const std::vector<double>& v) {
   int best = 0;
   for (int i = 0; i < (int)v.size(); i++) {
     if (std::isnan(v[size_t(i)])) return i;
-    if (v[size_t(i)] < v[size_t(best)]) best = i;
+    if (float(v[size_t(i)]) < float(v[size_t(best)])) best = i;
   }
   return best;
 }

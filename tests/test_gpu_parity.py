@@ -1,0 +1,223 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference goldens.
+Run on the B200 box: python -m pytest tests -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import scape_oracle as so
+from scape_b200 import _lib, synth
+from scape_b200.apa_core import fit_chunks
+from _helpers import check_against_golden, golden_chunk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    assert _lib.load().scape_b200_device_count() > 0, "no CUDA device: the gpu tests cannot fall back to anything"
+    with _lib.Engine(_lib.make_params()) as e:
+        yield e
+
+
+def _model(u, with_tensor=True):
+    prm = dict(so.DEFAULTS)
+    prm["utr_length"] = so.resolve_utr_length(u.x, u.l, prm)
+    m = so.build_model(u.x, u.l, u.r, u.pa, prm)
+    m.unif_loglik = so.uniform_loglik(m)
+    m.table = so.theta_table(m, m.theta)
+    if with_tensor:
+        m.tensor = so.get_loglik_marginal_tensor(m.theta, m.betas, m.table)
+    return m
+
+
+def _rel_err_on_finite(got, want):
+    fin = want > -1e30
+    assert np.array_equal(fin, got > -1e30), "sentinel pattern differs"
+    assert np.all(got[~fin] == so.SENTINEL)
+    return float(np.max(np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)))
+
+
+# ---- gate (i): element-wise table / tensor ---------------------------------------------------------
+@pytest.mark.parametrize("ui,reads", [(0, 300), (7, 60), (22, 1500)])
+def test_theta_table_and_marginal_tensor(engine, ui, reads):
+    m = _model(synth.make_utr(ui, reads))
+    tab = engine.loglik_table(m.x, m.l, m.r, m.pa, m.theta)
+    assert _rel_err_on_finite(tab, m.table) < 1e-12
+    ten = engine.marginal_tensor(m.theta, m.betas, m.table)
+    assert _rel_err_on_finite(ten, m.tensor) < 1e-12
+
+
+def test_theta_table_with_known_polya_lengths(engine):
+    """r_known reads (taichi_core.py:111-132) never occur in 10x data; cover the kernel branch anyway,
+    including r above every s (mass = 0 -> +inf like the reference's log(0))."""
+    rng = np.random.default_rng(11)
+    n = 120
+    x = rng.integers(0, 1500, n).astype(float)
+    l = rng.integers(20, 133, n).astype(float)
+    r = np.where(rng.random(n) < 0.6, rng.integers(5, 139, n), np.nan).astype(float)
+    pa = np.where(np.isnan(r) & (rng.random(n) < 0.3), x + l - 1, np.nan)
+    theta = np.arange(20.0, 2000.0, 9.0)
+    s_dis = np.arange(20, 150, 10)
+    pmf = np.repeat(1 / 13, 13); pmf = pmf / sum(pmf)
+    want = np.zeros((n, len(theta)))
+    kn, un, pj = ~np.isnan(r) & np.isnan(pa), np.isnan(r) & np.isnan(pa), ~np.isnan(pa)
+    for t, th in enumerate(theta):
+        want[kn, t] = so.loglik_xlr_t_r_known(x[kn], l[kn], r[kn], s_dis, pmf, th, 300, 50)
+        want[un, t] = so.loglik_xlr_t_r_unknown(x[un], l[un], r[un], s_dis, pmf, th, 300, 50)
+        want[pj, t] = so.loglik_xlr_t_pa(x[pj], l[pj], pa[pj], th, 50)
+    got = engine.loglik_table(x, l, r, pa, theta)
+    assert _rel_err_on_finite(got, want) < 1e-12
+
+
+def test_marginal_tensor_on_irregular_fixed_mode_grid(engine):
+    m = _model(synth.make_utr(3, 300), with_tensor=False)
+    keep = np.r_[10:60, 100:131, 180:200]
+    theta = m.theta[keep]
+    betas = np.array([45.0, 50.0, 55.0, 60.0])
+    table = np.ascontiguousarray(m.table[:, keep])
+    want = so.get_loglik_marginal_tensor(theta, betas, table)
+    got = engine.marginal_tensor(theta, betas, table)
+    assert _rel_err_on_finite(got, want) < 1e-12
+
+
+# ---- gate (ii): per-chain traces from identical init blobs -------------------------------------------
+@pytest.mark.parametrize("ui,reads", [(0, 300), (31, 300), (22, 3000)])
+def test_em_chain_traces(engine, ui, reads):
+    u = synth.make_utr(ui, reads)
+    m = _model(u)
+    m.prof_x, m.prof_y = so.coverage_profile(m)
+    m.peak_idx, m.peak_w = so.find_profile_peaks(m)
+    rng = np.random.RandomState(3)
+    inits, want = [], []
+    for K in (7, 5, 4, 3, 2, 1):
+        for _ in range(2):
+            ch = so.draw_chain(m, K, rng)
+            init = dict(K=K, a_idx=ch.a_idx.copy(), b_idx=ch.b_idx.copy(), ws=ch.ws.copy())
+            m.trace = []
+            done = so.run_chain(m, ch, rng)
+            init["k_order"] = done.k_order
+            inits.append(init)
+            want.append((done, m.trace))
+    # one weights-only chain (fixed_inference, apa_core.py:708-711)
+    base = want[2][0]
+    slim = so.Chain(a_idx=base.a_idx[:3].copy(), b_idx=base.b_idx[:3].copy(), ws=so.draw_weights(m, 3, rng))
+    init = dict(K=3, a_idx=slim.a_idx.copy(), b_idx=slim.b_idx.copy(), ws=slim.ws.copy(), weights_only=1)
+    m.trace = []
+    done = so.run_chain(m, slim, rng, weights_only=True)
+    init["k_order"] = done.k_order
+    inits.append(init)
+    want.append((done, m.trace))
+
+    got, (ta, tb, tw) = engine.em_chains(m.tensor, m.cnt, m.unif_loglik, inits, trace=True)
+    for i, (io, (ref, tr)) in enumerate(zip(got, want)):
+        K = io.K
+        assert io.n_iter == len(ref.lb_arr), f"chain {i}: iteration count"
+        for j, step in enumerate(tr):
+            assert list(ta[i, j, :K]) == list(step["a_idx"]) and list(tb[i, j, :K]) == list(step["b_idx"])
+            assert np.allclose(tw[i, j, :K + 1], step["ws"], rtol=0, atol=1e-12)
+            assert abs(io.lb_arr[j] - step["lb"]) <= 1e-10 * abs(step["lb"])
+        assert abs(io.bic - ref.bic) <= 1e-10 * abs(ref.bic)
+        assert list(io.a_idx[:K]) == list(ref.a_idx) and list(io.b_idx[:K]) == list(ref.b_idx)
+
+
+# ---- gate (iii): whole-UTR results --------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["toy", "chr17", "chr19", "synth8", "synth_rerun"])
+def test_fit_matches_reference_goldens(golden, case):
+    spec = golden["cases"][case]
+    res = fit_chunks([golden_chunk(golden, case)], seeds=[1], **spec["params"])[0]
+    assert len(res) == len(spec["utrs"])
+    for i, r in enumerate(res):
+        check_against_golden(r, spec["utrs"][i], golden["labels"][f"{case}/{i}"], tight=True)
+
+
+def test_fixed_mode_matches_reference_goldens(golden, tmp_path):
+    import pickle
+    from scape.apa_core import Parameters
+    spec = golden["cases"]["synth_fixed"]
+    pp = spec["pre_para"]
+    pre = Parameters(alpha_arr=np.array(pp["alpha_arr"]), beta_arr=np.array(pp["beta_arr"]), ws=None, L=pp["L"])
+    f = tmp_path / "pre.pkl"
+    with open(f, "wb") as fh:
+        pickle.dump(pre, fh)
+    res = fit_chunks([golden_chunk(golden, "synth_fixed")], seeds=[1], fixed_run_mode=True,
+                     pre_para_pkl_file=str(f))[0]
+    for i, r in enumerate(res):
+        # the third UTR collapses both sites onto one grid point: a degenerate fit whose weight split
+        # is decided by rounding noise, so only the BASELINE.json tolerances are required there
+        check_against_golden(r, spec["utrs"][i], golden["labels"][f"synth_fixed/{i}"], tight=(i < 2))
+
+
+def test_many_streams_in_one_call_equal_one_call_per_file():
+    """Wave scheduling must not change results: 3 chunks fitted together == fitted one by one, and
+    equal to the oracle's per-file streams."""
+    chunks = [[synth.make_utr(100 + 4 * f + i, 200) for i in range(4)] for f in range(3)]
+    frames = [[(u.gene_info_str, synth.to_dataframe(u)) for u in c] for c in chunks]
+    together = fit_chunks(frames, seeds=[1, 1, 1])
+    for f, c in enumerate(chunks):
+        alone = fit_chunks([frames[f]], seeds=[1])[0]
+        rng = np.random.RandomState(1)
+        for u, a, b in zip(c, together[f], alone):
+            assert a.K == b.K and np.array_equal(a.alpha_arr, b.alpha_arr) and np.array_equal(a.ws, b.ws)
+            assert a.lb_arr == b.lb_arr and np.array_equal(a.label_arr, b.label_arr)
+            w = so.fit_utr(u.x, u.l, u.r, u.pa, rng)
+            assert a.K == w.K and np.array_equal(a.alpha_arr, w.alpha_arr)
+            assert np.allclose(a.beta_arr, w.beta_arr) and np.allclose(a.ws, w.ws, atol=1e-9)
+            assert abs(a.lb_arr[-1] - w.lb_arr[-1]) <= 1e-9 * abs(w.lb_arr[-1])
+            assert np.array_equal(a.label_arr, w.label_arr)
+
+
+def test_ragged_and_tiny_utrs():
+    """10-read UTRs up to a 30k-read one in the same wave (cfg-3's heavy tail), vs the oracle."""
+    sizes = [10, 13, 4000, 25, 30000, 101]
+    utrs = [synth.make_utr(500 + i, n, long_utr=(n >= 30000)) for i, n in enumerate(sizes)]
+    frames = [[(u.gene_info_str, synth.to_dataframe(u))] for u in utrs]      # one stream each
+    got = fit_chunks(frames, seeds=[1] * len(utrs))
+    for u, (g,) in zip(utrs, got):
+        w = so.fit_utr(u.x, u.l, u.r, u.pa, np.random.RandomState(1))
+        assert g.K == w.K and np.array_equal(g.alpha_arr, w.alpha_arr), (u.n_reads, g.alpha_arr, w.alpha_arr)
+        assert np.allclose(g.beta_arr, w.beta_arr) and np.allclose(g.ws, w.ws, atol=1e-6)
+        assert abs(g.lb_arr[-1] - w.lb_arr[-1]) <= 1e-6 * abs(w.lb_arr[-1])
+        assert np.mean(g.label_arr == w.label_arr) >= 0.999
+        assert len(g.label_arr) == u.n_reads and g.label_arr.dtype == np.int64
+
+
+def test_global_numpy_rng_is_consumed_like_the_reference():
+    """subsample_run / infer use np.random's global legacy stream (apa_core.py:125); afterwards the
+    stream must be where the reference would have left it."""
+    from scape.apa_core import subsample_run
+    u = synth.make_utr(3, 300)
+    np.random.seed(1)
+    res = subsample_run(data=synth.to_dataframe(u), gene_info_str=u.gene_info_str, n_max_apa=5)
+    after = np.random.get_state()
+    rng = np.random.RandomState(1)
+    want = so.fit_utr(u.x, u.l, u.r, u.pa, rng)
+    assert res.K == want.K and np.array_equal(res.alpha_arr, want.alpha_arr)
+    assert np.array_equal(after[1], rng.get_state()[1]) and after[2] == rng.get_state()[2]
+
+
+def test_cli_writes_reference_format_pickles(tmp_path, golden):
+    """`scape infer_pa` end to end: file naming, TOML, pickle stream of scape.apa_core.Parameters."""
+    import pickle
+    from click.testing import CliRunner
+    from scape.cli import cli
+    us = [synth.make_utr(i, 300) for i in range(3)]
+    paths = synth.write_chunk_files(us, str(tmp_path), per_file=100, stem="demo")
+    synth.write_default_toml(str(tmp_path))
+    r = CliRunner().invoke(cli, ["infer_pa", "--pkl_input_file", paths[0], "--output_dir", str(tmp_path)])
+    assert r.exception is None, r.output
+    out = tmp_path / "pkl_output" / "demo.100.1.1.res.pkl"
+    assert out.exists()
+    got = []
+    with open(out, "rb") as fh:
+        while True:
+            try:
+                got.append(pickle.load(fh))
+            except EOFError:
+                break
+    assert len(got) == 3
+    spec = golden["cases"]["synth8"]
+    for i, g in enumerate(got):
+        assert type(g).__module__ == "scape.apa_core" and type(g).__name__ == "Parameters"
+        assert g.gene_info_str == us[i].gene_info_str
+        assert np.array_equal(g.cb_id_arr, us[i].cb_id) and np.array_equal(g.readID_arr, us[i].read_id)
+        assert g.alpha_arr.dtype == np.int64 and g.label_arr.dtype == np.int64
+        check_against_golden(g, spec["utrs"][i], golden["labels"][f"synth8/{i}"], tight=True)

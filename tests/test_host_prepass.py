@@ -1,0 +1,90 @@
+"""libscape_b200's host pre-pass (no GPU): binning, coverage profile, peaks and the numpy-legacy
+RNG replay must be bit-identical to numpy / scipy / the oracle, because every later result depends
+on the initial draws (hard part #1)."""
+import numpy as np
+import pytest
+
+from oracle import scape_oracle as so
+from scape_b200 import _lib, synth
+
+
+@pytest.mark.parametrize("seed", [1, 7, 2**31 + 5])
+def test_mt19937_streams(seed):
+    rs = np.random.RandomState(seed)
+    assert np.array_equal(rs.random_sample(1500), _lib.rng_draw(seed, 0, 0, 1500))
+    rs = np.random.RandomState(seed)
+    assert np.array_equal(rs.randint(0, 13, size=700), _lib.rng_draw(seed, 1, 13, 700))
+    for n in (2, 5, 2000, 4370):
+        rs = np.random.RandomState(seed)
+        assert np.array_equal(rs.permutation(n), _lib.rng_draw(seed, 2, n, n))
+
+
+def _oracle_model(u, **kw):
+    prm = dict(so.DEFAULTS)
+    prm.update(kw)
+    prm["utr_length"] = so.resolve_utr_length(u.x, u.l, prm)
+    m = so.build_model(u.x, u.l, u.r, u.pa, prm)
+    m.prof_x, m.prof_y = so.coverage_profile(m)
+    m.peak_idx, m.peak_w = so.find_profile_peaks(m)
+    return m
+
+
+@pytest.mark.parametrize("ui,reads", [(0, 300), (1, 3000), (5, 40), (39, 300), (17, 12), (22, 20000)])
+def test_binning_profile_peaks(ui, reads):
+    u = synth.make_utr(ui, reads)
+    want = so.bin_reads(u.x, u.l, u.r, u.pa)
+    got = _lib.bin_reads(u.x, u.l, u.r, u.pa)
+    for i in range(4):
+        assert np.array_equal(want[i], got[i], equal_nan=True)
+    assert np.array_equal(want[4], got[4]) and np.array_equal(want[5], got[5])
+    m = _oracle_model(u)
+    pr = _lib.profile(_lib.make_params(), u.x, u.l, u.r, u.pa)
+    assert pr["L"] == m.L
+    assert np.array_equal(pr["theta"], m.theta)
+    assert np.array_equal(pr["prof_y"], m.prof_y)          # numpy pairwise-sum order reproduced
+    assert np.array_equal(pr["peak_idx"], m.peak_idx)      # incl. np.argsort tie order (UTR 39)
+    assert np.array_equal(pr["peak_w"], m.peak_w)
+
+
+def test_binning_with_polya_lengths_and_nan_columns():
+    rng = np.random.default_rng(3)
+    n = 400
+    x = rng.integers(0, 1500, n).astype(float)
+    l = rng.integers(20, 133, n).astype(float)
+    r = np.where(rng.random(n) < 0.5, rng.integers(5, 120, n), np.nan).astype(float)
+    pa = np.where(rng.random(n) < 0.1, x + l - 1, np.nan)
+    want = so.bin_reads(x, l, r, pa)
+    got = _lib.bin_reads(x, l, r, pa)
+    for i in range(4):
+        assert np.array_equal(want[i], got[i], equal_nan=True)
+    assert np.array_equal(want[5], got[5])
+
+
+@pytest.mark.parametrize("ui,reads", [(0, 300), (3, 300), (12, 60), (22, 2000)])
+def test_chain_initialisation_draws(ui, reads):
+    """init_para + gen_k_arr for a whole K sweep, a prune refit, and a re-run block, back to back
+    on one stream (apa_core.py:817-829, 720, 708-711)."""
+    u = synth.make_utr(ui, reads)
+    m = _oracle_model(u)
+    ks = [5] * 10 + [4] * 10 + [3] * 10 + [2] * 10 + [1] * 10 + [-3] + [7] * 3 + [6] * 2 + [12]
+    got = _lib.draw_chains(_lib.make_params(), u.x, u.l, u.r, u.pa, 1, ks)
+    rng = np.random.RandomState(1)
+    for i, k in enumerate(ks):
+        if k < 0:
+            K, w = -k, so.draw_weights(m, -k, rng)
+        else:
+            K = k
+            ch = so.draw_chain(m, k, rng)
+            w = ch.ws
+            assert list(got[i].a_idx[:K]) == list(ch.a_idx)
+            assert list(got[i].b_idx[:K]) == list(ch.b_idx)
+        order = so.draw_component_order(K, 50, rng)
+        assert list(got[i].ws[:K + 1]) == list(w)
+        assert list(got[i].k_order[:50]) == list(order)
+
+
+def test_reference_assertion_is_reported():
+    """assert 0 <= x < utr_length (apa_core.py:388) -> negative status instead of a silent fit."""
+    x = np.array([-5.0, 10.0, 30.0]); l = np.array([50.0, 50.0, 50.0]); nan = np.full(3, np.nan)
+    with pytest.raises(_lib.ScapeB200Error):
+        _lib.profile(_lib.make_params(), x, l, nan, nan)
