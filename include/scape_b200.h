@@ -100,6 +100,7 @@ typedef struct scape_b200_timing {
   double em_grid_flops;
   double tensor_exp;                              /* exp() evaluations of the marginal kernel  */
   double h2d_bytes, d2h_bytes;
+  double em_scan_bytes;                           /* tensor bytes the grid search actually loads (fragment hull only) */
 } scape_b200_timing;
 
 typedef struct scape_b200_handle scape_b200_handle;

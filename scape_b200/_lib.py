@@ -69,7 +69,7 @@ class Timing(C.Structure):
         ("total_ms", C.c_double),
         ("launches", C.c_int64), ("waves", C.c_int64),
         ("em_grid_bytes", C.c_double), ("em_grid_flops", C.c_double), ("tensor_exp", C.c_double),
-        ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
+        ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("em_scan_bytes", C.c_double),
     ]
 
     def as_dict(self):

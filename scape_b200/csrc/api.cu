@@ -254,6 +254,7 @@ int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::v
     const UtrDev& u = utrs_host[size_t(c.utr)];
     h->tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;
     h->tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
+    h->tm.em_scan_bytes += c.grid_elems * 8.0;
   }
   return 0;
 }
@@ -430,14 +431,17 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
     // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
     for (;;) {
       std::vector<ChainDev> chains;
-      std::vector<size_t> owner;       // wave index of each chain
       double tr0 = now_ms();
-      for (size_t i = 0; i < W; i++) {
+      // RNG replay is serial per stream but streams are independent: one task per UTR of the wave
+      std::vector<std::vector<ChainDev>> drawn(W);
+      parallel_for(int64_t(W), h->host_threads, [&](int64_t ii) {
+        const size_t i = size_t(ii);
         WaveUtr& w = wave[i];
-        if (w.done) continue;
+        if (w.done) return;
         const UtrPrep& p = prep[size_t(w.u)];
         NpRandomState& g = rng[size_t(stream_of[size_t(w.u)])];
-        const size_t first_chain = chains.size();
+        std::vector<ChainDev>& mine = drawn[i];
+        mine.reserve(size_t(w.k_max - w.k_min + 1) * SCAPE_B200_NTRIAL);
         for (int K = w.k_max; K >= w.k_min && !w.done; K--)
           for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++) {
             ChainInit ci;
@@ -445,8 +449,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
             if (rc != kOk) {       // numpy's choice() would have raised inside the reference
               out->status[w.u] = rc;
               w.done = true;
-              chains.resize(first_chain);
-              owner.resize(first_chain);
+              mine.clear();
               break;
             }
             ChainDev c;
@@ -456,10 +459,10 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
             memcpy(c.b_idx, ci.b_idx, sizeof(ci.b_idx));
             memcpy(c.ws, ci.ws, sizeof(ci.ws));
             memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
-            chains.push_back(c);
-            owner.push_back(i);
+            mine.push_back(c);
           }
-      }
+      });
+      for (size_t i = 0; i < W; i++) chains.insert(chains.end(), drawn[i].begin(), drawn[i].end());
       h->tm.host_rng_ms += now_ms() - tr0;
       if (chains.empty()) break;
       if (int rc = run_chains(h, chains, ud)) return rc;

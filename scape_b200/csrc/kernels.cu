@@ -162,9 +162,19 @@ __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ 
     const double* col = tab + (int64_t)lo * ld;
     double m = (col[0] + lp[0]) - lps;
     for (int d = 1; d < w; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
-    double acc = 0.0;
-    for (int d = 0; d < w; d++) acc += exp(((col[(int64_t)d * ld] + lp[d]) - lps) - m);
-    out[(int64_t)j * ld] = log(acc) + m;
+    double res;
+    if (m < -1e30) {
+      // every term is the sentinel: exp(0) each, log(w) + sentinel == sentinel in FP64
+      res = log((double)w) + m;
+    } else {
+      double acc = 0.0;
+      for (int d = 0; d < w; d++) {
+        const double a = ((col[(int64_t)d * ld] + lp[d]) - lps) - m;
+        if (a > -746.0) acc += exp(a);   // below that exp() is exactly 0 (sentinel terms: a ~ -3.4e38)
+      }
+      res = log(acc) + m;
+    }
+    out[(int64_t)j * ld] = res;
   }
 }
 
@@ -210,13 +220,14 @@ __device__ __forceinline__ void block_reduce_sum(double (&val)[NV], double (*s_r
   __syncthreads();
 }
 
-// Candidate scan with LW lanes per tensor row (LW = 8 for short rows, 32 for long ones).
+// Candidate scan with LW lanes per tensor row.  Only the hull [i_lo, i_hi) (in double2 units) of the
+// fragments with v != 0 is read: terms with v == 0 contribute exactly +-0 to the reference's sum.
 template <int LW>
 __device__ __forceinline__ void grid_scan(const double* __restrict__ T, const double* __restrict__ v, int npad,
-                                          int row0, int row1, double& best_score, int& best_row) {
+                                          int i_lo, int i_hi, int row0, int row1, double& best_score,
+                                          int& best_row) {
   constexpr int G = EM_THREADS / LW;
   const int g = threadIdx.x / LW, lg = threadIdx.x % LW;
-  const int n2 = npad >> 1;
   const double2* v2 = reinterpret_cast<const double2*>(v);
   for (int rb = row0; rb < row1; rb += G) {
     const int r = rb + g;
@@ -224,7 +235,7 @@ __device__ __forceinline__ void grid_scan(const double* __restrict__ T, const do
     if (r < row1) {
       const double2* t2 = reinterpret_cast<const double2*>(T + (int64_t)r * npad);
 #pragma unroll 4
-      for (int i = lg; i < n2; i += LW) {
+      for (int i = i_lo + lg; i < i_hi; i += LW) {
         const double2 t = __ldg(t2 + i);
         const double2 w = v2[i];
         acc0 = fma(t.x, w.x, acc0);
@@ -241,18 +252,32 @@ __device__ __forceinline__ void grid_scan(const double* __restrict__ T, const do
   }
 }
 
+struct EmShared {
+  double w[SCAPE_B200_KCAP + 1], lw[SCAPE_B200_KCAP + 1];
+  int a[SCAPE_B200_KCAP], b[SCAPE_B200_KCAP];
+  double red[EM_WARPS][SCAPE_B200_KCAP + 4];
+  double tot[SCAPE_B200_KCAP + 4];
+  double bscore[EM_THREADS / 4];
+  int brow[EM_THREADS / 4];
+  int ctl[2];    // [1] converged
+  int hull[2];   // first / last fragment with v != 0
+};
+
 template <int NK>  // NK = K + 1 columns
-__device__ void em_chain_run(ChainDev& ch, const UtrDev& u, const double* __restrict__ T,
+__device__ void em_chain_run(EmShared& sh, ChainDev& ch, const UtrDev& u, const double* __restrict__ T,
                              const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ v,
                              int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
   constexpr int K = NK - 1;
-  __shared__ double s_w[SCAPE_B200_KCAP + 1], s_lw[SCAPE_B200_KCAP + 1];
-  __shared__ int s_a[SCAPE_B200_KCAP], s_b[SCAPE_B200_KCAP];
-  __shared__ double s_red[EM_WARPS][SCAPE_B200_KCAP + 4];
-  __shared__ double s_tot[SCAPE_B200_KCAP + 4];
-  __shared__ double s_bscore[EM_THREADS / 8];
-  __shared__ int s_brow[EM_THREADS / 8];
-  __shared__ int s_ctl[2];  // [0] guard requested, [1] converged
+  double (&s_w)[SCAPE_B200_KCAP + 1] = sh.w;
+  double (&s_lw)[SCAPE_B200_KCAP + 1] = sh.lw;
+  int (&s_a)[SCAPE_B200_KCAP] = sh.a;
+  int (&s_b)[SCAPE_B200_KCAP] = sh.b;
+  double (*s_red)[SCAPE_B200_KCAP + 4] = sh.red;
+  double* s_tot = sh.tot;
+  double* s_bscore = sh.bscore;
+  int* s_brow = sh.brow;
+  int* s_ctl = sh.ctl;
+  int* s_hull = sh.hull;
 
   const int tid = threadIdx.x;
   const int N = u.N, npad = u.Npad, B = u.B;
@@ -284,7 +309,7 @@ __device__ void em_chain_run(ChainDev& ch, const UtrDev& u, const double* __rest
 
   double lb = SCAPE_SENTINEL;  // meaningful in thread 0 only
   double last_A = 0.0;
-  double grid_rows = 0.0;
+  double grid_rows = 0.0, grid_elems = 0.0;
   int n_iter = 0;
 
   for (int it = 0; it < SCAPE_B200_NROUND; it++) {
@@ -296,6 +321,8 @@ __device__ void em_chain_run(ChainDev& ch, const UtrDev& u, const double* __rest
       const double* trow = T + ((int64_t)s_a[k] * B + s_b[k]) * npad;
 #pragma unroll
       for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
+      int h_lo = N, h_hi = -1;
+      if (tid == 0) { s_hull[0] = N; s_hull[1] = -1; }
       for (int n = tid; n < N; n += EM_THREADS) {
         const double c = cnt[n];
         const double fresh = lwk + trow[n];
@@ -341,8 +368,12 @@ __device__ void em_chain_run(ChainDev& ch, const UtrDev& u, const double* __rest
         }
         red[NK + 1] += A;
         red[NK + 2] = fma(c, h, red[NK + 2]);
-        v[n] = zk * c;
+        const double vn = zk * c;
+        v[n] = vn;
+        if (vn != 0.0) { h_lo = min(h_lo, n); h_hi = n; }
       }
+      __syncthreads();
+      if (h_hi >= 0) { atomicMin(&s_hull[0], h_lo); atomicMax(&s_hull[1], h_hi); }
       block_reduce_sum<NK + 3>(red, s_red, s_tot);
       if (!guard && s_tot[NK] < 1e-8) {        // mstep guard (:526-529); uniform across the CTA
         guard = true;
@@ -382,12 +413,18 @@ __device__ void em_chain_run(ChainDev& ch, const UtrDev& u, const double* __rest
       double bscore = -CUDART_INF;
       int brow = row0;
       int groups;
-      if (npad <= 512) {
-        grid_scan<8>(T, v, npad, row0, row1, bscore, brow);
+      const int i_lo = s_hull[0] >> 1, i_hi = (s_hull[1] >> 1) + 1;   // empty hull -> i_hi <= i_lo, all scores 0
+      const int span = i_hi - i_lo;
+      if (span <= 32) {
+        grid_scan<4>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
+        groups = EM_THREADS / 4;
+        if ((tid & 3) == 0) { s_bscore[tid >> 2] = bscore; s_brow[tid >> 2] = brow; }
+      } else if (span <= 256) {
+        grid_scan<8>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
         groups = EM_THREADS / 8;
         if ((tid & 7) == 0) { s_bscore[tid >> 3] = bscore; s_brow[tid >> 3] = brow; }
       } else {
-        grid_scan<32>(T, v, npad, row0, row1, bscore, brow);
+        grid_scan<32>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
         groups = EM_THREADS / 32;
         if ((tid & 31) == 0) { s_bscore[tid >> 5] = bscore; s_brow[tid >> 5] = brow; }
       }
@@ -404,6 +441,7 @@ __device__ void em_chain_run(ChainDev& ch, const UtrDev& u, const double* __rest
         s_a[k] = row / B;
         s_b[k] = row % B;
         grid_rows += (double)(row1 - row0);
+        grid_elems += (double)(row1 - row0) * (double)(2 * max(span, 0));
       }
     }
     if (tid == 0) {
@@ -427,24 +465,56 @@ __device__ void em_chain_run(ChainDev& ch, const UtrDev& u, const double* __rest
     ch.n_iter = n_iter;
     ch.bic = -2.0 * last_A + (3 * K + 1) * log((double)N);      // cal_bic (:702-706)
     ch.grid_rows = grid_rows;
+    ch.grid_elems = grid_elems;
     for (int j = 0; j < K; j++) { ch.a_idx[j] = s_a[j]; ch.b_idx[j] = s_b[j]; }
     for (int j = 0; j < NK; j++) ch.ws[j] = s_w[j];
   }
 }
 
+constexpr int EM_MIN_BLOCKS = 3;
+constexpr int EM_MULTI_KMAX = 7;
+
+// K >= 8 (only reachable through re-runs): one instantiation per K.
 template <int NK>
-__global__ void __launch_bounds__(EM_THREADS) em_chain_kernel(ChainDev* chains, const int32_t* __restrict__ order,
-                                                              const UtrDev* __restrict__ utrs,
-                                                              const double* __restrict__ tensor,
-                                                              const double* __restrict__ cnt, double* lz_all,
-                                                              double* v_all, int smem_doubles, int32_t* trace_a,
-                                                              int32_t* trace_b, double* trace_ws) {
+__global__ void __launch_bounds__(EM_THREADS, 2) em_chain_kernel(ChainDev* chains, const int32_t* __restrict__ order,
+                                                                 const UtrDev* __restrict__ utrs,
+                                                                 const double* __restrict__ tensor,
+                                                                 const double* __restrict__ cnt, double* lz_all,
+                                                                 double* v_all, int smem_doubles, int32_t* trace_a,
+                                                                 int32_t* trace_b, double* trace_ws) {
   extern __shared__ double sm_v[];
   ChainDev& ch = chains[order[blockIdx.x]];
   const UtrDev u = utrs[ch.utr];
   double* v = (u.Npad <= smem_doubles) ? sm_v : (v_all + ch.v_off);
-  em_chain_run<NK>(ch, u, tensor + u.tensor_off, cnt + u.frag_off, lz_all + ch.lz_off, v, trace_a, trace_b,
+  __shared__ EmShared sh;
+  em_chain_run<NK>(sh, ch, u, tensor + u.tensor_off, cnt + u.frag_off, lz_all + ch.lz_off, v, trace_a, trace_b,
                    trace_ws);
+}
+
+// K = 1..7 in ONE launch: CTAs are ordered (UTR, K, restart), so the ~50 chains that share a UTR's
+// tensor are resident together and the tensor stays in L2 while they scan it.
+__global__ void __launch_bounds__(EM_THREADS, EM_MIN_BLOCKS)
+em_chain_kernel_multi(ChainDev* chains, const int32_t* __restrict__ order, const UtrDev* __restrict__ utrs,
+                      const double* __restrict__ tensor, const double* __restrict__ cnt, double* lz_all,
+                      double* v_all, int smem_doubles, int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
+  extern __shared__ double sm_v[];
+  ChainDev& ch = chains[order[blockIdx.x]];
+  const UtrDev u = utrs[ch.utr];
+  double* v = (u.Npad <= smem_doubles) ? sm_v : (v_all + ch.v_off);
+  const double* T = tensor + u.tensor_off;
+  const double* c = cnt + u.frag_off;
+  double* lz = lz_all + ch.lz_off;
+  __shared__ EmShared sh;
+  switch (ch.K) {
+    case 1: em_chain_run<2>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 2: em_chain_run<3>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 3: em_chain_run<4>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 4: em_chain_run<5>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 5: em_chain_run<6>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 6: em_chain_run<7>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 7: em_chain_run<8>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    default: break;
+  }
 }
 
 typedef void (*em_kernel_t)(ChainDev*, const int32_t*, const UtrDev*, const double*, const double*, double*, double*,
@@ -452,13 +522,7 @@ typedef void (*em_kernel_t)(ChainDev*, const int32_t*, const UtrDev*, const doub
 
 static em_kernel_t em_kernel_for(int K) {
   switch (K) {
-    case 1: return em_chain_kernel<2>;
-    case 2: return em_chain_kernel<3>;
-    case 3: return em_chain_kernel<4>;
-    case 4: return em_chain_kernel<5>;
-    case 5: return em_chain_kernel<6>;
-    case 6: return em_chain_kernel<7>;
-    case 7: return em_chain_kernel<8>;
+    case 0: return em_chain_kernel_multi;
     case 8: return em_chain_kernel<9>;
     case 9: return em_chain_kernel<10>;
     case 10: return em_chain_kernel<11>;
@@ -484,14 +548,15 @@ int launch_em_groups(ChainDev* chains_dev, const ChainDev* chains_host, int64_t 
     const ChainDev& c = chains_host[i];
     const int npad = utrs_host[c.utr].Npad;
     const int cls = npad <= SMALL ? 0 : 1;
-    buckets[c.K][cls].push_back((int32_t)i);
-    if (cls) big_max[c.K] = std::max(big_max[c.K], npad);
+    const int kb = c.K <= EM_MULTI_KMAX ? 0 : c.K;       // bucket 0 = the multi-K kernel
+    buckets[kb][cls].push_back((int32_t)i);
+    if (cls) big_max[kb] = std::max(big_max[kb], npad);
   }
   int64_t pos = 0;
   int launches = 0;
   struct Plan { int K, cls; int64_t off, n; };
   std::vector<Plan> plans;
-  for (int K = 1; K <= SCAPE_B200_KCAP; K++)
+  for (int K = 0; K <= SCAPE_B200_KCAP; K++)
     for (int cls = 0; cls < 2; cls++) {
       auto& b = buckets[K][cls];
       if (b.empty()) continue;

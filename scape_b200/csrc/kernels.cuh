@@ -57,6 +57,7 @@ struct ChainDev {
   double bic;                     // out
   double lb_arr[SCAPE_B200_NROUND];  // out
   double grid_rows;               // out: sum over iterations of candidate rows scanned (W*B)
+  double grid_elems;              // out: tensor elements actually read by the scans (rows * hull)
 };
 
 struct LabelDev {
