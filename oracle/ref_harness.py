@@ -43,7 +43,13 @@ def load_reference_apa_core():
     if "matplotlib" not in sys.modules:
         mpl = types.ModuleType("matplotlib")
         plt = types.ModuleType("matplotlib.pyplot")
-        plt.__getattr__ = lambda attr: (lambda *a, **k: None)  # type: ignore[attr-defined]
+
+        def _stub(attr):
+            if attr.startswith("__"):
+                raise AttributeError(attr)
+            return lambda *a, **k: None
+
+        plt.__getattr__ = _stub  # type: ignore[attr-defined]
         mpl.pyplot = plt
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.pyplot"] = plt
