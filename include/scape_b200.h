@@ -118,6 +118,11 @@ int scape_b200_destroy(scape_b200_handle* h);
 int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch* batch, scape_b200_results* out);
 int scape_b200_get_timing(scape_b200_handle* h, scape_b200_timing* out);
 
+/* Storage type of the marginal tensor in HBM: 4 = float (default; values are computed in FP64 and
+ * rounded once, every sum / product stays FP64), 8 = double (strict mode).  Environment override at
+ * create time: SCAPE_B200_TENSOR=f64. */
+int scape_b200_set_tensor_dtype(scape_b200_handle* h, int bytes);
+
 /* ---- kernel-seam entry points (parity tests; reference seam B3, apa_core.py:23) ------------- */
 
 /* loglik_xlr_t over a theta list (apa_core.py:620-640, taichi_core.py:183-215):

@@ -93,6 +93,7 @@ EXPORTS = [
     "scape_b200_destroy", "scape_b200_fit_batch", "scape_b200_get_timing", "scape_b200_loglik_table",
     "scape_b200_marginal_tensor", "scape_b200_em_chains", "scape_b200_bin_reads", "scape_b200_profile",
     "scape_b200_draw_chains", "scape_b200_rng_draw", "scape_b200_set_argsort_callback",
+    "scape_b200_set_tensor_dtype",
 ]
 
 ARGSORT_FN = C.CFUNCTYPE(None, c_double_p, C.c_int64, c_int64_p)
@@ -127,6 +128,7 @@ def load():
     lib.scape_b200_destroy.argtypes = [C.c_void_p]
     lib.scape_b200_fit_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Results)]
     lib.scape_b200_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    lib.scape_b200_set_tensor_dtype.argtypes = [C.c_void_p, C.c_int]
     lib.scape_b200_loglik_table.argtypes = [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
                                             C.c_int64, c_double_p, c_double_p]
     lib.scape_b200_marginal_tensor.argtypes = [C.c_void_p, C.c_int64, C.c_int64, c_double_p, C.c_int64, c_double_p,
@@ -248,11 +250,14 @@ class FitOutput:
 class Engine:
     """One handle = one GPU + one parameter set (ApaModel(**kwargs) lifetime)."""
 
-    def __init__(self, params: Params, device: int = 0):
+    def __init__(self, params: Params, device: int = 0, tensor_dtype: Optional[str] = None):
+        """tensor_dtype: "f32" (default) or "f64" storage of the marginal tensor; arithmetic is FP64."""
         self._lib = load()
         self._h = C.c_void_p()
         self.params = params
         _check(self._lib.scape_b200_create(device, C.byref(params), C.byref(self._h)))
+        if tensor_dtype is not None:
+            _check(self._lib.scape_b200_set_tensor_dtype(self._h, {"f32": 4, "f64": 8}[tensor_dtype]))
 
     def close(self):
         if self._h:

@@ -159,7 +159,8 @@ def _load_pre_para(kwargs):
 
 
 def fit_chunks(chunks: Sequence[Sequence[tuple]], seeds: Optional[Sequence[int]] = None, device: int = 0,
-               engine: Optional[_lib.Engine] = None, return_raw: bool = False, stream_state=None, **kwargs):
+               engine: Optional[_lib.Engine] = None, return_raw: bool = False, stream_state=None,
+               tensor_dtype: Optional[str] = None, **kwargs):
     """Fit every UTR of several in-memory chunks in ONE library call.  Each chunk is one RNG stream
     (seed 1 by default, like `_infer_pa`), so results equal running `infer` per file.  Returns a
     list (per chunk) of lists of Parameters."""
@@ -173,7 +174,7 @@ def fit_chunks(chunks: Sequence[Sequence[tuple]], seeds: Optional[Sequence[int]]
         seeds = [1] * len(chunks)
     own = engine is None
     if own:
-        engine = _lib.Engine(_lib.make_params(pre_para=pre_para, **kwargs), device=device)
+        engine = _lib.Engine(_lib.make_params(pre_para=pre_para, **kwargs), device=device, tensor_dtype=tensor_dtype)
     try:
         off, x, l, r, pa, sid = batch.packed()
         out = engine.fit(off, x, l, r, pa, sid, np.asarray(seeds, np.uint32), stream_state=stream_state)

@@ -26,8 +26,8 @@
 
 namespace scape {
 int launch_em_groups(ChainDev* chains_dev, const ChainDev* chains_host, int64_t n_chains, const UtrDev* utrs_host,
-                     const UtrDev* utrs_dev, const double* tensor, const double* cnt, double* lz, double* vbuf,
-                     int32_t* order_dev, int32_t* order_host, int32_t* trace_a, int32_t* trace_b,
+                     const UtrDev* utrs_dev, const void* tensor, bool f32, const double* cnt, double* lz,
+                     double* vbuf, int32_t* order_dev, int32_t* order_host, int32_t* trace_a, int32_t* trace_b,
                      double* trace_ws, cudaStream_t st);
 }
 
@@ -80,6 +80,7 @@ struct scape_b200_handle {
   cudaEvent_t ev[8];
   scape_b200_timing tm;
   double wave_budget_bytes = 24e9;
+  bool tensor_f32 = true;   // tensor storage: FP32 (default) or FP64; all arithmetic is FP64 either way
   int host_threads = 0;
 };
 
@@ -155,6 +156,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   memset(&h->tm, 0, sizeof(h->tm));
   if (const char* s = getenv("SCAPE_B200_WAVE_GB")) h->wave_budget_bytes = atof(s) * 1e9;
   if (const char* s = getenv("SCAPE_B200_THREADS")) h->host_threads = atoi(s);
+  if (const char* s = getenv("SCAPE_B200_TENSOR")) h->tensor_f32 = (strcmp(s, "f64") != 0);
   *out = h;
   return 0;
 }
@@ -171,6 +173,13 @@ int scape_b200_destroy(scape_b200_handle* h) {
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
   delete h;
+  return 0;
+}
+
+int scape_b200_set_tensor_dtype(scape_b200_handle* h, int bytes) {
+  if (!h) return fail(-5, "null handle");
+  if (bytes != 4 && bytes != 8) return fail(-5, "tensor dtype must be 4 (float) or 8 (double) bytes");
+  h->tensor_f32 = (bytes == 4);
   return 0;
 }
 
@@ -238,7 +247,7 @@ int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::v
   h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size());
   CU(cudaEventRecord(h->ev[4], h->st));
   int nl = launch_em_groups(h->d_chains.p, chains.data(), int64_t(chains.size()), utrs_host.data(), h->d_utrs.p,
-                            h->d_tensor.p, h->d_cnt.p, h->d_lz.p, h->d_v.p, h->d_order.p, order.data(),
+                            h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_lz.p, h->d_v.p, h->d_order.p, order.data(),
                             h->d_trace_a.p, h->d_trace_b.p, h->d_trace_ws.p, h->st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev[5], h->st));
@@ -412,7 +421,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
                  h->d_fpa.p, h->d_theta.p, h->d_table.p, h->st);
     CU(cudaEventRecord(h->ev[1], h->st));
     launch_tensor(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), max_n, P.n_beta, maxwin, h->d_theta.p,
-                  h->d_table.p, h->d_tensor.p, h->st);
+                  h->d_table.p, h->d_tensor.p, h->tensor_f32, h->st);
     CU(cudaEventRecord(h->ev[2], h->st));
     CU(cudaGetLastError());
     h->tm.launches += 2;
@@ -566,7 +575,8 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
     CU(h->d_labels.ensure(size_t(nl)));
     CU(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), sizeof(LabelDev) * W, cudaMemcpyHostToDevice, h->st));
     CU(cudaEventRecord(h->ev[6], h->st));
-    launch_labels(h->d_jobs.p, int64_t(W), max_n, h->d_utrs.p, h->d_tensor.p, h->d_cnt.p, h->d_labels.p, h->st);
+    launch_labels(h->d_jobs.p, int64_t(W), max_n, h->d_utrs.p, h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_labels.p,
+                h->st);
     CU(cudaEventRecord(h->ev[7], h->st));
     CU(cudaGetLastError());
     h->tm.launches += 1;
@@ -685,11 +695,18 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
   CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, h->st));
   launch_tensor(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), d.Npad, int(n_beta), maxwin, h->d_theta.p,
-                h->d_table.p, h->d_tensor.p, h->st);
+                h->d_table.p, h->d_tensor.p, h->tensor_f32, h->st);
   CU(cudaGetLastError());
   std::vector<double> ten(size_t(n_theta) * size_t(n_beta) * np_);
-  CU(cudaMemcpyAsync(ten.data(), h->d_tensor.p, 8 * ten.size(), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  if (h->tensor_f32) {
+    std::vector<float> tf(ten.size());
+    CU(cudaMemcpyAsync(tf.data(), h->d_tensor.p, 4 * tf.size(), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    for (size_t i = 0; i < tf.size(); i++) ten[i] = double(tf[i]);
+  } else {
+    CU(cudaMemcpyAsync(ten.data(), h->d_tensor.p, 8 * ten.size(), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+  }
   for (int64_t tb = 0; tb < n_theta * n_beta; tb++)
     memcpy(tensor_out + tb * n_frag, ten.data() + size_t(tb) * np_, 8 * size_t(n_frag));
   CU(upload_model_const(h->mc));
@@ -712,7 +729,14 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
     memcpy(ten.data() + size_t(tb) * np_, tensor + tb * n_frag, 8 * size_t(n_frag));
   std::copy(cnt, cnt + n_frag, pc.begin());
   CU(h->d_tensor.ensure(ten.size())); CU(h->d_cnt.ensure(np_)); CU(h->d_utrs.ensure(1));
-  CU(cudaMemcpyAsync(h->d_tensor.p, ten.data(), 8 * ten.size(), cudaMemcpyHostToDevice, h->st));
+  std::vector<float> tf;
+  if (h->tensor_f32) {
+    tf.resize(ten.size());
+    for (size_t i = 0; i < ten.size(); i++) tf[i] = float(ten[i]);
+    CU(cudaMemcpyAsync(h->d_tensor.p, tf.data(), 4 * tf.size(), cudaMemcpyHostToDevice, h->st));
+  } else {
+    CU(cudaMemcpyAsync(h->d_tensor.p, ten.data(), 8 * ten.size(), cudaMemcpyHostToDevice, h->st));
+  }
   CU(cudaMemcpyAsync(h->d_cnt.p, pc.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
   std::vector<UtrDev> ud(1, d);

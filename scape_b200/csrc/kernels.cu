@@ -101,9 +101,10 @@ void launch_table(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int ma
 // normalised log weights are built once per CTA in shared memory, then every thread owns one
 // fragment and does the reference's two-pass log-sum-exp per beta (taichi_core.py:41-54, 172-179).
 // ------------------------------------------------------------------------------------------------
+template <typename TT>
 __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ utrs, const RowRef* __restrict__ rows,
                                                      int max_win, const double* __restrict__ theta,
-                                                     const double* __restrict__ table, double* __restrict__ tensor) {
+                                                     const double* __restrict__ table, TT* __restrict__ tensor) {
   extern __shared__ double sm[];
   const RowRef rr = rows[blockIdx.x];
   const UtrDev u = utrs[rr.utr];
@@ -149,10 +150,10 @@ __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ 
   const int n = blockIdx.y * blockDim.x + tid;
   if (n >= u.Npad) return;
   const double* tab = table + u.table_off + n;
-  double* out = tensor + u.tensor_off + (int64_t)rr.t * B * u.Npad + n;
+  TT* out = tensor + u.tensor_off + (int64_t)rr.t * B * u.Npad + n;
   const int64_t ld = u.Npad;
   if (n >= u.N) {
-    for (int j = 0; j < B; j++) out[(int64_t)j * ld] = 0.0;
+    for (int j = 0; j < B; j++) out[(int64_t)j * ld] = TT(0);
     return;
   }
   for (int j = 0; j < B; j++) {
@@ -174,17 +175,22 @@ __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ 
       }
       res = log(acc) + m;
     }
-    out[(int64_t)j * ld] = res;
+    out[(int64_t)j * ld] = TT(res);   // float storage keeps the sentinel exactly (it IS float's lowest)
   }
 }
 
 void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, int n_beta, int max_win,
-                   const double* theta, const double* table, double* tensor, cudaStream_t st) {
+                   const double* theta, const double* table, void* tensor, bool f32, cudaStream_t st) {
   if (n_rows <= 0) return;
   dim3 grid((unsigned)n_rows, (unsigned)((max_n + 255) / 256));
   size_t smem = (size_t)n_beta * max_win * 2 * sizeof(double) + n_beta * sizeof(double) + 2 * n_beta * sizeof(int);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tensor_kernel<<<grid, 256, smem, st>>>(utrs, rows, max_win, theta, table, tensor);
+  if (f32) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(tensor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tensor_kernel<float><<<grid, 256, smem, st>>>(utrs, rows, max_win, theta, table, (float*)tensor);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(tensor_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tensor_kernel<double><<<grid, 256, smem, st>>>(utrs, rows, max_win, theta, table, (double*)tensor);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -220,27 +226,45 @@ __device__ __forceinline__ void block_reduce_sum(double (&val)[NV], double (*s_r
   __syncthreads();
 }
 
-// Candidate scan with LW lanes per tensor row.  Only the hull [i_lo, i_hi) (in double2 units) of the
-// fragments with v != 0 is read: terms with v == 0 contribute exactly +-0 to the reference's sum.
-template <int LW>
-__device__ __forceinline__ void grid_scan(const double* __restrict__ T, const double* __restrict__ v, int npad,
+// Candidate scan with LW lanes per tensor row, 16-byte loads (2 doubles or 4 floats).  Only the hull
+// [i_lo, i_hi) (in 16-byte units) of the fragments with v != 0 is read: terms with v == 0 contribute
+// exactly +-0 to the reference's sum.  Products and sums are FP64 whatever the storage type.
+template <typename TT> struct Vec16;
+template <> struct Vec16<double> {
+  static constexpr int E = 2;
+  static __device__ __forceinline__ void dot(const double* row, const double* v, int i, double& a0, double& a1) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(row) + i);
+    const double2 w = reinterpret_cast<const double2*>(v)[i];
+    a0 = fma(t.x, w.x, a0);
+    a1 = fma(t.y, w.y, a1);
+  }
+};
+template <> struct Vec16<float> {
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void dot(const float* row, const double* v, int i, double& a0, double& a1) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(row) + i);
+    const double2 w0 = reinterpret_cast<const double2*>(v)[2 * i];
+    const double2 w1 = reinterpret_cast<const double2*>(v)[2 * i + 1];
+    a0 = fma((double)t.x, w0.x, a0);
+    a1 = fma((double)t.y, w0.y, a1);
+    a0 = fma((double)t.z, w1.x, a0);
+    a1 = fma((double)t.w, w1.y, a1);
+  }
+};
+
+template <int LW, typename TT>
+__device__ __forceinline__ void grid_scan(const TT* __restrict__ T, const double* __restrict__ v, int npad,
                                           int i_lo, int i_hi, int row0, int row1, double& best_score,
                                           int& best_row) {
   constexpr int G = EM_THREADS / LW;
   const int g = threadIdx.x / LW, lg = threadIdx.x % LW;
-  const double2* v2 = reinterpret_cast<const double2*>(v);
   for (int rb = row0; rb < row1; rb += G) {
     const int r = rb + g;
     double acc0 = 0.0, acc1 = 0.0;
     if (r < row1) {
-      const double2* t2 = reinterpret_cast<const double2*>(T + (int64_t)r * npad);
+      const TT* row = T + (int64_t)r * npad;
 #pragma unroll 4
-      for (int i = i_lo + lg; i < i_hi; i += LW) {
-        const double2 t = __ldg(t2 + i);
-        const double2 w = v2[i];
-        acc0 = fma(t.x, w.x, acc0);
-        acc1 = fma(t.y, w.y, acc1);
-      }
+      for (int i = i_lo + lg; i < i_hi; i += LW) Vec16<TT>::dot(row, v, i, acc0, acc1);
     }
     double acc = acc0 + acc1;
 #pragma unroll
@@ -263,8 +287,8 @@ struct EmShared {
   int hull[2];   // first / last fragment with v != 0
 };
 
-template <int NK>  // NK = K + 1 columns
-__device__ void em_chain_run(EmShared& sh, ChainDev& ch, const UtrDev& u, const double* __restrict__ T,
+template <int NK, typename TT>  // NK = K + 1 columns, TT = tensor storage type
+__device__ void em_chain_run(EmShared& sh, ChainDev& ch, const UtrDev& u, const TT* __restrict__ T,
                              const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ v,
                              int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
   constexpr int K = NK - 1;
@@ -298,8 +322,8 @@ __device__ void em_chain_run(EmShared& sh, ChainDev& ch, const UtrDev& u, const 
   for (int j = 0; j < NK; j++) {
     const double lw = s_lw[j];
     if (j < K) {
-      const double* row = T + ((int64_t)s_a[j] * B + s_b[j]) * npad;
-      for (int n = tid; n < N; n += EM_THREADS) lz[(int64_t)j * npad + n] = lw + row[n];
+      const TT* row = T + ((int64_t)s_a[j] * B + s_b[j]) * npad;
+      for (int n = tid; n < N; n += EM_THREADS) lz[(int64_t)j * npad + n] = lw + (double)row[n];
     } else {
       const double val = lw + u.unif_loglik;
       for (int n = tid; n < N; n += EM_THREADS) lz[(int64_t)j * npad + n] = val;
@@ -318,14 +342,14 @@ __device__ void em_chain_run(EmShared& sh, ChainDev& ch, const UtrDev& u, const 
     double red[NK + 3];
     while (true) {
       const double lwk = s_lw[k];
-      const double* trow = T + ((int64_t)s_a[k] * B + s_b[k]) * npad;
+      const TT* trow = T + ((int64_t)s_a[k] * B + s_b[k]) * npad;
 #pragma unroll
       for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
       int h_lo = N, h_hi = -1;
       if (tid == 0) { s_hull[0] = N; s_hull[1] = -1; }
       for (int n = tid; n < N; n += EM_THREADS) {
         const double c = cnt[n];
-        const double fresh = lwk + trow[n];
+        const double fresh = lwk + (double)trow[n];
         double z[NK], lzv[NK];
         double m = -CUDART_INF;
 #pragma unroll
@@ -413,18 +437,19 @@ __device__ void em_chain_run(EmShared& sh, ChainDev& ch, const UtrDev& u, const 
       double bscore = -CUDART_INF;
       int brow = row0;
       int groups;
-      const int i_lo = s_hull[0] >> 1, i_hi = (s_hull[1] >> 1) + 1;   // empty hull -> i_hi <= i_lo, all scores 0
+      constexpr int VE = Vec16<TT>::E;   // elements per 16-byte load
+      const int i_lo = s_hull[0] / VE, i_hi = s_hull[1] < 0 ? 0 : s_hull[1] / VE + 1;   // empty hull -> no loads, all scores 0
       const int span = i_hi - i_lo;
       if (span <= 32) {
-        grid_scan<4>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
+        grid_scan<4, TT>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
         groups = EM_THREADS / 4;
         if ((tid & 3) == 0) { s_bscore[tid >> 2] = bscore; s_brow[tid >> 2] = brow; }
       } else if (span <= 256) {
-        grid_scan<8>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
+        grid_scan<8, TT>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
         groups = EM_THREADS / 8;
         if ((tid & 7) == 0) { s_bscore[tid >> 3] = bscore; s_brow[tid >> 3] = brow; }
       } else {
-        grid_scan<32>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
+        grid_scan<32, TT>(T, v, npad, i_lo, i_hi, row0, row1, bscore, brow);
         groups = EM_THREADS / 32;
         if ((tid & 31) == 0) { s_bscore[tid >> 5] = bscore; s_brow[tid >> 5] = brow; }
       }
@@ -441,7 +466,7 @@ __device__ void em_chain_run(EmShared& sh, ChainDev& ch, const UtrDev& u, const 
         s_a[k] = row / B;
         s_b[k] = row % B;
         grid_rows += (double)(row1 - row0);
-        grid_elems += (double)(row1 - row0) * (double)(2 * max(span, 0));
+        grid_elems += (double)(row1 - row0) * (double)(VE * max(span, 0));
       }
     }
     if (tid == 0) {
@@ -475,62 +500,64 @@ constexpr int EM_MIN_BLOCKS = 3;
 constexpr int EM_MULTI_KMAX = 7;
 
 // K >= 8 (only reachable through re-runs): one instantiation per K.
-template <int NK>
+template <int NK, typename TT>
 __global__ void __launch_bounds__(EM_THREADS, 2) em_chain_kernel(ChainDev* chains, const int32_t* __restrict__ order,
                                                                  const UtrDev* __restrict__ utrs,
-                                                                 const double* __restrict__ tensor,
+                                                                 const void* __restrict__ tensor,
                                                                  const double* __restrict__ cnt, double* lz_all,
                                                                  double* v_all, int smem_doubles, int32_t* trace_a,
                                                                  int32_t* trace_b, double* trace_ws) {
   extern __shared__ double sm_v[];
+  __shared__ EmShared sh;
   ChainDev& ch = chains[order[blockIdx.x]];
   const UtrDev u = utrs[ch.utr];
   double* v = (u.Npad <= smem_doubles) ? sm_v : (v_all + ch.v_off);
-  __shared__ EmShared sh;
-  em_chain_run<NK>(sh, ch, u, tensor + u.tensor_off, cnt + u.frag_off, lz_all + ch.lz_off, v, trace_a, trace_b,
-                   trace_ws);
+  em_chain_run<NK, TT>(sh, ch, u, (const TT*)tensor + u.tensor_off, cnt + u.frag_off, lz_all + ch.lz_off, v, trace_a,
+                       trace_b, trace_ws);
 }
 
 // K = 1..7 in ONE launch: CTAs are ordered (UTR, K, restart), so the ~50 chains that share a UTR's
 // tensor are resident together and the tensor stays in L2 while they scan it.
+template <typename TT>
 __global__ void __launch_bounds__(EM_THREADS, EM_MIN_BLOCKS)
 em_chain_kernel_multi(ChainDev* chains, const int32_t* __restrict__ order, const UtrDev* __restrict__ utrs,
-                      const double* __restrict__ tensor, const double* __restrict__ cnt, double* lz_all,
+                      const void* __restrict__ tensor, const double* __restrict__ cnt, double* lz_all,
                       double* v_all, int smem_doubles, int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
   extern __shared__ double sm_v[];
+  __shared__ EmShared sh;
   ChainDev& ch = chains[order[blockIdx.x]];
   const UtrDev u = utrs[ch.utr];
   double* v = (u.Npad <= smem_doubles) ? sm_v : (v_all + ch.v_off);
-  const double* T = tensor + u.tensor_off;
+  const TT* T = (const TT*)tensor + u.tensor_off;
   const double* c = cnt + u.frag_off;
   double* lz = lz_all + ch.lz_off;
-  __shared__ EmShared sh;
   switch (ch.K) {
-    case 1: em_chain_run<2>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
-    case 2: em_chain_run<3>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
-    case 3: em_chain_run<4>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
-    case 4: em_chain_run<5>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
-    case 5: em_chain_run<6>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
-    case 6: em_chain_run<7>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
-    case 7: em_chain_run<8>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 1: em_chain_run<2, TT>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 2: em_chain_run<3, TT>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 3: em_chain_run<4, TT>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 4: em_chain_run<5, TT>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 5: em_chain_run<6, TT>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 6: em_chain_run<7, TT>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
+    case 7: em_chain_run<8, TT>(sh, ch, u, T, c, lz, v, trace_a, trace_b, trace_ws); break;
     default: break;
   }
 }
 
-typedef void (*em_kernel_t)(ChainDev*, const int32_t*, const UtrDev*, const double*, const double*, double*, double*,
+typedef void (*em_kernel_t)(ChainDev*, const int32_t*, const UtrDev*, const void*, const double*, double*, double*,
                             int, int32_t*, int32_t*, double*);
 
+template <typename TT>
 static em_kernel_t em_kernel_for(int K) {
   switch (K) {
-    case 0: return em_chain_kernel_multi;
-    case 8: return em_chain_kernel<9>;
-    case 9: return em_chain_kernel<10>;
-    case 10: return em_chain_kernel<11>;
-    case 11: return em_chain_kernel<12>;
-    case 12: return em_chain_kernel<13>;
-    case 13: return em_chain_kernel<14>;
-    case 14: return em_chain_kernel<15>;
-    case 15: return em_chain_kernel<16>;
+    case 0: return em_chain_kernel_multi<TT>;
+    case 8: return em_chain_kernel<9, TT>;
+    case 9: return em_chain_kernel<10, TT>;
+    case 10: return em_chain_kernel<11, TT>;
+    case 11: return em_chain_kernel<12, TT>;
+    case 12: return em_chain_kernel<13, TT>;
+    case 13: return em_chain_kernel<14, TT>;
+    case 14: return em_chain_kernel<15, TT>;
+    case 15: return em_chain_kernel<16, TT>;
   }
   return nullptr;
 }
@@ -538,8 +565,8 @@ static em_kernel_t em_kernel_for(int K) {
 // Host-side launch plan: chains are grouped by (K, small/large fragment count); `order_dev` must
 // hold n_chains int32 and is filled here through `order_host` (pinned or pageable).
 int launch_em_groups(ChainDev* chains_dev, const ChainDev* chains_host, int64_t n_chains, const UtrDev* utrs_host,
-                     const UtrDev* utrs_dev, const double* tensor, const double* cnt, double* lz, double* vbuf,
-                     int32_t* order_dev, int32_t* order_host, int32_t* trace_a, int32_t* trace_b,
+                     const UtrDev* utrs_dev, const void* tensor, bool f32, const double* cnt, double* lz,
+                     double* vbuf, int32_t* order_dev, int32_t* order_host, int32_t* trace_a, int32_t* trace_b,
                      double* trace_ws, cudaStream_t st) {
   constexpr int SMALL = 1024, LARGE_CAP = 24576;
   std::vector<int32_t> buckets[SCAPE_B200_KCAP + 1][2];
@@ -566,7 +593,7 @@ int launch_em_groups(ChainDev* chains_dev, const ChainDev* chains_host, int64_t 
     }
   cudaMemcpyAsync(order_dev, order_host, sizeof(int32_t) * (size_t)n_chains, cudaMemcpyHostToDevice, st);
   for (const Plan& p : plans) {
-    em_kernel_t kern = em_kernel_for(p.K);
+    em_kernel_t kern = f32 ? em_kernel_for<float>(p.K) : em_kernel_for<double>(p.K);
     int smem_doubles = p.cls == 0 ? SMALL : std::min(big_max[p.K], LARGE_CAP);
     size_t smem = (size_t)smem_doubles * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -581,9 +608,10 @@ int launch_em_groups(ChainDev* chains_dev, const ChainDev* chains_host, int64_t 
 // K5: labels.  get_label (:873-881): refresh all columns with the final parameters, tempered
 // softmax, first arg-max per fragment.
 // ------------------------------------------------------------------------------------------------
+template <typename TT>
 __global__ void __launch_bounds__(256) label_kernel(const LabelDev* __restrict__ jobs,
                                                     const UtrDev* __restrict__ utrs,
-                                                    const double* __restrict__ tensor,
+                                                    const TT* __restrict__ tensor,
                                                     const double* __restrict__ cnt, int32_t* __restrict__ labels) {
   const LabelDev& jb = jobs[blockIdx.x];
   const UtrDev u = utrs[jb.utr];
@@ -598,7 +626,7 @@ __global__ void __launch_bounds__(256) label_kernel(const LabelDev* __restrict__
     const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
     double val;
     if (j < K)
-      val = lw + tensor[u.tensor_off + ((int64_t)jb.a_idx[j] * u.B + jb.b_idx[j]) * u.Npad + n];
+      val = lw + (double)tensor[u.tensor_off + ((int64_t)jb.a_idx[j] * u.B + jb.b_idx[j]) * u.Npad + n];
     else
       val = lw + u.unif_loglik;
     lzv[j] = val;
@@ -618,11 +646,14 @@ __global__ void __launch_bounds__(256) label_kernel(const LabelDev* __restrict__
   labels[jb.out_off + n] = best;
 }
 
-void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const double* tensor,
+void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
                    const double* cnt, int32_t* labels, cudaStream_t st) {
   if (n_jobs <= 0) return;
   dim3 grid((unsigned)n_jobs, (unsigned)((max_n + 255) / 256));
-  label_kernel<<<grid, 256, 0, st>>>(jobs, utrs, tensor, cnt, labels);
+  if (f32)
+    label_kernel<float><<<grid, 256, 0, st>>>(jobs, utrs, (const float*)tensor, cnt, labels);
+  else
+    label_kernel<double><<<grid, 256, 0, st>>>(jobs, utrs, (const double*)tensor, cnt, labels);
 }
 
 }  // namespace scape

@@ -10,7 +10,9 @@
 //   frag columns x,l,r,pa,cnt  double[sum N]            CSR by UtrDev.frag_off
 //   theta grids                double[sum T]            CSR by UtrDev.theta_off
 //   table                      double[sum T*Npad]       [t][n]  (transposed w.r.t. the reference so that n is contiguous)
-//   tensor                     double[sum T*B*Npad]     [t][b][n], Npad = N rounded up to 4 (32-byte rows)
+//   tensor                     float|double[sum T*B*Npad]  [t][b][n], Npad = N rounded up to 4 (16/32-byte rows);
+//                              FP32 storage by default (values are computed in FP64 and rounded once; the
+//                              sentinel is exactly float's lowest), FP64 storage on request
 //   log_zmat scratch           double[sum_chains (K+1)*Npad]  [k][n]
 #pragma once
 #include <cuda_runtime.h>
@@ -79,12 +81,12 @@ void launch_table(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int ma
                   const double* fl, const double* fr, const double* fpa, const double* theta, double* table,
                   cudaStream_t st);
 void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, int n_beta, int max_win,
-                   const double* theta, const double* table, double* tensor, cudaStream_t st);
+                   const double* theta, const double* table, void* tensor, bool f32, cudaStream_t st);
 // returns the number of kernel launches made
 int launch_em(ChainDev* chains, int64_t n_chains, const UtrDev* utrs, const double* tensor, const double* cnt,
               double* lz, double* vbuf, int max_npad, int32_t* trace_a, int32_t* trace_b, double* trace_ws,
               cudaStream_t st);
-void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const double* tensor,
+void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
                    const double* cnt, int32_t* labels, cudaStream_t st);
 cudaError_t upload_model_const(const ModelConst& mc);
 
