@@ -24,13 +24,6 @@
 #include "host_prep.hpp"
 #include "kernels.cuh"
 
-namespace scape {
-int launch_em_groups(ChainDev* chains_dev, const ChainDev* chains_host, int64_t n_chains, const UtrDev* utrs_host,
-                     const UtrDev* utrs_dev, const void* tensor, bool f32, const double* cnt, double* lz,
-                     double* vbuf, int32_t* order_dev, int32_t* order_host, int32_t* trace_a, int32_t* trace_b,
-                     double* trace_ws, cudaStream_t st);
-}
-
 using namespace scape;
 
 static thread_local std::string g_err;
@@ -75,11 +68,13 @@ struct scape_b200_handle {
   DevBuf<UtrDev> d_utrs;
   DevBuf<RowRef> d_rows;
   DevBuf<ChainDev> d_chains;
-  DevBuf<int32_t> d_order, d_labels, d_trace_a, d_trace_b;
+  DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
+  DevBuf<GroupDev> d_groups;
   DevBuf<LabelDev> d_jobs;
   cudaEvent_t ev[8];
   scape_b200_timing tm;
   double wave_budget_bytes = 24e9;
+  int group_size = SCAPE_B200_NTRIAL;   // restarts of one (UTR, K) that share a CTA (lockstep scan)
   bool tensor_f32 = true;   // tensor storage: FP32 (default) or FP64; all arithmetic is FP64 either way
   int host_threads = 0;
 };
@@ -157,6 +152,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   if (const char* s = getenv("SCAPE_B200_WAVE_GB")) h->wave_budget_bytes = atof(s) * 1e9;
   if (const char* s = getenv("SCAPE_B200_THREADS")) h->host_threads = atoi(s);
   if (const char* s = getenv("SCAPE_B200_TENSOR")) h->tensor_f32 = (strcmp(s, "f64") != 0);
+  if (const char* s = getenv("SCAPE_B200_GROUP")) h->group_size = std::max(1, std::min(SCAPE_B200_NTRIAL, atoi(s)));
   *out = h;
   return 0;
 }
@@ -168,7 +164,7 @@ int scape_b200_destroy(scape_b200_handle* h) {
   h->d_fx.release(); h->d_fl.release(); h->d_fr.release(); h->d_fpa.release(); h->d_cnt.release();
   h->d_theta.release(); h->d_table.release(); h->d_tensor.release(); h->d_lz.release(); h->d_v.release();
   h->d_trace_ws.release(); h->d_utrs.release(); h->d_rows.release(); h->d_chains.release();
-  h->d_order.release(); h->d_labels.release(); h->d_trace_a.release(); h->d_trace_b.release();
+  h->d_groups.release(); h->d_labels.release(); h->d_trace_a.release(); h->d_trace_b.release();
   h->d_jobs.release();
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
@@ -217,38 +213,56 @@ int np_argmin(const std::vector<double>& v) {
   return best;
 }
 
-// Upload chains, run them, bring them back.  `utrs_host` is the wave's UtrDev array.
+// Upload chains, run them, bring them back.  `utrs_host` is the wave's UtrDev array.  Consecutive
+// chains with the same (utr, K, weights_only) form one group = one CTA (at most NTRIAL chains).
 int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::vector<UtrDev>& utrs_host,
                bool want_trace = false) {
   if (chains.empty()) return 0;
   int64_t lz = 0, vsz = 0, tr = 0;
-  for (auto& c : chains) {
+  std::vector<GroupDev> groups;
+  for (size_t i = 0; i < chains.size(); i++) {
+    ChainDev& c = chains[i];
     const UtrDev& u = utrs_host[size_t(c.utr)];
     c.lz_off = lz;
     lz += int64_t(c.K + 1) * u.Npad;
-    c.v_off = vsz;
-    if (u.Npad > 24576) vsz += u.Npad;
+    c.v_off = 0;
     c.trace_off = want_trace ? tr : -1;
     tr += int64_t(SCAPE_B200_NROUND) * (SCAPE_B200_KCAP + 1);
     c.n_iter = 0;
+    c.grid_rows = c.grid_elems = 0;
+    if (!groups.empty()) {
+      GroupDev& g = groups.back();
+      const ChainDev& f = chains[size_t(g.first_chain)];
+      if (g.utr == c.utr && g.K == c.K && f.weights_only == c.weights_only && g.n_chains < h->group_size) {
+        g.n_chains++;
+        continue;
+      }
+    }
+    GroupDev g;
+    g.utr = c.utr; g.K = c.K; g.n_chains = 1; g.first_chain = int32_t(i); g.v_off = 0;
+    groups.push_back(g);
+  }
+  for (GroupDev& g : groups) {
+    const UtrDev& u = utrs_host[size_t(g.utr)];
+    g.v_off = vsz;
+    if (u.N > 1024) vsz += int64_t((u.N + 3) & ~3) * SCAPE_B200_NTRIAL;   // V does not fit shared memory
   }
   CU(h->d_lz.ensure(size_t(lz)));
   CU(h->d_v.ensure(size_t(std::max<int64_t>(vsz, 1))));
   CU(h->d_chains.ensure(chains.size()));
-  CU(h->d_order.ensure(chains.size()));
+  CU(h->d_groups.ensure(groups.size()));
   if (want_trace) {
     CU(h->d_trace_a.ensure(size_t(tr)));
     CU(h->d_trace_b.ensure(size_t(tr)));
     CU(h->d_trace_ws.ensure(size_t(tr)));
   }
-  std::vector<int32_t> order(chains.size());
-  double t0 = now_ms();
+  std::vector<GroupDev> staging(groups.size());
   CU(cudaMemcpyAsync(h->d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, h->st));
-  h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size());
+  h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(GroupDev) * groups.size());
   CU(cudaEventRecord(h->ev[4], h->st));
-  int nl = launch_em_groups(h->d_chains.p, chains.data(), int64_t(chains.size()), utrs_host.data(), h->d_utrs.p,
-                            h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_lz.p, h->d_v.p, h->d_order.p, order.data(),
-                            h->d_trace_a.p, h->d_trace_b.p, h->d_trace_ws.p, h->st);
+  int nl = launch_em_groups(groups, h->d_groups.p, staging.data(), h->d_chains.p, utrs_host.data(), h->d_utrs.p,
+                            h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_lz.p, h->d_v.p, h->d_trace_a.p,
+                            h->d_trace_b.p, h->d_trace_ws.p, h->st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev[5], h->st));
   CU(cudaMemcpyAsync(chains.data(), h->d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, h->st));
@@ -258,12 +272,14 @@ int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::v
   CU(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
   h->tm.em_ms += ms;
   h->tm.launches += nl;
-  (void)t0;
+  const double esz = h->tensor_f32 ? 4.0 : 8.0;
   for (auto& c : chains) {
     const UtrDev& u = utrs_host[size_t(c.utr)];
-    h->tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;
+    h->tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;     // FP64 tensor, one chain at a time
     h->tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
-    h->tm.em_scan_bytes += c.grid_elems * 8.0;
+    h->tm.em_scan_bytes += c.grid_elems * esz;                  // what the lockstep scan really loads
+    if (getenv("SCAPE_B200_DBG") && c.dbg[3] > 0)
+      fprintf(stderr, "grp K=%d wo=%d N=%d steps=%.0f E=%.0f scan=%.0f book=%.0f cyc\n", c.K, c.weights_only, u.N, c.dbg[3], c.dbg[0], c.dbg[1], c.dbg[2]);
   }
   return 0;
 }
@@ -357,7 +373,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
         int64_t u = stream_utrs[size_t(s)][cursor[size_t(s)]];
         if (prep[size_t(u)].status != kOk) { cursor[size_t(s)]++; continue; }   // the reference would have raised
         const UtrPrep& p = prep[size_t(u)];
-        double need = double(p.T()) * p.B() * pad4(p.n()) * 8.0 * 1.1;
+        double need = double(p.T() * p.B() + 4) * pad4(p.n()) * (h->tensor_f32 ? 4.0 : 8.0) + double(p.T()) * pad4(p.n()) * 8.0;
         if (!wave.empty() && bytes + need > h->wave_budget_bytes) break;
         bytes += need;
         WaveUtr w;
@@ -383,9 +399,10 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
       const UtrPrep& p = prep[size_t(wave[i].u)];
       UtrDev& d = ud[i];
       d.N = int32_t(p.n()); d.Npad = pad4(p.n()); d.T = int32_t(p.T()); d.B = int32_t(p.B());
+      d.ldR = pad4(int64_t(d.T) * d.B);
       d.frag_off = nf; d.theta_off = nt; d.table_off = ntab; d.tensor_off = nten;
       d.unif_loglik = p.unif_loglik;
-      nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += int64_t(d.T) * d.B * d.Npad;
+      nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += d.ldR * d.N;
       max_n = std::max(max_n, d.Npad);
       for (int t = 0; t < d.T; t++) rows.push_back({int32_t(i), t});
     }
@@ -633,6 +650,7 @@ extern "C" int scape_b200_loglik_table(scape_b200_handle* h, int64_t n_frag, con
   UtrDev d;
   memset(&d, 0, sizeof(d));
   d.N = int32_t(n_frag); d.Npad = pad4(n_frag); d.T = int32_t(n_theta); d.B = h->P.n_beta;
+  d.ldR = pad4(int64_t(d.T) * d.B);
   std::vector<RowRef> rows;
   for (int t = 0; t < d.T; t++) rows.push_back({0, t});
   const size_t np_ = size_t(d.Npad);
@@ -681,6 +699,7 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
   UtrDev d;
   memset(&d, 0, sizeof(d));
   d.N = int32_t(n_frag); d.Npad = pad4(n_frag); d.T = int32_t(n_theta); d.B = int32_t(n_beta);
+  d.ldR = pad4(int64_t(d.T) * d.B);
   const size_t np_ = size_t(d.Npad);
   std::vector<RowRef> rows;
   for (int t = 0; t < d.T; t++) rows.push_back({0, t});
@@ -688,7 +707,7 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
   for (int64_t n = 0; n < n_frag; n++)
     for (int64_t t = 0; t < n_theta; t++) tt[size_t(t) * np_ + size_t(n)] = table[n * n_theta + t];
   CU(h->d_theta.ensure(size_t(n_theta))); CU(h->d_table.ensure(tt.size()));
-  CU(h->d_tensor.ensure(size_t(n_theta) * size_t(n_beta) * np_));
+  CU(h->d_tensor.ensure(size_t(d.ldR) * size_t(n_frag)));
   CU(h->d_utrs.ensure(1)); CU(h->d_rows.ensure(rows.size()));
   CU(cudaMemcpyAsync(h->d_theta.p, theta, 8 * size_t(n_theta), cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(h->d_table.p, tt.data(), 8 * tt.size(), cudaMemcpyHostToDevice, h->st));
@@ -697,7 +716,8 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
   launch_tensor(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), d.Npad, int(n_beta), maxwin, h->d_theta.p,
                 h->d_table.p, h->d_tensor.p, h->tensor_f32, h->st);
   CU(cudaGetLastError());
-  std::vector<double> ten(size_t(n_theta) * size_t(n_beta) * np_);
+  const size_t Rr = size_t(n_theta) * size_t(n_beta), ldr = size_t(d.ldR);
+  std::vector<double> ten(ldr * size_t(n_frag));
   if (h->tensor_f32) {
     std::vector<float> tf(ten.size());
     CU(cudaMemcpyAsync(tf.data(), h->d_tensor.p, 4 * tf.size(), cudaMemcpyDeviceToHost, h->st));
@@ -707,8 +727,8 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
     CU(cudaMemcpyAsync(ten.data(), h->d_tensor.p, 8 * ten.size(), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
   }
-  for (int64_t tb = 0; tb < n_theta * n_beta; tb++)
-    memcpy(tensor_out + tb * n_frag, ten.data() + size_t(tb) * np_, 8 * size_t(n_frag));
+  for (size_t n = 0; n < size_t(n_frag); n++)          // device [n][t][b] -> reference [t][b][n]
+    for (size_t r = 0; r < Rr; r++) tensor_out[r * size_t(n_frag) + n] = ten[n * ldr + r];
   CU(upload_model_const(h->mc));
   return 0;
 }
@@ -722,11 +742,13 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
   UtrDev d;
   memset(&d, 0, sizeof(d));
   d.N = int32_t(n_frag); d.Npad = pad4(n_frag); d.T = int32_t(n_theta); d.B = int32_t(n_beta);
+  d.ldR = pad4(int64_t(d.T) * d.B);
   d.unif_loglik = unif_loglik;
   const size_t np_ = size_t(d.Npad);
-  std::vector<double> ten(size_t(n_theta) * size_t(n_beta) * np_, 0.0), pc(np_, 0.0);
-  for (int64_t tb = 0; tb < n_theta * n_beta; tb++)
-    memcpy(ten.data() + size_t(tb) * np_, tensor + tb * n_frag, 8 * size_t(n_frag));
+  const size_t Rr = size_t(n_theta) * size_t(n_beta), ldr = size_t(d.ldR);
+  std::vector<double> ten(ldr * size_t(n_frag), 0.0), pc(np_, 0.0);
+  for (size_t n = 0; n < size_t(n_frag); n++)          // reference [t][b][n] -> device [n][t][b]
+    for (size_t r = 0; r < Rr; r++) ten[n * ldr + r] = tensor[r * size_t(n_frag) + n];
   std::copy(cnt, cnt + n_frag, pc.begin());
   CU(h->d_tensor.ensure(ten.size())); CU(h->d_cnt.ensure(np_)); CU(h->d_utrs.ensure(1));
   std::vector<float> tf;

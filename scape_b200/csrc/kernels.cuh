@@ -3,14 +3,16 @@
 //
 //   table_kernel    K2  loglik_xlr_t for every (fragment, theta)         apa_core.py:620-640, taichi_core.py:101-157
 //   tensor_kernel   K3  marginal log-likelihood tensor[t][b][n]          taichi_core.py:160-179, 218-246
-//   em_chain_kernel K4  one coordinate-wise EM chain per CTA, resident   apa_core.py:473-573, 702-779
+//   em_group_kernel K4  the 10 restarts of one (UTR, K) per CTA, lockstep   apa_core.py:473-573, 702-779
 //   label_kernel    K5  full E-step + row arg-max                        apa_core.py:873-881
 //
 // HBM layout (per wave of UTRs, one arena):
 //   frag columns x,l,r,pa,cnt  double[sum N]            CSR by UtrDev.frag_off
 //   theta grids                double[sum T]            CSR by UtrDev.theta_off
 //   table                      double[sum T*Npad]       [t][n]  (transposed w.r.t. the reference so that n is contiguous)
-//   tensor                     float|double[sum T*B*Npad]  [t][b][n], Npad = N rounded up to 4 (16/32-byte rows);
+//   tensor                     float|double[sum N*T*B]     [n][t][b]: for one fragment the R = T*B candidate rows
+//                              (alpha-major, beta-minor) are contiguous, so the grid search (thread <-> row)
+//                              reads it perfectly coalesced;
 //                              FP32 storage by default (values are computed in FP64 and rounded once; the
 //                              sentinel is exactly float's lowest), FP64 storage on request
 //   log_zmat scratch           double[sum_chains (K+1)*Npad]  [k][n]
@@ -18,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+
+#include <vector>
 
 #include "../../include/scape_b200.h"
 
@@ -28,6 +32,7 @@ namespace scape {
 
 struct UtrDev {
   int32_t N, Npad, T, B;
+  int64_t ldR;                    // pitch of the tensor: T*B candidate rows rounded up to 4 (16-byte aligned TMA rows)
   int64_t frag_off;
   int64_t theta_off;
   int64_t table_off;
@@ -60,6 +65,16 @@ struct ChainDev {
   double lb_arr[SCAPE_B200_NROUND];  // out
   double grid_rows;               // out: sum over iterations of candidate rows scanned (W*B)
   double grid_elems;              // out: tensor elements actually read by the scans (rows * hull)
+  double dbg[4];                  // out (first chain of a group): cycles in E phase / scan / bookkeeping, steps
+};
+
+// One CTA of the EM kernel: the restarts of one (UTR, K) pair; chains [first_chain, +n_chains).
+struct GroupDev {
+  int32_t utr;
+  int32_t K;
+  int32_t n_chains;
+  int32_t first_chain;
+  int64_t v_off;                  // into the global V scratch (used when N*10 doubles exceed shared memory)
 };
 
 struct LabelDev {
@@ -82,12 +97,13 @@ void launch_table(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int ma
                   cudaStream_t st);
 void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, int n_beta, int max_win,
                    const double* theta, const double* table, void* tensor, bool f32, cudaStream_t st);
-// returns the number of kernel launches made
-int launch_em(ChainDev* chains, int64_t n_chains, const UtrDev* utrs, const double* tensor, const double* cnt,
-              double* lz, double* vbuf, int max_npad, int32_t* trace_a, int32_t* trace_b, double* trace_ws,
-              cudaStream_t st);
 void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
                    const double* cnt, int32_t* labels, cudaStream_t st);
 cudaError_t upload_model_const(const ModelConst& mc);
+// returns the number of kernel launches made; `staging` is host scratch for the reordered groups
+int launch_em_groups(const std::vector<GroupDev>& groups_host, GroupDev* groups_dev, GroupDev* staging,
+                     ChainDev* chains_dev, const UtrDev* utrs_host, const UtrDev* utrs_dev, const void* tensor,
+                     bool f32, const double* cnt, double* lz, double* vbuf, int32_t* trace_a, int32_t* trace_b,
+                     double* trace_ws, cudaStream_t st);
 
 }  // namespace scape
