@@ -69,12 +69,13 @@ struct scape_b200_handle {
   DevBuf<RowRef> d_rows;
   DevBuf<ChainDev> d_chains;
   DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
-  DevBuf<GroupDev> d_groups;
+  DevBuf<ScanRef> d_refs;
+  DevBuf<int32_t> d_chain_off;
+  DevBuf<double> d_partials, d_counter;
   DevBuf<LabelDev> d_jobs;
   cudaEvent_t ev[8];
   scape_b200_timing tm;
   double wave_budget_bytes = 24e9;
-  int group_size = SCAPE_B200_NTRIAL;   // restarts of one (UTR, K) that share a CTA (lockstep scan)
   bool tensor_f32 = true;   // tensor storage: FP32 (default) or FP64; all arithmetic is FP64 either way
   int host_threads = 0;
 };
@@ -152,7 +153,6 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   if (const char* s = getenv("SCAPE_B200_WAVE_GB")) h->wave_budget_bytes = atof(s) * 1e9;
   if (const char* s = getenv("SCAPE_B200_THREADS")) h->host_threads = atoi(s);
   if (const char* s = getenv("SCAPE_B200_TENSOR")) h->tensor_f32 = (strcmp(s, "f64") != 0);
-  if (const char* s = getenv("SCAPE_B200_GROUP")) h->group_size = std::max(1, std::min(SCAPE_B200_NTRIAL, atoi(s)));
   *out = h;
   return 0;
 }
@@ -164,7 +164,8 @@ int scape_b200_destroy(scape_b200_handle* h) {
   h->d_fx.release(); h->d_fl.release(); h->d_fr.release(); h->d_fpa.release(); h->d_cnt.release();
   h->d_theta.release(); h->d_table.release(); h->d_tensor.release(); h->d_lz.release(); h->d_v.release();
   h->d_trace_ws.release(); h->d_utrs.release(); h->d_rows.release(); h->d_chains.release();
-  h->d_groups.release(); h->d_labels.release(); h->d_trace_a.release(); h->d_trace_b.release();
+  h->d_refs.release(); h->d_chain_off.release(); h->d_partials.release(); h->d_counter.release();
+  h->d_labels.release(); h->d_trace_a.release(); h->d_trace_b.release();
   h->d_jobs.release();
   for (auto& e : h->ev) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
@@ -213,74 +214,86 @@ int np_argmin(const std::vector<double>& v) {
   return best;
 }
 
-// Upload chains, run them, bring them back.  `utrs_host` is the wave's UtrDev array.  Consecutive
-// chains with the same (utr, K, weights_only) form one group = one CTA (at most NTRIAL chains).
+// Upload chains, run them (NROUND bulk-synchronous steps), bring them back.  `utrs_host` is the
+// wave's UtrDev array; chains must be ordered by UTR (they are generated that way).
 int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::vector<UtrDev>& utrs_host,
                bool want_trace = false) {
   if (chains.empty()) return 0;
-  int64_t lz = 0, vsz = 0, tr = 0;
-  std::vector<GroupDev> groups;
+  const size_t W = utrs_host.size();
+  int64_t lz = 0, vsz = 0, tr = 0, pb = 0;
+  std::vector<int32_t> chain_off(W + 1, 0);
+  std::vector<char> scans(W, 0);
+  bool any_scan = false;
   for (size_t i = 0; i < chains.size(); i++) {
     ChainDev& c = chains[i];
+    if (i > 0 && c.utr < chains[i - 1].utr) return fail(-5, "internal: chains not ordered by UTR");
     const UtrDev& u = utrs_host[size_t(c.utr)];
+    const int64_t n_blk = (int64_t(u.T) * u.B + kScanRows - 1) / kScanRows;
     c.lz_off = lz;
     lz += int64_t(c.K + 1) * u.Npad;
-    c.v_off = 0;
+    c.v_off = vsz;
+    vsz += (int64_t(u.N) + 7) / 8 * 8;
+    c.pb_off = pb;
+    pb += n_blk;
     c.trace_off = want_trace ? tr : -1;
     tr += int64_t(SCAPE_B200_NROUND) * (SCAPE_B200_KCAP + 1);
     c.n_iter = 0;
-    c.grid_rows = c.grid_elems = 0;
-    if (!groups.empty()) {
-      GroupDev& g = groups.back();
-      const ChainDev& f = chains[size_t(g.first_chain)];
-      if (g.utr == c.utr && g.K == c.K && f.weights_only == c.weights_only && g.n_chains < h->group_size) {
-        g.n_chains++;
-        continue;
-      }
+    c.grid_rows = 0;
+    c.lb_prev = kSentinel;
+    c.last_a = 0;
+    c.state = 1;
+    c.pending = 0;
+    c.trace_pending = 0;
+    chain_off[size_t(c.utr) + 1]++;
+    if (!c.weights_only) { scans[size_t(c.utr)] = 1; any_scan = true; }
+  }
+  for (size_t i = 0; i < W; i++) chain_off[i + 1] += chain_off[i];
+  std::vector<ScanRef> refs;
+  for (size_t i = 0; i < W; i++)
+    if (scans[i]) {
+      const int32_t n_blk = int32_t((int64_t(utrs_host[i].T) * utrs_host[i].B + kScanRows - 1) / kScanRows);
+      for (int32_t b = 0; b < n_blk; b++) refs.push_back(ScanRef{int32_t(i), b});
     }
-    GroupDev g;
-    g.utr = c.utr; g.K = c.K; g.n_chains = 1; g.first_chain = int32_t(i); g.v_off = 0;
-    groups.push_back(g);
-  }
-  for (GroupDev& g : groups) {
-    const UtrDev& u = utrs_host[size_t(g.utr)];
-    g.v_off = vsz;
-    if (u.N > 1024) vsz += int64_t((u.N + 3) & ~3) * SCAPE_B200_NTRIAL;   // V does not fit shared memory
-  }
   CU(h->d_lz.ensure(size_t(lz)));
-  CU(h->d_v.ensure(size_t(std::max<int64_t>(vsz, 1))));
+  CU(h->d_v.ensure(size_t(vsz + 8)));
   CU(h->d_chains.ensure(chains.size()));
-  CU(h->d_groups.ensure(groups.size()));
+  CU(h->d_chain_off.ensure(W + 1));
+  CU(h->d_refs.ensure(refs.size() + 1));
+  CU(h->d_partials.ensure(size_t(pb) * 2 + 2));
+  CU(h->d_counter.ensure(1));
   if (want_trace) {
     CU(h->d_trace_a.ensure(size_t(tr)));
     CU(h->d_trace_b.ensure(size_t(tr)));
     CU(h->d_trace_ws.ensure(size_t(tr)));
   }
-  std::vector<GroupDev> staging(groups.size());
   CU(cudaMemcpyAsync(h->d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, h->st));
-  h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(GroupDev) * groups.size());
+  CU(cudaMemcpyAsync(h->d_chain_off.p, chain_off.data(), sizeof(int32_t) * (W + 1), cudaMemcpyHostToDevice, h->st));
+  if (!refs.empty())
+    CU(cudaMemcpyAsync(h->d_refs.p, refs.data(), sizeof(ScanRef) * refs.size(), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemsetAsync(h->d_counter.p, 0, sizeof(double), h->st));
+  h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * refs.size() + 4 * (W + 1));
   CU(cudaEventRecord(h->ev[4], h->st));
-  int nl = launch_em_groups(groups, h->d_groups.p, staging.data(), h->d_chains.p, utrs_host.data(), h->d_utrs.p,
-                            h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_lz.p, h->d_v.p, h->d_trace_a.p,
-                            h->d_trace_b.p, h->d_trace_ws.p, h->st);
+  int nl = launch_em_steps(h->d_chains.p, int64_t(chains.size()), any_scan, h->d_refs.p, int64_t(refs.size()),
+                           h->d_utrs.p, h->d_chain_off.p, h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_lz.p,
+                           h->d_v.p, h->d_partials.p, h->d_counter.p, h->d_trace_a.p, h->d_trace_b.p,
+                           h->d_trace_ws.p, h->st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev[5], h->st));
+  double scan_elems = 0;
   CU(cudaMemcpyAsync(chains.data(), h->d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(&scan_elems, h->d_counter.p, sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   h->tm.d2h_bytes += double(sizeof(ChainDev) * chains.size());
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
   h->tm.em_ms += ms;
   h->tm.launches += nl;
-  const double esz = h->tensor_f32 ? 4.0 : 8.0;
   for (auto& c : chains) {
     const UtrDev& u = utrs_host[size_t(c.utr)];
     h->tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;     // FP64 tensor, one chain at a time
     h->tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
-    h->tm.em_scan_bytes += c.grid_elems * esz;                  // what the lockstep scan really loads
-    if (getenv("SCAPE_B200_DBG") && c.dbg[3] > 0)
-      fprintf(stderr, "grp K=%d wo=%d N=%d steps=%.0f E=%.0f scan=%.0f book=%.0f cyc\n", c.K, c.weights_only, u.N, c.dbg[3], c.dbg[0], c.dbg[1], c.dbg[2]);
   }
+  h->tm.em_scan_bytes += scan_elems * (h->tensor_f32 ? 4.0 : 8.0);   // what the blocked scan really loads
   return 0;
 }
 

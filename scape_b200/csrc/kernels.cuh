@@ -3,7 +3,7 @@
 //
 //   table_kernel    K2  loglik_xlr_t for every (fragment, theta)         apa_core.py:620-640, taichi_core.py:101-157
 //   tensor_kernel   K3  marginal log-likelihood tensor[t][b][n]          taichi_core.py:160-179, 218-246
-//   em_group_kernel K4  the 10 restarts of one (UTR, K) per CTA, lockstep   apa_core.py:473-573, 702-779
+//   em_estep_kernel + em_scan_kernel  K4  bulk-synchronous EM iterations    apa_core.py:473-573, 702-779
 //   label_kernel    K5  full E-step + row arg-max                        apa_core.py:873-881
 //
 // HBM layout (per wave of UTRs, one arena):
@@ -53,10 +53,11 @@ struct ChainDev {
   int32_t utr;
   int32_t K;
   int32_t weights_only;
-  int32_t n_iter;                 // out
+  int32_t n_iter;                 // in/out: iterations done
   int64_t lz_off;                 // into the log_zmat scratch
-  int64_t v_off;                  // into the global v scratch (only used when v does not fit in smem)
+  int64_t v_off;                  // this chain's row of V (fragment pitch = UTR's N rounded up to 8)
   int64_t trace_off;              // into the trace buffers, or -1
+  int64_t pb_off;                 // into the scan partials: one ScanPartial per row block of the UTR
   int32_t a_idx[SCAPE_B200_KCAP];
   int32_t b_idx[SCAPE_B200_KCAP];
   double ws[SCAPE_B200_KCAP + 1];
@@ -64,17 +65,18 @@ struct ChainDev {
   double bic;                     // out
   double lb_arr[SCAPE_B200_NROUND];  // out
   double grid_rows;               // out: sum over iterations of candidate rows scanned (W*B)
-  double grid_elems;              // out: tensor elements actually read by the scans (rows * hull)
-  double dbg[4];                  // out (first chain of a group): cycles in E phase / scan / bookkeeping, steps
+  // device working state
+  double lw[SCAPE_B200_KCAP + 1];
+  double lb_prev, last_a;
+  int32_t state;                  // 0 finished, 1 running, 2 converged (finishes once its last arg-max is applied)
+  int32_t pending;                // the scan of this step must cover this chain
+  int32_t cur_k, row0, row1, hlo, hhi, trace_pending;
 };
 
-// One CTA of the EM kernel: the restarts of one (UTR, K) pair; chains [first_chain, +n_chains).
-struct GroupDev {
+// (UTR, block of candidate rows) work item of the scan kernel
+struct ScanRef {
   int32_t utr;
-  int32_t K;
-  int32_t n_chains;
-  int32_t first_chain;
-  int64_t v_off;                  // into the global V scratch (used when N*10 doubles exceed shared memory)
+  int32_t blk;
 };
 
 struct LabelDev {
@@ -100,10 +102,12 @@ void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int m
 void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
                    const double* cnt, int32_t* labels, cudaStream_t st);
 cudaError_t upload_model_const(const ModelConst& mc);
-// returns the number of kernel launches made; `staging` is host scratch for the reordered groups
-int launch_em_groups(const std::vector<GroupDev>& groups_host, GroupDev* groups_dev, GroupDev* staging,
-                     ChainDev* chains_dev, const UtrDev* utrs_host, const UtrDev* utrs_dev, const void* tensor,
-                     bool f32, const double* cnt, double* lz, double* vbuf, int32_t* trace_a, int32_t* trace_b,
-                     double* trace_ws, cudaStream_t st);
+constexpr int kScanRows = 512;    // candidate rows per scan CTA (must equal SCAN_ROWS in kernels.cu)
+constexpr int kPartialBytes = 16; // sizeof(ScanPartial)
+// returns the number of kernel launches made
+int launch_em_steps(ChainDev* chains_dev, int64_t n_chains, bool any_scan, const ScanRef* refs_dev, int64_t n_refs,
+                    const UtrDev* utrs_dev, const int32_t* utr_chain_off_dev, const void* tensor, bool f32,
+                    const double* cnt, double* lz, double* vbuf, void* partials, double* scan_elems,
+                    int32_t* trace_a, int32_t* trace_b, double* trace_ws, cudaStream_t st);
 
 }  // namespace scape
