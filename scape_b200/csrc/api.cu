@@ -70,7 +70,8 @@ struct scape_b200_handle {
   DevBuf<ChainDev> d_chains;
   DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
   DevBuf<ScanRef> d_refs;
-  DevBuf<int32_t> d_chain_off;
+  DevBuf<ScanDesc> d_descs;
+  DevBuf<int32_t> d_chain_off, d_chain_idx;
   DevBuf<double> d_partials, d_counter;
   DevBuf<LabelDev> d_jobs;
   cudaEvent_t ev[8];
@@ -164,7 +165,7 @@ int scape_b200_destroy(scape_b200_handle* h) {
   h->d_fx.release(); h->d_fl.release(); h->d_fr.release(); h->d_fpa.release(); h->d_cnt.release();
   h->d_theta.release(); h->d_table.release(); h->d_tensor.release(); h->d_lz.release(); h->d_v.release();
   h->d_trace_ws.release(); h->d_utrs.release(); h->d_rows.release(); h->d_chains.release();
-  h->d_refs.release(); h->d_chain_off.release(); h->d_partials.release(); h->d_counter.release();
+  h->d_refs.release(); h->d_descs.release(); h->d_chain_off.release(); h->d_chain_idx.release(); h->d_partials.release(); h->d_counter.release();
   h->d_labels.release(); h->d_trace_a.release(); h->d_trace_b.release();
   h->d_jobs.release();
   for (auto& e : h->ev) cudaEventDestroy(e);
@@ -248,6 +249,14 @@ int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::v
     if (!c.weights_only) { scans[size_t(c.utr)] = 1; any_scan = true; }
   }
   for (size_t i = 0; i < W; i++) chain_off[i + 1] += chain_off[i];
+  std::vector<int32_t> index;
+  index.reserve(chains.size());
+  for (size_t i = 0; i < chains.size(); i++)
+    if (utrs_host[size_t(chains[i].utr)].N <= kWarpEstepMaxN) index.push_back(int32_t(i));
+  const int64_t n_small = int64_t(index.size());
+  for (size_t i = 0; i < chains.size(); i++)
+    if (utrs_host[size_t(chains[i].utr)].N > kWarpEstepMaxN) index.push_back(int32_t(i));
+  const int64_t n_big = int64_t(index.size()) - n_small;
   std::vector<ScanRef> refs;
   for (size_t i = 0; i < W; i++)
     if (scans[i]) {
@@ -258,6 +267,9 @@ int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::v
   CU(h->d_v.ensure(size_t(vsz + 8)));
   CU(h->d_chains.ensure(chains.size()));
   CU(h->d_chain_off.ensure(W + 1));
+  CU(h->d_descs.ensure(chains.size()));
+  CU(cudaMemsetAsync(h->d_descs.p, 0, sizeof(ScanDesc) * chains.size(), h->st));
+  CU(h->d_chain_idx.ensure(index.size()));
   CU(h->d_refs.ensure(refs.size() + 1));
   CU(h->d_partials.ensure(size_t(pb) * 2 + 2));
   CU(h->d_counter.ensure(1));
@@ -268,12 +280,13 @@ int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::v
   }
   CU(cudaMemcpyAsync(h->d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, h->st));
   CU(cudaMemcpyAsync(h->d_chain_off.p, chain_off.data(), sizeof(int32_t) * (W + 1), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(h->d_chain_idx.p, index.data(), sizeof(int32_t) * index.size(), cudaMemcpyHostToDevice, h->st));
   if (!refs.empty())
     CU(cudaMemcpyAsync(h->d_refs.p, refs.data(), sizeof(ScanRef) * refs.size(), cudaMemcpyHostToDevice, h->st));
   CU(cudaMemsetAsync(h->d_counter.p, 0, sizeof(double), h->st));
   h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * refs.size() + 4 * (W + 1));
   CU(cudaEventRecord(h->ev[4], h->st));
-  int nl = launch_em_steps(h->d_chains.p, int64_t(chains.size()), any_scan, h->d_refs.p, int64_t(refs.size()),
+  int nl = launch_em_steps(h->d_chains.p, h->d_descs.p, h->d_chain_idx.p, n_small, n_big, any_scan, h->d_refs.p, int64_t(refs.size()),
                            h->d_utrs.p, h->d_chain_off.p, h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_lz.p,
                            h->d_v.p, h->d_partials.p, h->d_counter.p, h->d_trace_a.p, h->d_trace_b.p,
                            h->d_trace_ws.p, h->st);

@@ -1,5 +1,8 @@
 // See kernels.cuh for the kernel list, the reference lines each kernel follows and the HBM layout.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "kernels.cuh"
@@ -214,10 +217,11 @@ void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int m
 // ------------------------------------------------------------------------------------------------
 constexpr int GT = 256;                    // threads per CTA
 constexpr int GW = GT / 32;                // warps
-constexpr int SCAN_ROWS = 2 * GT;          // candidate rows per block (2 per thread)
-constexpr int SCAN_GB = 8;                 // chains per register sub-batch
-constexpr int SCAN_MAXCH = 96;             // running chains of one UTR a scan CTA can list
-constexpr int SCAN_VCHUNK = 512;           // fragments of V staged per chunk (8 x 512 doubles = 32 KB)
+constexpr int SCAN_ROWS = GT;              // candidate rows per block (1 per thread)
+constexpr int SCAN_GB = 32;                // chains per register sub-batch (32 FP64 accumulators per thread)
+constexpr int SCAN_MAXCH = 160;            // running chains of one UTR a scan CTA can list
+constexpr int SCAN_VCHUNK = 256;           // fragments of V staged per chunk
+constexpr int SCAN_VPITCH = SCAN_VCHUNK + 4;  // pitch = 4 mod 16 doubles: the 8x4 B-fragment loads are bank-conflict free
 constexpr int RING_STAGES = 3;             // TMA ring: stages in flight
 constexpr int RING_CH = 8;                 // fragments (tensor n-rows) per stage
 constexpr int RING_PITCH = SCAN_ROWS + 8;  // elements per staged n-row (up to 3 + 3 elements of 16-byte alignment slack)
@@ -269,6 +273,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // ------------------------------------------------------------------------------------------------
 // E step
 // ------------------------------------------------------------------------------------------------
+struct ScanPartial {
+  double score;
+  int row;
+  int pad;
+};
 struct EShared {
   double red[GW][SCAPE_B200_KCAP + 4];
   double tot[SCAPE_B200_KCAP + 4];
@@ -303,14 +312,240 @@ __device__ __forceinline__ void finalize_chain(ChainDev& ch, int N) {
   ch.state = 0;
 }
 
+// (0) of a step, executed by one full warp: apply the arg-max the previous scan found for this chain
+// (first maximum in row order over the per-block partials), write the trace, finalise converged
+// chains.  Returns 1 (in every lane) if the chain still has an E step to do.
+__device__ __forceinline__ int apply_pending(ChainDev& ch, ScanDesc& sd, const UtrDev& u,
+                                             const ScanPartial* __restrict__ partials, int32_t* trace_a,
+                                             int32_t* trace_b, double* trace_ws) {
+  const int lane = threadIdx.x & 31;
+  int go = 1;
+  if (ch.pending) {
+    const int b0 = ch.row0 / SCAN_ROWS, b1 = (ch.row1 - 1) / SCAN_ROWS;
+    double best = -CUDART_INF;
+    int row = 0x7fffffff;
+    for (int b = b0 + lane; b <= b1; b += 32) {
+      const ScanPartial p = partials[ch.pb_off + b];
+      if (p.score > best || (p.score == best && p.row < row)) { best = p.score; row = p.row; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int orow = __shfl_xor_sync(0xffffffffu, row, o);
+      if (ob > best || (ob == best && orow < row)) { best = ob; row = orow; }
+    }
+    if (lane == 0) {
+      ch.a_idx[ch.cur_k] = row / u.B;
+      ch.b_idx[ch.cur_k] = row % u.B;
+      ch.pending = 0;
+      sd.pending = 0;
+      if (ch.trace_off >= 0) ch.trace_pending = ch.n_iter;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (ch.trace_off >= 0 && ch.trace_pending > 0) {
+      const int64_t o = ch.trace_off + (int64_t)(ch.trace_pending - 1) * (SCAPE_B200_KCAP + 1);
+      for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
+      for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
+      ch.trace_pending = 0;
+    }
+    if (ch.state == 2) { finalize_chain(ch, u.N); go = 0; }
+    if (ch.n_iter >= SCAPE_B200_NROUND) go = 0;
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, go, 0);
+}
+
+// After the E pass: weights (maximize_ws :498-505), ELBO (:559-561), convergence (:743), and the
+// candidate window / fragment hull the scan needs.  `tot` = [cnt@Z (NK), sum Z[:,k], A term, H term].
+template <int NK>
+__device__ __forceinline__ void estep_epilogue(ChainDev& ch, ScanDesc& sd, const UtrDev& u, const double* tot, int k,
+                                               int it, int hull_lo, int hull_hi) {
+  constexpr int K = NK - 1;
+  const double cap = c_mc.max_unif_ws;
+  const int N = u.N, B = u.B;
+  double w[NK];
+  double sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < NK; j++) sum += tot[j];
+#pragma unroll
+  for (int j = 0; j < NK; j++) w[j] = tot[j] / sum;
+  if (w[K] > cap) {
+    double rest = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) rest += w[j];
+#pragma unroll
+    for (int j = 0; j < K; j++) w[j] = (1 - cap) * w[j] / rest;
+    w[K] = cap;
+  }
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    ch.ws[j] = w[j];
+    ch.lw[j] = (w[j] <= 0.0) ? SCAPE_SENTINEL : log(w[j]);
+  }
+  const double lb_new = tot[NK + 1] + tot[NK + 2];
+  ch.last_a = tot[NK + 1];
+  ch.lb_arr[it] = lb_new;
+  ch.n_iter = it + 1;
+  const double lb = ch.lb_prev;
+  const bool conv = fabs(lb_new - lb) < fabs(1e-6 * lb);
+  if (!conv) ch.lb_prev = lb_new;
+  const bool last = conv || it == SCAPE_B200_NROUND - 1;
+  ch.cur_k = k;
+  if (ch.weights_only) {                                        // mstep_fixed (:552-557): no grid search
+    if (last) finalize_chain(ch, N); else ch.state = 1;
+  } else {
+    // max_alpha_beta (:507-523): candidate window of component k
+    const int lo = (k == 0) ? 0 : ch.a_idx[k - 1];
+    const int hi = (k == K - 1) ? u.T - 1 : ch.a_idx[k + 1];
+    ch.row0 = lo * B;
+    ch.row1 = (hi + 1) * B;
+    ch.hlo = hull_lo;
+    ch.hhi = hull_hi;
+    ch.grid_rows += (double)(ch.row1 - ch.row0);
+    ch.pending = 1;
+    ch.state = last ? 2 : 1;
+    sd.row0 = ch.row0; sd.row1 = ch.row1; sd.hlo = hull_lo; sd.hhi = hull_hi;
+    sd.v_off = ch.v_off; sd.pb_off = ch.pb_off;
+    sd.pending = 1;
+  }
+}
+
+// One fragment of the E pass (shared by the warp- and the block-per-chain kernels).
 template <int NK, typename TT>
-__device__ void estep_run(EShared& sh, ChainDev& ch, const UtrDev& u, const TT* __restrict__ A,
+__device__ __forceinline__ void estep_fragment(int n, int k, double lwk, int64_t rk, bool guard, int npad, int64_t R,
+                                               const TT* __restrict__ A, const double* __restrict__ cnt,
+                                               double* __restrict__ lz, double* __restrict__ V, double (&red)[NK + 3],
+                                               int& h_lo, int& h_hi) {
+  const double c = cnt[n];
+  const double fresh = lwk + (double)A[(int64_t)n * R + rk];
+  double z[NK], lzv[NK];
+  double m = -CUDART_INF;
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    lzv[j] = (j == k) ? fresh : lz[(int64_t)j * npad + n];
+    m = fmax(m, lzv[j]);
+  }
+  lz[(int64_t)k * npad + n] = fresh;
+  double s = 0.0, ex[NK];
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    ex[j] = (lzv[j] - m) * c;                // exponent of the count-tempered softmax (norm_z :491-493)
+    z[j] = exp(ex[j]);
+    s += z[j];
+  }
+  const double inv_s = 1.0 / s;              // one reciprocal instead of NK divisions (<= 1 ulp per entry)
+  double zk = 0.0;
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    z[j] = z[j] * inv_s;
+    if (j == k) zk = z[j];
+  }
+  red[NK] += zk;                             // np.sum(Z[:, k]) before the guard
+  if (guard) {
+    zk += 1e-8;
+#pragma unroll
+    for (int j = 0; j < NK; j++)
+      if (j == k) z[j] = zk;
+  }
+  double ps = 0.0, Aterm = 0.0;
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    red[j] = fma(c, z[j], red[j]);           // cnt @ Z
+    if (z[j] != 0.0) Aterm += (z[j] * c) * lzv[j];
+    ps += z[j];
+  }
+  // scipy.stats.entropy(Z[n, :]) = -sum p log p with p = Z / sum(Z).  Without the guard,
+  // log p_j = ex_j - log(s) - log(ps) exactly in real arithmetic: two logs instead of NK.
+  double h = 0.0;
+  const double inv_ps = 1.0 / ps;
+  if (!guard) {
+    const double lnorm = log(s) + log(ps);
+#pragma unroll
+    for (int j = 0; j < NK; j++) {
+      const double p = z[j] * inv_ps;
+      if (p > 0.0) h -= p * (ex[j] - lnorm);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NK; j++) {
+      const double p = z[j] * inv_ps;
+      if (p > 0.0) h -= p * log(p);
+    }
+  }
+  red[NK + 1] += Aterm;
+  red[NK + 2] = fma(c, h, red[NK + 2]);
+  const double vn = zk * c;
+  V[n] = vn;
+  if (vn != 0.0) { h_lo = min(h_lo, n); h_hi = n; }
+}
+
+// Warp-per-chain E step (small fragment counts): no block barriers, reductions by shuffles.
+template <int NK, typename TT>
+__device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, const TT* __restrict__ A,
+                               const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ V) {
+  constexpr int K = NK - 1;
+  const int lane = threadIdx.x & 31;
+  const int N = u.N, npad = u.Npad, B = u.B;
+  const int64_t R = u.ldR;
+  const int it = ch.n_iter;
+  if (it == 0) {
+    for (int j = 0; j < NK; j++) {
+      const double w = ch.ws[j];
+      const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
+      if (lane == 0) ch.lw[j] = lw;
+      if (j < K) {
+        const int64_t rj = (int64_t)ch.a_idx[j] * B + ch.b_idx[j];
+        for (int n = lane; n < N; n += 32) lz[(int64_t)j * npad + n] = lw + (double)A[(int64_t)n * R + rj];
+      } else {
+        const double val = lw + u.unif_loglik;
+        for (int n = lane; n < N; n += 32) lz[(int64_t)j * npad + n] = val;
+      }
+    }
+    __syncwarp();
+  }
+  const int k = ch.k_order[it];
+  const double lwk = ch.lw[k];
+  const int64_t rk = (int64_t)ch.a_idx[k] * B + ch.b_idx[k];
+  bool guard = false;
+  double red[NK + 3];
+  int h_lo, h_hi;
+  while (true) {
+#pragma unroll
+    for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
+    h_lo = N;
+    h_hi = -1;
+    for (int n = lane; n < N; n += 32) estep_fragment<NK, TT>(n, k, lwk, rk, guard, npad, R, A, cnt, lz, V, red, h_lo, h_hi);
+#pragma unroll
+    for (int j = 0; j < NK + 3; j++) {
+      double x = red[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      red[j] = x;
+    }
+    if (!guard && red[NK] < 1e-8) {          // mstep guard (:526-529), uniform across the warp
+      guard = true;
+      continue;
+    }
+    break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    h_lo = min(h_lo, __shfl_xor_sync(0xffffffffu, h_lo, o));
+    h_hi = max(h_hi, __shfl_xor_sync(0xffffffffu, h_hi, o));
+  }
+  __syncwarp();
+  if (lane == 0) estep_epilogue<NK>(ch, sd, u, red, k, it, h_lo, h_hi);
+}
+
+template <int NK, typename TT>
+__device__ void estep_run(EShared& sh, ChainDev& ch, ScanDesc& sd, const UtrDev& u, const TT* __restrict__ A,
                           const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ V) {
   constexpr int K = NK - 1;
   const int tid = threadIdx.x;
   const int N = u.N, npad = u.Npad, B = u.B;
   const int64_t R = u.ldR;
-  const double cap = c_mc.max_unif_ws;
   const int it = ch.n_iter;
   if (it == 0) {
     // initial log_zmat: all K+1 columns (em_algo :722-724)
@@ -345,55 +580,7 @@ __device__ void estep_run(EShared& sh, ChainDev& ch, const UtrDev& u, const TT* 
     for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
     int h_lo = N, h_hi = -1;
     if (tid == 0) { sh.hull[0] = N; sh.hull[1] = -1; }
-    for (int n = tid; n < N; n += GT) {
-      const double c = cnt[n];
-      const double fresh = lwk + (double)A[(int64_t)n * R + rk];
-      double z[NK], lzv[NK];
-      double m = -CUDART_INF;
-#pragma unroll
-      for (int j = 0; j < NK; j++) {
-        lzv[j] = (j == k) ? fresh : lz[(int64_t)j * npad + n];
-        m = fmax(m, lzv[j]);
-      }
-      lz[(int64_t)k * npad + n] = fresh;
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < NK; j++) {
-        z[j] = exp((lzv[j] - m) * c);
-        s += z[j];
-      }
-      double zk = 0.0;
-#pragma unroll
-      for (int j = 0; j < NK; j++) {
-        z[j] = z[j] / s;
-        if (j == k) zk = z[j];
-      }
-      red[NK] += zk;                         // np.sum(Z[:, k]) before the guard
-      if (guard) {
-        zk += 1e-8;
-#pragma unroll
-        for (int j = 0; j < NK; j++)
-          if (j == k) z[j] = zk;
-      }
-      double ps = 0.0, Aterm = 0.0;
-#pragma unroll
-      for (int j = 0; j < NK; j++) {
-        red[j] = fma(c, z[j], red[j]);       // cnt @ Z
-        if (z[j] != 0.0) Aterm += (z[j] * c) * lzv[j];
-        ps += z[j];
-      }
-      double h = 0.0;                        // scipy.stats.entropy(Z[n, :])
-#pragma unroll
-      for (int j = 0; j < NK; j++) {
-        const double p = z[j] / ps;
-        if (p > 0.0) h -= p * log(p);
-      }
-      red[NK + 1] += Aterm;
-      red[NK + 2] = fma(c, h, red[NK + 2]);
-      const double vn = zk * c;
-      V[n] = vn;
-      if (vn != 0.0) { h_lo = min(h_lo, n); h_hi = n; }
-    }
+    for (int n = tid; n < N; n += GT) estep_fragment<NK, TT>(n, k, lwk, rk, guard, npad, R, A, cnt, lz, V, red, h_lo, h_hi);
     __syncthreads();
     if (h_hi >= 0) { atomicMin(&sh.hull[0], h_lo); atomicMax(&sh.hull[1], h_hi); }
     block_reduce_sum<NK + 3>(red, sh);
@@ -404,106 +591,24 @@ __device__ void estep_run(EShared& sh, ChainDev& ch, const UtrDev& u, const TT* 
     }
     break;
   }
-  if (tid == 0) {
-    // maximize_ws (:498-505)
-    double w[NK];
-    double tot = 0.0;
-#pragma unroll
-    for (int j = 0; j < NK; j++) tot += sh.tot[j];
-#pragma unroll
-    for (int j = 0; j < NK; j++) w[j] = sh.tot[j] / tot;
-    if (w[K] > cap) {
-      double rest = 0.0;
-#pragma unroll
-      for (int j = 0; j < K; j++) rest += w[j];
-#pragma unroll
-      for (int j = 0; j < K; j++) w[j] = (1 - cap) * w[j] / rest;
-      w[K] = cap;
-    }
-#pragma unroll
-    for (int j = 0; j < NK; j++) {
-      ch.ws[j] = w[j];
-      ch.lw[j] = (w[j] <= 0.0) ? SCAPE_SENTINEL : log(w[j]);
-    }
-    const double lb_new = sh.tot[NK + 1] + sh.tot[NK + 2];      // elbo (:559-561)
-    ch.last_a = sh.tot[NK + 1];
-    ch.lb_arr[it] = lb_new;
-    ch.n_iter = it + 1;
-    const double lb = ch.lb_prev;
-    const bool conv = fabs(lb_new - lb) < fabs(1e-6 * lb);      // (:743)
-    if (!conv) ch.lb_prev = lb_new;
-    const bool last = conv || it == SCAPE_B200_NROUND - 1;
-    ch.cur_k = k;
-    if (ch.weights_only) {                                      // mstep_fixed (:552-557): no grid search
-      if (last) finalize_chain(ch, N); else ch.state = 1;
-    } else {
-      // max_alpha_beta (:507-523): candidate window of component k
-      const int lo = (k == 0) ? 0 : ch.a_idx[k - 1];
-      const int hi = (k == K - 1) ? u.T - 1 : ch.a_idx[k + 1];
-      ch.row0 = lo * B;
-      ch.row1 = (hi + 1) * B;
-      ch.hlo = sh.hull[0];
-      ch.hhi = sh.hull[1];
-      ch.grid_rows += (double)(ch.row1 - ch.row0);
-      ch.pending = 1;
-      ch.state = last ? 2 : 1;
-    }
-  }
+  if (tid == 0) estep_epilogue<NK>(ch, sd, u, sh.tot, k, it, sh.hull[0], sh.hull[1]);
 }
-
-struct ScanPartial {
-  double score;
-  int row;
-  int pad;
-};
 
 // one CTA per chain; `chains` are the wave's chains in launch order
 template <typename TT>
 __global__ void __launch_bounds__(GT, 2)
-em_estep_kernel(ChainDev* chains, const UtrDev* __restrict__ utrs, const void* __restrict__ tensor,
-                const double* __restrict__ cnt_all, double* lz_all, double* v_all,
+em_estep_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ index, const UtrDev* __restrict__ utrs,
+                const void* __restrict__ tensor, const double* __restrict__ cnt_all, double* lz_all, double* v_all,
                 const ScanPartial* __restrict__ partials, int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
   __shared__ EShared sh;
-  ChainDev& ch = chains[blockIdx.x];
+  ChainDev& ch = chains[index[blockIdx.x]];
+  ScanDesc& sd = descs[index[blockIdx.x]];
   if (ch.state == 0) return;
   const UtrDev u = utrs[ch.utr];
   const int tid = threadIdx.x;
-  // ---- (0) apply the arg-max of the previous step's scan: first maximum in row order ----
   if (tid < 32) {
-    int go = 1;
-    if (ch.pending) {
-      const int b0 = ch.row0 / SCAN_ROWS, b1 = (ch.row1 - 1) / SCAN_ROWS;
-      double best = -CUDART_INF;
-      int row = 0x7fffffff;
-      for (int b = b0 + tid; b <= b1; b += 32) {
-        const ScanPartial p = partials[ch.pb_off + b];
-        if (p.score > best || (p.score == best && p.row < row)) { best = p.score; row = p.row; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int orow = __shfl_xor_sync(0xffffffffu, row, o);
-        if (ob > best || (ob == best && orow < row)) { best = ob; row = orow; }
-      }
-      if (tid == 0) {
-        ch.a_idx[ch.cur_k] = row / u.B;
-        ch.b_idx[ch.cur_k] = row % u.B;
-        ch.pending = 0;
-        if (ch.trace_off >= 0) ch.trace_pending = ch.n_iter;
-      }
-    }
-    __syncwarp();
-    if (tid == 0) {
-      if (ch.trace_off >= 0 && ch.trace_pending > 0) {
-        const int64_t o = ch.trace_off + (int64_t)(ch.trace_pending - 1) * (SCAPE_B200_KCAP + 1);
-        for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
-        for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
-        ch.trace_pending = 0;
-      }
-      if (ch.state == 2) { finalize_chain(ch, u.N); go = 0; }
-      if (ch.n_iter >= SCAPE_B200_NROUND) go = 0;
-      sh.go = go;
-    }
+    const int go = apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws);
+    if (tid == 0) sh.go = go;
   }
   __syncthreads();
   if (!sh.go) return;
@@ -512,24 +617,68 @@ em_estep_kernel(ChainDev* chains, const UtrDev* __restrict__ utrs, const void* _
   double* lz = lz_all + ch.lz_off;
   double* V = v_all + ch.v_off;
   switch (ch.K) {
-    case 1: estep_run<2, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 2: estep_run<3, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 3: estep_run<4, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 4: estep_run<5, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 5: estep_run<6, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 6: estep_run<7, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 7: estep_run<8, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 8: estep_run<9, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 9: estep_run<10, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 10: estep_run<11, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 11: estep_run<12, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 12: estep_run<13, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 13: estep_run<14, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 14: estep_run<15, TT>(sh, ch, u, A, cnt, lz, V); break;
-    case 15: estep_run<16, TT>(sh, ch, u, A, cnt, lz, V); break;
+    case 1: estep_run<2, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 2: estep_run<3, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 3: estep_run<4, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 4: estep_run<5, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 5: estep_run<6, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 6: estep_run<7, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 7: estep_run<8, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 8: estep_run<9, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 9: estep_run<10, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 10: estep_run<11, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 11: estep_run<12, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 12: estep_run<13, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 13: estep_run<14, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 14: estep_run<15, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
+    case 15: estep_run<16, TT>(sh, ch, sd, u, A, cnt, lz, V); break;
     default: break;
   }
   if (tid == 0 && ch.weights_only && ch.trace_off >= 0) {     // weights-only chains never wait for a scan
+    const int64_t o = ch.trace_off + (int64_t)(ch.n_iter - 1) * (SCAPE_B200_KCAP + 1);
+    for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
+    for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
+  }
+}
+
+// one WARP per chain (8 chains per CTA) for UTRs with few fragments: no block barriers at all
+template <typename TT>
+__global__ void __launch_bounds__(GT, 2)
+em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ index, int n_index,
+                     const UtrDev* __restrict__ utrs, const void* __restrict__ tensor,
+                     const double* __restrict__ cnt_all, double* lz_all, double* v_all,
+                     const ScanPartial* __restrict__ partials, int32_t* trace_a, int32_t* trace_b,
+                     double* trace_ws) {
+  const int slot = blockIdx.x * GW + (threadIdx.x >> 5);
+  if (slot >= n_index) return;
+  ChainDev& ch = chains[index[slot]];
+  ScanDesc& sd = descs[index[slot]];
+  if (ch.state == 0) return;
+  const UtrDev u = utrs[ch.utr];
+  if (!apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws)) return;
+  const TT* A = (const TT*)tensor + u.tensor_off;
+  const double* cnt = cnt_all + u.frag_off;
+  double* lz = lz_all + ch.lz_off;
+  double* V = v_all + ch.v_off;
+  switch (ch.K) {
+    case 1: estep_warp_run<2, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 2: estep_warp_run<3, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 3: estep_warp_run<4, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 4: estep_warp_run<5, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 5: estep_warp_run<6, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 6: estep_warp_run<7, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 7: estep_warp_run<8, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 8: estep_warp_run<9, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 9: estep_warp_run<10, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 10: estep_warp_run<11, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 11: estep_warp_run<12, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 12: estep_warp_run<13, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 13: estep_warp_run<14, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 14: estep_warp_run<15, TT>(ch, sd, u, A, cnt, lz, V); break;
+    case 15: estep_warp_run<16, TT>(ch, sd, u, A, cnt, lz, V); break;
+    default: break;
+  }
+  if ((threadIdx.x & 31) == 0 && ch.weights_only && ch.trace_off >= 0) {
     const int64_t o = ch.trace_off + (int64_t)(ch.n_iter - 1) * (SCAPE_B200_KCAP + 1);
     for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
     for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
@@ -542,131 +691,145 @@ em_estep_kernel(ChainDev* chains, const UtrDev* __restrict__ utrs, const void* _
 struct ScanShared {
   int list[SCAN_MAXCH];          // chain indices (into the wave's chain array) that need this block
   int n_list, N0, N1;
-  unsigned long long full_bar[RING_STAGES];
   double wbest[GW][SCAN_GB];
   int wrow[GW][SCAN_GB];
+  int w0[SCAN_GB], w1[SCAN_GB];  // candidate windows of the sub-batch's chains
+  long long voff[SCAN_GB], pboff[SCAN_GB];
 };
 
-template <int GB, typename TT>
-__device__ __forceinline__ void scan_subbatch(ScanShared& sh, ChainDev* chains, const UtrDev& u,
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor-core MMA.  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
+//   A: a0 = A[lane>>2][lane&3]     B: b0 = B[lane&3][lane>>2]     D: d{0,1} = D[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// One sub-batch of up to 8*NG chains against this CTA's 256 candidate rows:
+//   scores[row][chain] = sum_n tensor[n][row] * V[chain][n]        (max_alpha_beta's np.sum, :522)
+// as a blocked FP64 matrix product on the tensor cores.  M = candidate rows (8 per MMA, 32 per
+// warp), N = chains (8 per MMA), K = fragments (4 per MMA).  A fragments come straight from the
+// [n][row] tensor (32-byte segments, software-prefetched one k-step ahead, converted to FP64 once),
+// B fragments from V staged in shared memory with a conflict-free pitch.  The operand reuse that a
+// CUDA-core version has to buy with shared-memory broadcasts (128 B/clk/SM, i.e. <= 1 FMA pair per
+// 4 SM cycles) happens inside the MMA datapath here.
+template <int NG, typename TT>
+__device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __restrict__ descs, const UtrDev& u,
                                               const TT* __restrict__ A, const double* __restrict__ v_all,
                                               ScanPartial* partials, int first, int cnt, int blk, double* Vs,
-                                              TT* ring, uint32_t& ring_it, double* scan_elems) {
+                                              double* scan_elems) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;         // MMA group id / thread-in-group
   const int64_t R = u.ldR;
+  const int N = u.N;
   const int Rv = u.T * u.B;                     // valid candidate rows
   const int base = blk * SCAN_ROWS;
   const int blk_end = min(base + SCAN_ROWS, Rv);
-  // hull of this sub-batch
-  int N0 = 1 << 30, N1 = 0;
-  int w0[GB], w1[GB];
-  const double* vrow[GB];
-#pragma unroll
-  for (int j = 0; j < GB; j++) {
-    const ChainDev& c = chains[sh.list[first + (j < cnt ? j : 0)]];
-    w0[j] = c.row0;
-    w1[j] = c.row1;
-    vrow[j] = v_all + c.v_off;
-    if (j < cnt && c.hhi >= 0) { N0 = min(N0, c.hlo); N1 = max(N1, c.hhi + 1); }
-  }
-  if (N1 <= N0) { N0 = 0; N1 = 0; }             // every v is zero: all scores 0, first row of each window wins
-  N0 &= ~7;
-  if (threadIdx.x == 0 && scan_elems) atomicAdd(scan_elems, (double)(min(base + SCAN_ROWS, Rv) - base) * (double)(N1 - N0));                                     // aligned start (V is exactly 0 outside a chain's hull)
-  const int r0 = base + tid, r1 = r0 + GT;
-  const int base_al = base & ~3;
-  const int end_al = min((blk_end + 3) & ~3, (int)R);
-  const uint32_t row_bytes = (uint32_t)(end_al - base_al) * (uint32_t)sizeof(TT);
-  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
-  const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(sh.full_bar);
-  constexpr uint32_t STAGE_BYTES = RING_CH * RING_PITCH * sizeof(TT);
-  const uint32_t off0 = (uint32_t)(r0 - base_al) * (uint32_t)sizeof(TT);
-  const uint32_t off1 = off0 + GT * (uint32_t)sizeof(TT);
-  const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
-
-  double acc0[GB], acc1[GB];
-#pragma unroll
-  for (int j = 0; j < GB; j++) acc0[j] = acc1[j] = 0.0;
-  for (int c0 = N0; c0 < N1; c0 += SCAN_VCHUNK) {
-    const int c1 = min(c0 + SCAN_VCHUNK, N1);
-    __syncthreads();                            // previous chunk / sub-batch fully consumed
-    for (int e = tid; e < GB * (c1 - c0); e += GT) {
-      const int j = e / (c1 - c0), o = e % (c1 - c0);
-      Vs[j * SCAN_VCHUNK + o] = (j < cnt) ? vrow[j < cnt ? j : 0][c0 + o] : 0.0;
+  // fragment hull of this sub-batch (union over its chains) and the chains' windows
+  if (tid < SCAN_GB) {
+    int lo = 0, hi = 0, h0 = 1 << 30, h1 = 0;
+    if (tid < cnt) {
+      const ScanDesc d = descs[sh.list[first + tid]];
+      lo = d.row0; hi = d.row1;
+      if (d.hhi >= 0) { h0 = d.hlo; h1 = d.hhi + 1; }
+      sh.voff[tid] = d.v_off;
+      sh.pboff[tid] = d.pb_off;
     }
-    const int n_it = (c1 - c0 + RING_CH - 1) / RING_CH;
-    if (tid == 0) {                             // producer prologue: fill the ring
-      for (int p = 0; p < min(n_it, RING_STAGES); p++) {
-        const uint32_t st = (ring_it + p) % RING_STAGES;
-        const int nb = c0 + p * RING_CH, ne = min(nb + RING_CH, c1);
-        const uint32_t bar = bar_base + st * 8u;
-        mbar_expect_tx(bar, row_bytes * (uint32_t)(ne - nb));
-        for (int n = nb; n < ne; n++)
-          tma_load_1d(ring_base + st * STAGE_BYTES + (uint32_t)(n - nb) * RING_PITCH * (uint32_t)sizeof(TT),
-                      A + (int64_t)n * R + base_al, row_bytes, bar);
-      }
-    }
-    __syncthreads();
-    uint32_t vj = vs_base;
-    for (int it = 0; it < n_it; it++) {
-      const uint32_t st = ring_it % RING_STAGES, parity = (ring_it / RING_STAGES) & 1u;
-      mbar_wait(bar_base + st * 8u, parity);
-      const uint32_t sa = ring_base + st * STAGE_BYTES;
-      const int nb = c0 + it * RING_CH, ne = min(nb + RING_CH, c1);
-      if (ne - nb == RING_CH) {
-#pragma unroll
-        for (int i = 0; i < RING_CH; i += 2) {
-          const double a0 = lds_elem<TT>(sa + (uint32_t)i * RING_PITCH * (uint32_t)sizeof(TT) + off0);
-          const double b0 = lds_elem<TT>(sa + (uint32_t)i * RING_PITCH * (uint32_t)sizeof(TT) + off1);
-          const double a1 = lds_elem<TT>(sa + (uint32_t)(i + 1) * RING_PITCH * (uint32_t)sizeof(TT) + off0);
-          const double b1 = lds_elem<TT>(sa + (uint32_t)(i + 1) * RING_PITCH * (uint32_t)sizeof(TT) + off1);
-#pragma unroll
-          for (int j = 0; j < GB; j++) {
-            const double2 v = lds_f64x2(vj + (uint32_t)(j * SCAN_VCHUNK + i) * 8u);
-            acc0[j] = fma(a0, v.x, acc0[j]);
-            acc1[j] = fma(b0, v.x, acc1[j]);
-            acc0[j] = fma(a1, v.y, acc0[j]);
-            acc1[j] = fma(b1, v.y, acc1[j]);
-          }
-        }
-      } else {
-        for (int i = 0; i < ne - nb; i++) {
-          const double a0 = lds_elem<TT>(sa + (uint32_t)i * RING_PITCH * (uint32_t)sizeof(TT) + off0);
-          const double b0 = lds_elem<TT>(sa + (uint32_t)i * RING_PITCH * (uint32_t)sizeof(TT) + off1);
-#pragma unroll
-          for (int j = 0; j < GB; j++) {
-            const double v = lds_f64(vj + (uint32_t)(j * SCAN_VCHUNK + i) * 8u);
-            acc0[j] = fma(a0, v, acc0[j]);
-            acc1[j] = fma(b0, v, acc1[j]);
-          }
-        }
-      }
-      vj += RING_CH * 8u;
-      __syncthreads();                          // every thread is done with this stage
-      if (tid == 0 && it + RING_STAGES < n_it) {
-        const int fb = c0 + (it + RING_STAGES) * RING_CH, fe = min(fb + RING_CH, c1);
-        const uint32_t bar = bar_base + st * 8u;
-        mbar_expect_tx(bar, row_bytes * (uint32_t)(fe - fb));
-        for (int n = fb; n < fe; n++)
-          tma_load_1d(sa + (uint32_t)(n - fb) * RING_PITCH * (uint32_t)sizeof(TT), A + (int64_t)n * R + base_al,
-                      row_bytes, bar);
-      }
-      ring_it++;
-    }
-  }
-  // first maximum of this block per chain: larger score wins, ties go to the smaller row
-#pragma unroll
-  for (int j = 0; j < GB; j++) {
-    double b = -CUDART_INF;
-    int r = 0x7fffffff;
-    if (r0 >= w0[j] && r0 < w1[j] && r0 < blk_end) { b = acc0[j]; r = r0; }
-    if (r1 >= w0[j] && r1 < w1[j] && r1 < blk_end && acc1[j] > b) { b = acc1[j]; r = r1; }
+    sh.w0[tid] = lo;
+    sh.w1[tid] = hi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, b, o);
-      const int orow = __shfl_xor_sync(0xffffffffu, r, o);
-      if (ob > b || (ob == b && orow < r)) { b = ob; r = orow; }
+      h0 = min(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+      h1 = max(h1, __shfl_xor_sync(0xffffffffu, h1, o));
     }
-    if (lane == 0) { sh.wbest[warp][j] = b; sh.wrow[warp][j] = r; }
+    if (tid == 0) {
+      if (h1 <= h0) { h0 = 0; h1 = 0; }         // every v is zero: all scores 0, first row of each window wins
+      sh.N0 = h0 & ~7;                          // aligned start (V is exactly 0 outside a chain's hull)
+      sh.N1 = h1;
+      if (scan_elems) atomicAdd(scan_elems, (double)(blk_end - base) * (double)(h1 - (h0 & ~7)));
+    }
+  }
+  __syncthreads();
+  const int N0 = sh.N0, N1 = sh.N1;
+  const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+  // this lane's A rows: row(mi) = base + 32*warp + 8*mi + g  (clamped; out-of-range rows are masked later)
+  const TT* arow[4];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++) arow[mi] = A + min(base + 32 * warp + 8 * mi + g, Rv - 1);
+
+  double acc[4][NG][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NG; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  for (int c0 = N0; c0 < N1; c0 += SCAN_VCHUNK) {
+    const int c1 = min(c0 + SCAN_VCHUNK, N1);
+    const int len = c1 - c0, len4 = (len + 3) & ~3;
+    __syncthreads();                            // previous chunk / sub-batch fully consumed
+    for (int e = tid; e < 8 * NG * len4; e += GT) {
+      const int j = e / len4, o = e - j * len4;
+      Vs[j * SCAN_VPITCH + o] = (j < cnt && o < len) ? v_all[sh.voff[j] + c0 + o] : 0.0;
+    }
+    __syncthreads();
+    // B fragment of this lane: V[chain = 8*ni + g][n = k0 + q]
+    const uint32_t vb = vs_base + (uint32_t)(g * SCAN_VPITCH + q) * 8u;
+    // register ring: A fragments are fetched PFD k-steps (4*PFD fragments) ahead of their use
+    constexpr int PFD = 4;
+    TT pre[PFD][4];
+#pragma unroll
+    for (int p = 0; p < PFD; p++) {
+      const int64_t nn = min(c0 + 4 * p + q, N - 1);       // clamped: V is zero-padded there
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) pre[p][mi] = __ldg(arow[mi] + nn * R);
+    }
+    for (int k0 = 0; k0 < len4; k0 += 4 * PFD) {
+#pragma unroll
+      for (int p = 0; p < PFD; p++) {
+        const int kk = k0 + 4 * p;
+        if (kk < len4) {                                   // uniform across the CTA
+          double a[4];
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++) a[mi] = (double)pre[p][mi];
+          if (kk + 4 * PFD < len4) {
+            const int64_t nn = min(c0 + kk + 4 * PFD + q, N - 1);
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) pre[p][mi] = __ldg(arow[mi] + nn * R);
+          }
+          double b[NG];
+#pragma unroll
+          for (int ni = 0; ni < NG; ni++) b[ni] = lds_f64(vb + (uint32_t)(ni * 8 * SCAN_VPITCH + kk) * 8u);
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+      }
+    }
+  }
+  // first maximum of this block per chain: larger score wins, ties go to the smaller row.
+  // acc[mi][ni][i] = score[row = base + 32*warp + 8*mi + g][chain = 8*ni + 2*q + i]
+#pragma unroll
+  for (int ni = 0; ni < NG; ni++) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int c = 8 * ni + 2 * q + i;
+      const int w0 = sh.w0[c], w1 = min(sh.w1[c], blk_end);
+      double b = -CUDART_INF;
+      int r = 0x7fffffff;
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) {
+        const int row = base + 32 * warp + 8 * mi + g;
+        if (row >= w0 && row < w1 && acc[mi][ni][i] > b) { b = acc[mi][ni][i]; r = row; }   // rows ascend with mi
+      }
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {        // lanes with the same q hold the same chain
+        const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+        const int orow = __shfl_xor_sync(0xffffffffu, r, o);
+        if (ob > b || (ob == b && orow < r)) { b = ob; r = orow; }
+      }
+      if (g == 0) { sh.wbest[warp][c] = b; sh.wrow[warp][c] = r; }
+    }
   }
   __syncthreads();
   if (tid < cnt) {
@@ -679,14 +842,14 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, ChainDev* chains, 
     }
     ScanPartial p;
     p.score = b; p.row = r; p.pad = 0;
-    partials[chains[sh.list[first + tid]].pb_off + blk] = p;
+    partials[sh.pboff[tid] + blk] = p;
   }
 }
 
 // one CTA per (UTR, block of SCAN_ROWS candidate rows)
 template <typename TT>
 __global__ void __launch_bounds__(GT, 2)
-em_scan_kernel(const ScanRef* __restrict__ refs, ChainDev* chains, const UtrDev* __restrict__ utrs,
+em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ descs, const UtrDev* __restrict__ utrs,
                const int32_t* __restrict__ utr_chain_off, const void* __restrict__ tensor,
                const double* __restrict__ v_all, ScanPartial* partials, double* scan_elems) {
   extern __shared__ double sm_dyn[];
@@ -700,8 +863,8 @@ em_scan_kernel(const ScanRef* __restrict__ refs, ChainDev* chains, const UtrDev*
   __syncthreads();
   const int c_begin = utr_chain_off[ref.utr], c_end = utr_chain_off[ref.utr + 1];
   for (int c = c_begin + tid; c < c_end; c += GT) {
-    const ChainDev& ch = chains[c];
-    if (ch.pending && ch.row0 < hi && ch.row1 > lo) {
+    const ScanDesc d = descs[c];
+    if (d.pending && d.row0 < hi && d.row1 > lo) {
       const int slot = atomicAdd(&sh.n_list, 1);
       if (slot < SCAN_MAXCH) sh.list[slot] = c;
     }
@@ -717,55 +880,96 @@ em_scan_kernel(const ScanRef* __restrict__ refs, ChainDev* chains, const UtrDev*
       while (j >= 0 && sh.list[j] > v) { sh.list[j + 1] = sh.list[j]; j--; }
       sh.list[j + 1] = v;
     }
-    for (int st = 0; st < RING_STAGES; st++) mbar_init((uint32_t)__cvta_generic_to_shared(&sh.full_bar[st]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  double* Vs = sm_dyn;                                           // [SCAN_GB][SCAN_VCHUNK]
-  TT* ring = reinterpret_cast<TT*>(sm_dyn + SCAN_GB * SCAN_VCHUNK);
+  double* Vs = sm_dyn;                                           // [SCAN_GB][SCAN_VPITCH]
   const TT* A = (const TT*)tensor + u.tensor_off;
-  uint32_t ring_it = 0;
+#define SCAN_CALL(G) scan_subbatch<G, TT>(sh, descs, u, A, v_all, partials, first, cnt, ref.blk, Vs, scan_elems)
   for (int first = 0; first < n_list; first += SCAN_GB) {
     const int cnt = min(SCAN_GB, n_list - first);
-    if (cnt <= 1) scan_subbatch<1, TT>(sh, chains, u, A, v_all, partials, first, cnt, ref.blk, Vs, ring, ring_it, scan_elems);
-    else if (cnt <= 2) scan_subbatch<2, TT>(sh, chains, u, A, v_all, partials, first, cnt, ref.blk, Vs, ring, ring_it, scan_elems);
-    else if (cnt <= 3) scan_subbatch<3, TT>(sh, chains, u, A, v_all, partials, first, cnt, ref.blk, Vs, ring, ring_it, scan_elems);
-    else if (cnt <= 4) scan_subbatch<4, TT>(sh, chains, u, A, v_all, partials, first, cnt, ref.blk, Vs, ring, ring_it, scan_elems);
-    else if (cnt <= 6) scan_subbatch<6, TT>(sh, chains, u, A, v_all, partials, first, cnt, ref.blk, Vs, ring, ring_it, scan_elems);
-    else scan_subbatch<8, TT>(sh, chains, u, A, v_all, partials, first, cnt, ref.blk, Vs, ring, ring_it, scan_elems);
+    if (cnt <= 8) SCAN_CALL(1);
+    else if (cnt <= 16) SCAN_CALL(2);
+    else if (cnt <= 24) SCAN_CALL(3);
+    else SCAN_CALL(4);
     __syncthreads();
   }
+#undef SCAN_CALL
 }
 
 // One EM run = NROUND steps of {estep, scan} plus a closing estep that applies the last arg-max.
-int launch_em_steps(ChainDev* chains_dev, int64_t n_chains, bool any_scan, const ScanRef* refs_dev, int64_t n_refs,
-                    const UtrDev* utrs_dev, const int32_t* utr_chain_off_dev, const void* tensor, bool f32,
-                    const double* cnt, double* lz, double* vbuf, void* partials, double* scan_elems,
-                    int32_t* trace_a, int32_t* trace_b, double* trace_ws, cudaStream_t st) {
-  const size_t smem = (size_t)SCAN_GB * SCAN_VCHUNK * sizeof(double) +
-                      (size_t)RING_STAGES * RING_CH * RING_PITCH * (f32 ? sizeof(float) : sizeof(double));
-  if (f32) cudaFuncSetAttribute(em_scan_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  else cudaFuncSetAttribute(em_scan_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// `index_dev` lists the chains with few fragments first (warp-per-chain kernel, n_small of them),
+// then the others (block-per-chain kernel).
+template <typename TT>
+static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big,
+                             bool any_scan, const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
+                             const int32_t* utr_chain_off_dev, const void* tensor, const double* cnt, double* lz,
+                             double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
+                             double* trace_ws, cudaStream_t st) {
+  const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
+  cudaFuncSetAttribute(em_scan_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
+  static const bool dbg = getenv("SCAPE_B200_DBG") != nullptr;   // per-launch event timing (development aid)
+  std::vector<cudaEvent_t> evs;
+  std::vector<int> kinds;
+  auto mark = [&](int kind) {
+    if (!dbg) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    evs.push_back(e);
+    kinds.push_back(kind);
+  };
+  mark(-1);
   for (int step = 0; step <= SCAPE_B200_NROUND; step++) {
-    if (f32)
-      em_estep_kernel<float><<<(unsigned)n_chains, GT, 0, st>>>(chains_dev, utrs_dev, tensor, cnt, lz, vbuf,
-                                                                (const ScanPartial*)partials, trace_a, trace_b, trace_ws);
-    else
-      em_estep_kernel<double><<<(unsigned)n_chains, GT, 0, st>>>(chains_dev, utrs_dev, tensor, cnt, lz, vbuf,
-                                                                 (const ScanPartial*)partials, trace_a, trace_b, trace_ws);
-    launches++;
+    if (n_small > 0) {
+      em_estep_warp_kernel<TT><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+          chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
+          trace_b, trace_ws);
+      launches++;
+      mark(0);
+    }
+    if (n_big > 0) {
+      em_estep_kernel<TT><<<(unsigned)n_big, GT, 0, st>>>(chains_dev, descs_dev, index_dev + n_small, utrs_dev, tensor, cnt, lz,
+                                                           vbuf, (const ScanPartial*)partials, trace_a, trace_b,
+                                                           trace_ws);
+      launches++;
+      mark(1);
+    }
     if (step == SCAPE_B200_NROUND || !any_scan || n_refs == 0) continue;
-    if (f32)
-      em_scan_kernel<float><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, chains_dev, utrs_dev, utr_chain_off_dev,
-                                                                tensor, vbuf, (ScanPartial*)partials, scan_elems);
-    else
-      em_scan_kernel<double><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, chains_dev, utrs_dev, utr_chain_off_dev,
-                                                                 tensor, vbuf, (ScanPartial*)partials, scan_elems);
+    em_scan_kernel<TT><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
+                                                           vbuf, (ScanPartial*)partials, scan_elems);
     launches++;
+    mark(2);
+  }
+  if (dbg) {
+    cudaStreamSynchronize(st);
+    double tot[3] = {0, 0, 0};
+    std::string line;
+    for (size_t i = 1; i < evs.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, evs[i - 1], evs[i]);
+      tot[kinds[i]] += ms;
+      if (kinds[i] == 2 && any_scan) line += std::to_string((int)(ms * 1000)) + " ";
+    }
+    fprintf(stderr, "em run: chains small=%lld big=%lld refs=%lld | estep_warp %.2f ms, estep_block %.2f ms, scan %.2f ms | scan us/step: %s\n",
+            (long long)n_small, (long long)n_big, (long long)n_refs, tot[0], tot[1], tot[2], line.c_str());
+    for (auto e : evs) cudaEventDestroy(e);
   }
   return launches;
+}
+
+int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
+                    const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
+                    const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
+                    double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
+                    double* trace_ws, cudaStream_t st) {
+  if (f32)
+    return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, refs_dev, n_refs, utrs_dev,
+                                    utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
+                                    trace_ws, st);
+  return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, refs_dev, n_refs, utrs_dev,
+                                   utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
+                                   trace_ws, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -73,6 +73,12 @@ struct ChainDev {
   int32_t cur_k, row0, row1, hlo, hhi, trace_pending;
 };
 
+// What the scan needs to know about a chain, compact (the E step writes it, scan CTAs read 50 of them)
+struct ScanDesc {
+  int32_t pending, row0, row1, hlo, hhi, pad;
+  int64_t v_off, pb_off;
+};
+
 // (UTR, block of candidate rows) work item of the scan kernel
 struct ScanRef {
   int32_t utr;
@@ -102,12 +108,14 @@ void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int m
 void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
                    const double* cnt, int32_t* labels, cudaStream_t st);
 cudaError_t upload_model_const(const ModelConst& mc);
-constexpr int kScanRows = 512;    // candidate rows per scan CTA (must equal SCAN_ROWS in kernels.cu)
+constexpr int kScanRows = 256;    // candidate rows per scan CTA (must equal SCAN_ROWS in kernels.cu)
 constexpr int kPartialBytes = 16; // sizeof(ScanPartial)
 // returns the number of kernel launches made
-int launch_em_steps(ChainDev* chains_dev, int64_t n_chains, bool any_scan, const ScanRef* refs_dev, int64_t n_refs,
-                    const UtrDev* utrs_dev, const int32_t* utr_chain_off_dev, const void* tensor, bool f32,
-                    const double* cnt, double* lz, double* vbuf, void* partials, double* scan_elems,
-                    int32_t* trace_a, int32_t* trace_b, double* trace_ws, cudaStream_t st);
+constexpr int kWarpEstepMaxN = 1024;   // UTRs with at most this many fragments use the warp-per-chain E step
+int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
+                    const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
+                    const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
+                    double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
+                    double* trace_ws, cudaStream_t st);
 
 }  // namespace scape
