@@ -101,8 +101,11 @@ void launch_table(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int ma
 
 // ------------------------------------------------------------------------------------------------
 // K3: marginal tensor.  One CTA per (alpha row, 256-fragment tile); the 13 beta windows and their
-// normalised log weights are built once per CTA in shared memory, then every thread owns one
-// fragment and does the reference's two-pass log-sum-exp per beta (taichi_core.py:41-54, 172-179).
+// normalised weights are built once per CTA in shared memory, then every thread owns one fragment.
+// The reference does a two-pass log-sum-exp per (alpha, beta) (taichi_core.py:41-54, 172-179): 307
+// exp per (fragment, alpha).  Here the exp of each table entry is taken ONCE relative to the maximum
+// over the widest window and reused by all betas (43 exp + 13*43 FMA); a beta whose own window would
+// underflow falls back to the reference's exact form.
 // ------------------------------------------------------------------------------------------------
 template <typename TT>
 __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ utrs, const RowRef* __restrict__ rows,
@@ -150,33 +153,81 @@ __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ 
     s_lps[tid] = log(acc);
   }
   __syncthreads();
+  // normalised window weights g[j][d] = N(theta_d; alpha, beta_j) / sum, laid out on the UNION window
+  // [lo_all, lo_all + w_all) and zero outside beta_j's own window (s_p is reused for them)
+  int lo_all = s_lo[0], hi_all = s_lo[0] + s_w[0];
+  for (int j = 1; j < B; j++) { lo_all = min(lo_all, s_lo[j]); hi_all = max(hi_all, s_lo[j] + s_w[j]); }
+  const int w_all = hi_all - lo_all;
+  __syncthreads();
+  for (int e = tid; e < B * max_win; e += blockDim.x) {
+    const int j = e / max_win, d = e % max_win;
+    const int dj = d - (s_lo[j] - lo_all);                 // index inside beta_j's own window
+    s_p[e] = (d < w_all && dj >= 0 && dj < s_w[j]) ? exp(s_logp[j * max_win + dj] - s_lps[j]) : 0.0;
+  }
+  __syncthreads();
   const int n = blockIdx.y * blockDim.x + tid;
-  if (n >= u.Npad) return;
+  if (n >= u.N) return;   // the tensor has no padding fragments
   const double* tab = table + u.table_off + n;
   // tensor layout [n][R], R = T*B candidate rows (alpha-major, beta-minor) contiguous per fragment
   TT* out = tensor + u.tensor_off + (int64_t)n * u.ldR + (int64_t)rr.t * B;
   const int64_t ld = u.Npad;
-  if (n >= u.N) return;   // the tensor has no padding fragments
-  for (int j = 0; j < B; j++) {
-    const int lo = s_lo[j], w = s_w[j];
-    const double lps = s_lps[j];
-    const double* lp = s_logp + j * max_win;
-    const double* col = tab + (int64_t)lo * ld;
-    double m = (col[0] + lp[0]) - lps;
-    for (int d = 1; d < w; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
-    double res;
-    if (m < -1e30) {
-      // every term is the sentinel: exp(0) each, log(w) + sentinel == sentinel in FP64
-      res = log((double)w) + m;
-    } else {
-      double acc = 0.0;
-      for (int d = 0; d < w; d++) {
-        const double a = ((col[(int64_t)d * ld] + lp[d]) - lps) - m;
-        if (a > -746.0) acc += exp(a);   // below that exp() is exactly 0 (sentinel terms: a ~ -3.4e38)
+  const double* col_all = tab + (int64_t)lo_all * ld;
+  // One exp per theta of the union window, shared by all betas:
+  //   sum_d exp(table_d + logp_jd - lps_j) = exp(M) * sum_d exp(table_d - M) * g_jd,   M = max_d table_d.
+  // Identical to the reference's per-beta two-pass log-sum-exp up to rounding; when a beta's own
+  // window lies so far below M that the shared sum underflows, that beta falls back to the exact
+  // two-pass form (this also reproduces the all-sentinel case exactly).
+  double M = col_all[0];
+  for (int d = 1; d < w_all; d++) M = fmax(M, col_all[(int64_t)d * ld]);
+  if (M < -1e30) {
+    // the read is incompatible with every theta near this alpha (71-74 % of all entries): each beta's
+    // log-sum-exp is log(w) + sentinel, which IS the sentinel in FP64 (ulp(3.4e38) = 3.8e22)
+    for (int j = 0; j < B; j++) out[j] = TT(SCAPE_SENTINEL);
+    return;
+  }
+  constexpr int JB = 16;                                   // betas handled per pass over the window
+  double acc[JB];
+  for (int j0 = 0; j0 < B; j0 += JB) {
+    const int nj = min(JB, B - j0);
+#pragma unroll
+    for (int j = 0; j < JB; j++) acc[j] = 0.0;
+    for (int d = 0; d < w_all; d++) {
+      const double a = col_all[(int64_t)d * ld] - M;
+      if (a > -746.0) {                                    // below that exp() is exactly 0 (sentinel: a ~ -3.4e38)
+        const double e = exp(a);
+#pragma unroll
+        for (int j = 0; j < JB; j++)
+          if (j < nj) acc[j] = fma(e, s_p[(j0 + j) * max_win + d], acc[j]);
       }
-      res = log(acc) + m;
     }
-    out[j] = TT(res);   // float storage keeps the sentinel exactly (it IS float's lowest)
+#pragma unroll
+    for (int j = 0; j < JB; j++) {
+      if (j < nj) {
+        double res;
+        if (acc[j] > 1e-290 && M > -1e30) {
+          res = log(acc[j]) + M;
+        } else {
+          // exact two-pass log-sum-exp over beta_j's own window (taichi_core.py:41-54, 172-179)
+          const int jj = j0 + j, lo = s_lo[jj], w = s_w[jj];
+          const double lps = s_lps[jj];
+          const double* lp = s_logp + jj * max_win;
+          const double* col = tab + (int64_t)lo * ld;
+          double m = (col[0] + lp[0]) - lps;
+          for (int d = 1; d < w; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
+          if (m < -1e30) {
+            res = log((double)w) + m;   // every term is the sentinel: exp(0) each, log(w) + sentinel == sentinel
+          } else {
+            double sum = 0.0;
+            for (int d = 0; d < w; d++) {
+              const double a = ((col[(int64_t)d * ld] + lp[d]) - lps) - m;
+              if (a > -746.0) sum += exp(a);
+            }
+            res = log(sum) + m;
+          }
+        }
+        out[j0 + j] = TT(res);   // float storage keeps the sentinel exactly (it IS float's lowest)
+      }
+    }
   }
 }
 
