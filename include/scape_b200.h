@@ -90,10 +90,13 @@ typedef struct scape_b200_results {
   double* em_work;   /* [n_utr * 2]          sum over chains/iterations of N*(K+1); total EM iterations */
 } scape_b200_results;
 
-/* Device-side timing of the last fit_batch, CUDA events on the library's stream. */
+/* Timing of the last fit_batch.  Kernel durations come from CUDA events on the library's own
+ * streams (one per lane); device_busy_ms is the length of the UNION of all kernel intervals, i.e.
+ * the time the GPU was executing this library's kernels (lanes overlap, so the per-phase sums can
+ * exceed it). */
 typedef struct scape_b200_timing {
-  double table_ms, tensor_ms, em_ms, label_ms;    /* summed kernel durations                  */
-  double host_prep_ms, host_rng_ms, h2d_ms, d2h_ms, total_ms; /* wall clock                    */
+  double table_ms, tensor_ms, em_ms, label_ms;    /* summed kernel durations (all lanes)      */
+  double host_prep_ms, host_rng_ms, device_busy_ms, d2h_ms, total_ms; /* wall clock, except device_busy_ms */
   int64_t launches;                               /* kernels launched by this library          */
   int64_t waves;
   double em_grid_bytes;                           /* algorithmic tensor bytes read by the EM grid search */

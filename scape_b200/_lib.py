@@ -65,7 +65,7 @@ class Results(C.Structure):
 class Timing(C.Structure):
     _fields_ = [
         ("table_ms", C.c_double), ("tensor_ms", C.c_double), ("em_ms", C.c_double), ("label_ms", C.c_double),
-        ("host_prep_ms", C.c_double), ("host_rng_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("host_prep_ms", C.c_double), ("host_rng_ms", C.c_double), ("device_busy_ms", C.c_double), ("d2h_ms", C.c_double),
         ("total_ms", C.c_double),
         ("launches", C.c_int64), ("waves", C.c_int64),
         ("em_grid_bytes", C.c_double), ("em_grid_flops", C.c_double), ("tensor_exp", C.c_double),

@@ -59,10 +59,10 @@ struct DevBuf {
   }
 };
 
-struct scape_b200_handle {
-  int device = 0;
-  scape_b200_params P;
-  ModelConst mc;
+// Device-side state of one lane.  A fit splits its RNG streams over the lanes; every lane runs its
+// own wave loop in its own host thread on its own CUDA stream, so the host work of one lane (RNG
+// replay, model selection, result assembly) overlaps the kernels of the others.
+struct Lane {
   cudaStream_t st = nullptr;
   DevBuf<double> d_fx, d_fl, d_fr, d_fpa, d_cnt, d_theta, d_table, d_tensor, d_lz, d_v, d_trace_ws;
   DevBuf<UtrDev> d_utrs;
@@ -75,6 +75,28 @@ struct scape_b200_handle {
   DevBuf<double> d_partials, d_counter;
   DevBuf<LabelDev> d_jobs;
   cudaEvent_t ev[8];
+  scape_b200_timing tm;
+  std::vector<std::pair<float, float>> busy;   // kernel intervals (ms since the fit's base event)
+  std::string err;
+  int rc = 0;
+  void release() {
+    d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
+    d_table.release(); d_tensor.release(); d_lz.release(); d_v.release(); d_trace_ws.release(); d_utrs.release();
+    d_rows.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
+    d_refs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
+    d_counter.release(); d_jobs.release();
+  }
+};
+
+constexpr int kMaxLanes = 4;
+
+struct scape_b200_handle {
+  int device = 0;
+  scape_b200_params P;
+  ModelConst mc;
+  Lane lanes[kMaxLanes];
+  int n_lanes = 2;
+  cudaEvent_t base_ev = nullptr;
   scape_b200_timing tm;
   double wave_budget_bytes = 24e9;
   bool tensor_f32 = true;   // tensor storage: FP32 (default) or FP64; all arithmetic is FP64 either way
@@ -148,12 +170,19 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   h->device = device;
   h->P = *params;
   fill_model_const(h->P, h->mc);
-  CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  for (Lane& L : h->lanes) {
+    CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    for (auto& e : L.ev) CU(cudaEventCreate(&e));
+    memset(&L.tm, 0, sizeof(L.tm));
+  }
+  CU(cudaEventCreate(&h->base_ev));
+  CU(cudaEventRecord(h->base_ev, 0));
+  CU(cudaEventSynchronize(h->base_ev));
   memset(&h->tm, 0, sizeof(h->tm));
   if (const char* s = getenv("SCAPE_B200_WAVE_GB")) h->wave_budget_bytes = atof(s) * 1e9;
   if (const char* s = getenv("SCAPE_B200_THREADS")) h->host_threads = atoi(s);
   if (const char* s = getenv("SCAPE_B200_TENSOR")) h->tensor_f32 = (strcmp(s, "f64") != 0);
+  if (const char* s = getenv("SCAPE_B200_LANES")) h->n_lanes = std::max(1, std::min(kMaxLanes, atoi(s)));
   *out = h;
   return 0;
 }
@@ -161,15 +190,13 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
 int scape_b200_destroy(scape_b200_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->st);
-  h->d_fx.release(); h->d_fl.release(); h->d_fr.release(); h->d_fpa.release(); h->d_cnt.release();
-  h->d_theta.release(); h->d_table.release(); h->d_tensor.release(); h->d_lz.release(); h->d_v.release();
-  h->d_trace_ws.release(); h->d_utrs.release(); h->d_rows.release(); h->d_chains.release();
-  h->d_refs.release(); h->d_descs.release(); h->d_chain_off.release(); h->d_chain_idx.release(); h->d_partials.release(); h->d_counter.release();
-  h->d_labels.release(); h->d_trace_a.release(); h->d_trace_b.release();
-  h->d_jobs.release();
-  for (auto& e : h->ev) cudaEventDestroy(e);
-  cudaStreamDestroy(h->st);
+  for (Lane& L : h->lanes) {
+    cudaStreamSynchronize(L.st);
+    L.release();
+    for (auto& e : L.ev) cudaEventDestroy(e);
+    cudaStreamDestroy(L.st);
+  }
+  cudaEventDestroy(h->base_ev);
   delete h;
   return 0;
 }
@@ -217,7 +244,7 @@ int np_argmin(const std::vector<double>& v) {
 
 // Upload chains, run them (NROUND bulk-synchronous steps), bring them back.  `utrs_host` is the
 // wave's UtrDev array; chains must be ordered by UTR (they are generated that way).
-int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::vector<UtrDev>& utrs_host,
+int run_chains(scape_b200_handle* h, Lane& L, std::vector<ChainDev>& chains, const std::vector<UtrDev>& utrs_host,
                bool want_trace = false) {
   if (chains.empty()) return 0;
   const size_t W = utrs_host.size();
@@ -263,50 +290,52 @@ int run_chains(scape_b200_handle* h, std::vector<ChainDev>& chains, const std::v
       const int32_t n_blk = int32_t((int64_t(utrs_host[i].T) * utrs_host[i].B + kScanRows - 1) / kScanRows);
       for (int32_t b = 0; b < n_blk; b++) refs.push_back(ScanRef{int32_t(i), b});
     }
-  CU(h->d_lz.ensure(size_t(lz)));
-  CU(h->d_v.ensure(size_t(vsz + 8)));
-  CU(h->d_chains.ensure(chains.size()));
-  CU(h->d_chain_off.ensure(W + 1));
-  CU(h->d_descs.ensure(chains.size()));
-  CU(cudaMemsetAsync(h->d_descs.p, 0, sizeof(ScanDesc) * chains.size(), h->st));
-  CU(h->d_chain_idx.ensure(index.size()));
-  CU(h->d_refs.ensure(refs.size() + 1));
-  CU(h->d_partials.ensure(size_t(pb) * 2 + 2));
-  CU(h->d_counter.ensure(1));
+  CU(L.d_lz.ensure(size_t(lz)));
+  CU(L.d_v.ensure(size_t(vsz + 8)));
+  CU(L.d_chains.ensure(chains.size()));
+  CU(L.d_chain_off.ensure(W + 1));
+  CU(L.d_descs.ensure(chains.size()));
+  CU(cudaMemsetAsync(L.d_descs.p, 0, sizeof(ScanDesc) * chains.size(), L.st));
+  CU(L.d_chain_idx.ensure(index.size()));
+  CU(L.d_refs.ensure(refs.size() + 1));
+  CU(L.d_partials.ensure(size_t(pb) * 2 + 2));
+  CU(L.d_counter.ensure(1));
   if (want_trace) {
-    CU(h->d_trace_a.ensure(size_t(tr)));
-    CU(h->d_trace_b.ensure(size_t(tr)));
-    CU(h->d_trace_ws.ensure(size_t(tr)));
+    CU(L.d_trace_a.ensure(size_t(tr)));
+    CU(L.d_trace_b.ensure(size_t(tr)));
+    CU(L.d_trace_ws.ensure(size_t(tr)));
   }
-  CU(cudaMemcpyAsync(h->d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_chain_off.p, chain_off.data(), sizeof(int32_t) * (W + 1), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_chain_idx.p, index.data(), sizeof(int32_t) * index.size(), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(L.d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_chain_off.p, chain_off.data(), sizeof(int32_t) * (W + 1), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_chain_idx.p, index.data(), sizeof(int32_t) * index.size(), cudaMemcpyHostToDevice, L.st));
   if (!refs.empty())
-    CU(cudaMemcpyAsync(h->d_refs.p, refs.data(), sizeof(ScanRef) * refs.size(), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemsetAsync(h->d_counter.p, 0, sizeof(double), h->st));
-  h->tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * refs.size() + 4 * (W + 1));
-  CU(cudaEventRecord(h->ev[4], h->st));
-  int nl = launch_em_steps(h->d_chains.p, h->d_descs.p, h->d_chain_idx.p, n_small, n_big, any_scan, h->d_refs.p, int64_t(refs.size()),
-                           h->d_utrs.p, h->d_chain_off.p, h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_lz.p,
-                           h->d_v.p, h->d_partials.p, h->d_counter.p, h->d_trace_a.p, h->d_trace_b.p,
-                           h->d_trace_ws.p, h->st);
+    CU(cudaMemcpyAsync(L.d_refs.p, refs.data(), sizeof(ScanRef) * refs.size(), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemsetAsync(L.d_counter.p, 0, sizeof(double), L.st));
+  L.tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * refs.size() + 4 * (W + 1));
+  CU(cudaEventRecord(L.ev[4], L.st));
+  int nl = launch_em_steps(L.d_chains.p, L.d_descs.p, L.d_chain_idx.p, n_small, n_big, any_scan, L.d_refs.p, int64_t(refs.size()),
+                           L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_lz.p,
+                           L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
+                           L.d_trace_ws.p, L.st);
   CU(cudaGetLastError());
-  CU(cudaEventRecord(h->ev[5], h->st));
+  CU(cudaEventRecord(L.ev[5], L.st));
   double scan_elems = 0;
-  CU(cudaMemcpyAsync(chains.data(), h->d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaMemcpyAsync(&scan_elems, h->d_counter.p, sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
-  h->tm.d2h_bytes += double(sizeof(ChainDev) * chains.size());
-  float ms = 0;
-  CU(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
-  h->tm.em_ms += ms;
-  h->tm.launches += nl;
+  CU(cudaMemcpyAsync(chains.data(), L.d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, L.st));
+  CU(cudaMemcpyAsync(&scan_elems, L.d_counter.p, sizeof(double), cudaMemcpyDeviceToHost, L.st));
+  CU(cudaStreamSynchronize(L.st));
+  L.tm.d2h_bytes += double(sizeof(ChainDev) * chains.size());
+  float ms = 0, t0 = 0;
+  CU(cudaEventElapsedTime(&ms, L.ev[4], L.ev[5]));
+  CU(cudaEventElapsedTime(&t0, h->base_ev, L.ev[4]));
+  L.tm.em_ms += ms;
+  L.busy.emplace_back(t0, t0 + ms);
+  L.tm.launches += nl;
   for (auto& c : chains) {
     const UtrDev& u = utrs_host[size_t(c.utr)];
-    h->tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;     // FP64 tensor, one chain at a time
-    h->tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
+    L.tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;     // FP64 tensor, one chain at a time
+    L.tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
   }
-  h->tm.em_scan_bytes += scan_elems * (h->tensor_f32 ? 4.0 : 8.0);   // what the blocked scan really loads
+  L.tm.em_scan_bytes += scan_elems * (h->tensor_f32 ? 4.0 : 8.0);   // what the blocked scan really loads
   return 0;
 }
 
@@ -331,6 +360,310 @@ void parallel_for(int64_t n, int threads, const std::function<void(int64_t)>& fn
 }
 }  // namespace
 
+namespace {
+
+struct FitShared {
+  scape_b200_handle* h;
+  const scape_b200_batch* bt;
+  scape_b200_results* out;
+  std::vector<UtrPrep>* prep;
+  std::vector<std::vector<int64_t>>* stream_utrs;
+  std::vector<NpRandomState>* rng;
+  std::vector<size_t>* cursor;
+  std::vector<int32_t>* stream_of;
+  int maxwin;
+  int lane_threads;
+};
+
+// The wave loop of one lane over its own streams.
+int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
+  scape_b200_handle* h = F.h;
+  const scape_b200_batch* bt = F.bt;
+  scape_b200_results* out = F.out;
+  const scape_b200_params& P = h->P;
+  std::vector<UtrPrep>& prep = *F.prep;
+  std::vector<std::vector<int64_t>>& stream_utrs = *F.stream_utrs;
+  std::vector<NpRandomState>& rng = *F.rng;
+  std::vector<size_t>& cursor = *F.cursor;
+  std::vector<int32_t>& stream_of = *F.stream_of;
+  const int maxwin = F.maxwin, lane_threads = F.lane_threads;
+  CU(cudaSetDevice(h->device));
+  for (;;) {
+    // ---- pick the wave: next UTR of every stream, within the memory budget ---------------------
+    std::vector<WaveUtr> wave;
+    double bytes = 0;
+    for (int s : my_streams) {
+      while (cursor[size_t(s)] < stream_utrs[size_t(s)].size()) {
+        int64_t u = stream_utrs[size_t(s)][cursor[size_t(s)]];
+        if (prep[size_t(u)].status != kOk) { cursor[size_t(s)]++; continue; }   // the reference would have raised
+        const UtrPrep& p = prep[size_t(u)];
+        double need = double(p.T() * p.B() + 4) * pad4(p.n()) * (h->tensor_f32 ? 4.0 : 8.0) + double(p.T()) * pad4(p.n()) * 8.0;
+        if (!wave.empty() && bytes + need > h->wave_budget_bytes) break;
+        bytes += need;
+        WaveUtr w;
+        w.u = u;
+        w.k_max = P.fixed_run_mode ? P.pre_K : P.n_max_apa;
+        w.k_min = P.fixed_run_mode ? P.pre_K : P.n_min_apa;
+        memset(&w.best, 0, sizeof(ChainDev));
+        wave.push_back(w);
+        cursor[size_t(s)]++;
+        break;
+      }
+    }
+    if (wave.empty()) break;
+    L.tm.waves++;
+
+    // ---- device layout of the wave --------------------------------------------------------------
+    const size_t W = wave.size();
+    std::vector<UtrDev> ud(W);
+    std::vector<RowRef> rows;
+    int64_t nf = 0, nt = 0, ntab = 0, nten = 0;
+    int max_n = 0;
+    for (size_t i = 0; i < W; i++) {
+      const UtrPrep& p = prep[size_t(wave[i].u)];
+      UtrDev& d = ud[i];
+      d.N = int32_t(p.n()); d.Npad = pad4(p.n()); d.T = int32_t(p.T()); d.B = int32_t(p.B());
+      d.ldR = pad4(int64_t(d.T) * d.B);
+      d.frag_off = nf; d.theta_off = nt; d.table_off = ntab; d.tensor_off = nten;
+      d.unif_loglik = p.unif_loglik;
+      nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += d.ldR * d.N;
+      max_n = std::max(max_n, d.Npad);
+      for (int t = 0; t < d.T; t++) rows.push_back({int32_t(i), t});
+    }
+    std::vector<double> hx(size_t(nf), 0.0), hl(size_t(nf), 0.0), hr(size_t(nf), 0.0), hpa(size_t(nf), 0.0),
+        hc(size_t(nf), 0.0), hth(static_cast<size_t>(nt));
+    for (size_t i = 0; i < W; i++) {
+      const UtrPrep& p = prep[size_t(wave[i].u)];
+      std::copy(p.x.begin(), p.x.end(), hx.begin() + ud[i].frag_off);
+      std::copy(p.l.begin(), p.l.end(), hl.begin() + ud[i].frag_off);
+      std::copy(p.r.begin(), p.r.end(), hr.begin() + ud[i].frag_off);
+      std::copy(p.pa.begin(), p.pa.end(), hpa.begin() + ud[i].frag_off);
+      std::copy(p.cnt.begin(), p.cnt.end(), hc.begin() + ud[i].frag_off);
+      std::copy(p.theta.begin(), p.theta.end(), hth.begin() + ud[i].theta_off);
+    }
+    CU(L.d_fx.ensure(size_t(nf))); CU(L.d_fl.ensure(size_t(nf))); CU(L.d_fr.ensure(size_t(nf)));
+    CU(L.d_fpa.ensure(size_t(nf))); CU(L.d_cnt.ensure(size_t(nf))); CU(L.d_theta.ensure(size_t(nt)));
+    CU(L.d_table.ensure(size_t(ntab))); CU(L.d_tensor.ensure(size_t(nten)));
+    CU(L.d_utrs.ensure(W)); CU(L.d_rows.ensure(rows.size()));
+    const size_t fb = sizeof(double) * size_t(nf);
+    CU(cudaMemcpyAsync(L.d_fx.p, hx.data(), fb, cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_fl.p, hl.data(), fb, cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_fr.p, hr.data(), fb, cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_fpa.p, hpa.data(), fb, cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_cnt.p, hc.data(), fb, cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_theta.p, hth.data(), sizeof(double) * size_t(nt), cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_utrs.p, ud.data(), sizeof(UtrDev) * W, cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, L.st));
+    L.tm.h2d_bytes += double(5 * fb + sizeof(double) * size_t(nt) + sizeof(UtrDev) * W + sizeof(RowRef) * rows.size());
+
+    // ---- likelihood phases ----------------------------------------------------------------------
+    CU(cudaEventRecord(L.ev[0], L.st));
+    launch_table(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), max_n, L.d_fx.p, L.d_fl.p, L.d_fr.p,
+                 L.d_fpa.p, L.d_theta.p, L.d_table.p, L.st);
+    CU(cudaEventRecord(L.ev[1], L.st));
+    launch_tensor(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), max_n, P.n_beta, maxwin, L.d_theta.p,
+                  L.d_table.p, L.d_tensor.p, h->tensor_f32, L.st);
+    CU(cudaEventRecord(L.ev[2], L.st));
+    CU(cudaGetLastError());
+    L.tm.launches += 2;
+    for (size_t i = 0; i < W; i++) {
+      // exp() evaluations = N * sum over (t, beta) of the clipped window sizes (regular grid)
+      const UtrDev& d = ud[i];
+      double win = 0;
+      for (int j = 0; j < P.n_beta; j++) {
+        const int half = int(std::floor(3 * P.betas[j] / P.theta_step));
+        for (int t = 0; t < d.T; t++) win += std::min(d.T - 1, t + half) - std::max(0, t - half) + 1;
+      }
+      L.tm.tensor_exp += double(d.N) * win;
+    }
+    bool timed_lik = false;
+
+    // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
+    for (;;) {
+      std::vector<ChainDev> chains;
+      double tr0 = now_ms();
+      // RNG replay is serial per stream but streams are independent: one task per UTR of the wave
+      std::vector<std::vector<ChainDev>> drawn(W);
+      parallel_for(int64_t(W), lane_threads, [&](int64_t ii) {
+        const size_t i = size_t(ii);
+        WaveUtr& w = wave[i];
+        if (w.done) return;
+        const UtrPrep& p = prep[size_t(w.u)];
+        NpRandomState& g = rng[size_t(stream_of[size_t(w.u)])];
+        std::vector<ChainDev>& mine = drawn[i];
+        mine.reserve(size_t(w.k_max - w.k_min + 1) * SCAPE_B200_NTRIAL);
+        for (int K = w.k_max; K >= w.k_min && !w.done; K--)
+          for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++) {
+            ChainInit ci;
+            int32_t rc = draw_chain(g, P, p, K, ci);
+            if (rc != kOk) {       // numpy's choice() would have raised inside the reference
+              out->status[w.u] = rc;
+              w.done = true;
+              mine.clear();
+              break;
+            }
+            ChainDev c;
+            memset(&c, 0, sizeof(c));
+            c.utr = int32_t(i); c.K = K; c.weights_only = 0;
+            memcpy(c.a_idx, ci.a_idx, sizeof(ci.a_idx));
+            memcpy(c.b_idx, ci.b_idx, sizeof(ci.b_idx));
+            memcpy(c.ws, ci.ws, sizeof(ci.ws));
+            memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
+            mine.push_back(c);
+          }
+      });
+      for (size_t i = 0; i < W; i++) chains.insert(chains.end(), drawn[i].begin(), drawn[i].end());
+      L.tm.host_rng_ms += now_ms() - tr0;
+      if (chains.empty()) break;
+      if (int rc = run_chains(h, L, chains, ud)) return rc;
+      if (!timed_lik) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, L.ev[0], L.ev[1]));
+        CU(cudaEventElapsedTime(&b, L.ev[1], L.ev[2]));
+        L.tm.table_ms += a;
+        L.tm.tensor_ms += b;
+        float tb = 0;
+        CU(cudaEventElapsedTime(&tb, h->base_ev, L.ev[0]));
+        L.busy.emplace_back(tb, tb + a + b);
+        timed_lik = true;
+      }
+      // ---- selection (em_optim0 :865, run :972) + pruning (rm_component :832-844) -----------------
+      std::vector<ChainDev> refits;
+      std::vector<size_t> refit_owner;
+      tr0 = now_ms();
+      size_t pos = 0;
+      for (size_t i = 0; i < W; i++) {
+        WaveUtr& w = wave[i];
+        if (w.done) continue;
+        const int nK = w.k_max - w.k_min + 1;
+        std::vector<double> bic_k(static_cast<size_t>(nK));
+        std::vector<size_t> best_k(static_cast<size_t>(nK));
+        for (int ik = 0; ik < nK; ik++) {
+          std::vector<double> b(SCAPE_B200_NTRIAL);
+          for (int t = 0; t < SCAPE_B200_NTRIAL; t++) {
+            const ChainDev& c = chains[pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(t)];
+            b[size_t(t)] = c.bic;
+            w.work += double(c.n_iter) * ud[i].N * (c.K + 1);
+            w.iters += c.n_iter;
+          }
+          int m = np_argmin(b);
+          best_k[size_t(ik)] = pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(m);
+          bic_k[size_t(ik)] = b[size_t(m)];
+        }
+        pos += size_t(nK) * SCAPE_B200_NTRIAL;
+        w.chains_run += nK * SCAPE_B200_NTRIAL;
+        w.sweeps++;
+        w.best = chains[best_k[size_t(np_argmin(bic_k))]];
+        w.k_selected = w.best.K;
+        if (!P.fixed_run_mode) {
+          int keep[SCAPE_B200_KCAP], nk = 0;
+          for (int k = 0; k < w.best.K; k++)
+            if (!(w.best.ws[k] < P.min_ws)) keep[nk++] = k;
+          if (nk < w.best.K) {
+            ChainDev c;
+            memset(&c, 0, sizeof(c));
+            c.utr = int32_t(i); c.K = nk; c.weights_only = 1;
+            for (int k = 0; k < nk; k++) { c.a_idx[k] = w.best.a_idx[keep[k]]; c.b_idx[k] = w.best.b_idx[keep[k]]; }
+            ChainInit ci;
+            ci.K = nk;
+            draw_refit(rng[size_t(stream_of[size_t(w.u)])], P, ci);
+            memcpy(c.ws, ci.ws, sizeof(ci.ws));
+            memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
+            refits.push_back(c);
+            refit_owner.push_back(i);
+          }
+        }
+      }
+      L.tm.host_rng_ms += now_ms() - tr0;
+      if (int rc = run_chains(h, L, refits, ud)) return rc;
+      for (size_t j = 0; j < refits.size(); j++) {
+        WaveUtr& w = wave[refit_owner[j]];
+        w.best = refits[j];
+        w.chains_run += 1;
+        w.work += double(refits[j].n_iter) * ud[refit_owner[j]].N * (refits[j].K + 1);
+        w.iters += refits[j].n_iter;
+      }
+      bool again = false;
+      for (size_t i = 0; i < W; i++) {
+        WaveUtr& w = wave[i];
+        if (w.done) continue;
+        if (!P.fixed_run_mode && P.re_run_mode && w.best.K == w.k_max) {
+          if (w.k_max + 2 > SCAPE_B200_KCAP) {
+            out->status[w.u] = kErrKcap;
+            w.done = true;
+          } else {
+            w.k_min = w.k_max;
+            w.k_max += 2;
+            again = true;
+          }
+        } else {
+          w.done = true;
+        }
+      }
+      if (!again) break;
+    }
+
+    // ---- labels (get_label :873-881) + per-read expansion (:976) --------------------------------
+    std::vector<LabelDev> jobs(W);
+    int64_t nl = 0;
+    for (size_t i = 0; i < W; i++) {
+      LabelDev& j = jobs[i];
+      memset(&j, 0, sizeof(j));
+      j.utr = int32_t(i); j.K = wave[i].best.K; j.out_off = nl;
+      memcpy(j.a_idx, wave[i].best.a_idx, sizeof(j.a_idx));
+      memcpy(j.b_idx, wave[i].best.b_idx, sizeof(j.b_idx));
+      memcpy(j.ws, wave[i].best.ws, sizeof(j.ws));
+      nl += ud[i].N;
+    }
+    CU(L.d_jobs.ensure(W));
+    CU(L.d_labels.ensure(size_t(nl)));
+    CU(cudaMemcpyAsync(L.d_jobs.p, jobs.data(), sizeof(LabelDev) * W, cudaMemcpyHostToDevice, L.st));
+    CU(cudaEventRecord(L.ev[6], L.st));
+    launch_labels(L.d_jobs.p, int64_t(W), max_n, L.d_utrs.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_labels.p,
+                L.st);
+    CU(cudaEventRecord(L.ev[7], L.st));
+    CU(cudaGetLastError());
+    L.tm.launches += 1;
+    std::vector<int32_t> lab(static_cast<size_t>(nl));
+    CU(cudaMemcpyAsync(lab.data(), L.d_labels.p, sizeof(int32_t) * size_t(nl), cudaMemcpyDeviceToHost, L.st));
+    CU(cudaStreamSynchronize(L.st));
+    L.tm.h2d_bytes += double(sizeof(LabelDev) * W);
+    L.tm.d2h_bytes += double(sizeof(int32_t) * size_t(nl));
+    {
+      float a = 0;
+      CU(cudaEventElapsedTime(&a, L.ev[6], L.ev[7]));
+      L.tm.label_ms += a;
+      float tb = 0;
+      CU(cudaEventElapsedTime(&tb, h->base_ev, L.ev[6]));
+      L.busy.emplace_back(tb, tb + a);
+    }
+    for (size_t i = 0; i < W; i++) {
+      const WaveUtr& w = wave[i];
+      const UtrPrep& p = prep[size_t(w.u)];
+      const int64_t u = w.u;
+      const ChainDev& c = w.best;
+      out->K[u] = c.K;
+      for (int k = 0; k < c.K; k++) {
+        out->alpha[u * SCAPE_B200_KCAP + k] = std::nearbyint(p.theta[size_t(c.a_idx[k])]);   // np.rint (:770)
+        out->beta[u * SCAPE_B200_KCAP + k] = p.betas[size_t(c.b_idx[k])];
+      }
+      for (int k = 0; k <= c.K; k++) out->ws[u * (SCAPE_B200_KCAP + 1) + k] = c.ws[k];
+      out->bic[u] = c.bic;
+      out->n_lb[u] = c.n_iter;
+      for (int k = 0; k < c.n_iter; k++) out->lb_arr[u * SCAPE_B200_NROUND + k] = c.lb_arr[k];
+      out->path[u * 4 + 0] = w.sweeps; out->path[u * 4 + 1] = w.k_selected;
+      out->path[u * 4 + 2] = c.K; out->path[u * 4 + 3] = w.chains_run;
+      out->em_work[u * 2] = w.work; out->em_work[u * 2 + 1] = w.iters;
+      const int32_t* lb = lab.data() + jobs[i].out_off;
+      int64_t* dst = out->label + bt->read_off[u];
+      for (int64_t r = 0; r < p.n_reads; r++) dst[r] = lb[p.read_to_bin[size_t(r)]];
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
 extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch* bt, scape_b200_results* out) {
   if (!h || !bt || !out) return fail(-5, "null argument");
   CU(cudaSetDevice(h->device));
@@ -339,6 +672,8 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   memset(&h->tm, 0, sizeof(h->tm));
   const double t_begin = now_ms();
   CU(upload_model_const(h->mc));
+  CU(cudaEventRecord(h->base_ev, 0));
+  CU(cudaEventSynchronize(h->base_ev));
 
   // ---- host pre-pass (RNG free), parallel over UTRs -------------------------------------------
   std::vector<UtrPrep> prep(static_cast<size_t>(U));
@@ -390,271 +725,50 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   std::vector<int32_t> stream_of(static_cast<size_t>(U));
   for (int64_t u = 0; u < U; u++) stream_of[size_t(u)] = bt->stream_id[u];
 
-  for (;;) {
-    // ---- pick the wave: next UTR of every stream, within the memory budget ---------------------
-    std::vector<WaveUtr> wave;
-    double bytes = 0;
-    for (int s = 0; s < S; s++) {
-      while (cursor[size_t(s)] < stream_utrs[size_t(s)].size()) {
-        int64_t u = stream_utrs[size_t(s)][cursor[size_t(s)]];
-        if (prep[size_t(u)].status != kOk) { cursor[size_t(s)]++; continue; }   // the reference would have raised
-        const UtrPrep& p = prep[size_t(u)];
-        double need = double(p.T() * p.B() + 4) * pad4(p.n()) * (h->tensor_f32 ? 4.0 : 8.0) + double(p.T()) * pad4(p.n()) * 8.0;
-        if (!wave.empty() && bytes + need > h->wave_budget_bytes) break;
-        bytes += need;
-        WaveUtr w;
-        w.u = u;
-        w.k_max = P.fixed_run_mode ? P.pre_K : P.n_max_apa;
-        w.k_min = P.fixed_run_mode ? P.pre_K : P.n_min_apa;
-        memset(&w.best, 0, sizeof(ChainDev));
-        wave.push_back(w);
-        cursor[size_t(s)]++;
-        break;
-      }
-    }
-    if (wave.empty()) break;
-    h->tm.waves++;
-
-    // ---- device layout of the wave --------------------------------------------------------------
-    const size_t W = wave.size();
-    std::vector<UtrDev> ud(W);
-    std::vector<RowRef> rows;
-    int64_t nf = 0, nt = 0, ntab = 0, nten = 0;
-    int max_n = 0;
-    for (size_t i = 0; i < W; i++) {
-      const UtrPrep& p = prep[size_t(wave[i].u)];
-      UtrDev& d = ud[i];
-      d.N = int32_t(p.n()); d.Npad = pad4(p.n()); d.T = int32_t(p.T()); d.B = int32_t(p.B());
-      d.ldR = pad4(int64_t(d.T) * d.B);
-      d.frag_off = nf; d.theta_off = nt; d.table_off = ntab; d.tensor_off = nten;
-      d.unif_loglik = p.unif_loglik;
-      nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += d.ldR * d.N;
-      max_n = std::max(max_n, d.Npad);
-      for (int t = 0; t < d.T; t++) rows.push_back({int32_t(i), t});
-    }
-    std::vector<double> hx(size_t(nf), 0.0), hl(size_t(nf), 0.0), hr(size_t(nf), 0.0), hpa(size_t(nf), 0.0),
-        hc(size_t(nf), 0.0), hth(static_cast<size_t>(nt));
-    for (size_t i = 0; i < W; i++) {
-      const UtrPrep& p = prep[size_t(wave[i].u)];
-      std::copy(p.x.begin(), p.x.end(), hx.begin() + ud[i].frag_off);
-      std::copy(p.l.begin(), p.l.end(), hl.begin() + ud[i].frag_off);
-      std::copy(p.r.begin(), p.r.end(), hr.begin() + ud[i].frag_off);
-      std::copy(p.pa.begin(), p.pa.end(), hpa.begin() + ud[i].frag_off);
-      std::copy(p.cnt.begin(), p.cnt.end(), hc.begin() + ud[i].frag_off);
-      std::copy(p.theta.begin(), p.theta.end(), hth.begin() + ud[i].theta_off);
-    }
-    CU(h->d_fx.ensure(size_t(nf))); CU(h->d_fl.ensure(size_t(nf))); CU(h->d_fr.ensure(size_t(nf)));
-    CU(h->d_fpa.ensure(size_t(nf))); CU(h->d_cnt.ensure(size_t(nf))); CU(h->d_theta.ensure(size_t(nt)));
-    CU(h->d_table.ensure(size_t(ntab))); CU(h->d_tensor.ensure(size_t(nten)));
-    CU(h->d_utrs.ensure(W)); CU(h->d_rows.ensure(rows.size()));
-    const size_t fb = sizeof(double) * size_t(nf);
-    CU(cudaMemcpyAsync(h->d_fx.p, hx.data(), fb, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->d_fl.p, hl.data(), fb, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->d_fr.p, hr.data(), fb, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->d_fpa.p, hpa.data(), fb, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->d_cnt.p, hc.data(), fb, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->d_theta.p, hth.data(), sizeof(double) * size_t(nt), cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->d_utrs.p, ud.data(), sizeof(UtrDev) * W, cudaMemcpyHostToDevice, h->st));
-    CU(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, h->st));
-    h->tm.h2d_bytes += double(5 * fb + sizeof(double) * size_t(nt) + sizeof(UtrDev) * W + sizeof(RowRef) * rows.size());
-
-    // ---- likelihood phases ----------------------------------------------------------------------
-    CU(cudaEventRecord(h->ev[0], h->st));
-    launch_table(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), max_n, h->d_fx.p, h->d_fl.p, h->d_fr.p,
-                 h->d_fpa.p, h->d_theta.p, h->d_table.p, h->st);
-    CU(cudaEventRecord(h->ev[1], h->st));
-    launch_tensor(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), max_n, P.n_beta, maxwin, h->d_theta.p,
-                  h->d_table.p, h->d_tensor.p, h->tensor_f32, h->st);
-    CU(cudaEventRecord(h->ev[2], h->st));
-    CU(cudaGetLastError());
-    h->tm.launches += 2;
-    for (size_t i = 0; i < W; i++) {
-      // exp() evaluations = N * sum over (t, beta) of the clipped window sizes (regular grid)
-      const UtrDev& d = ud[i];
-      double win = 0;
-      for (int j = 0; j < P.n_beta; j++) {
-        const int half = int(std::floor(3 * P.betas[j] / P.theta_step));
-        for (int t = 0; t < d.T; t++) win += std::min(d.T - 1, t + half) - std::max(0, t - half) + 1;
-      }
-      h->tm.tensor_exp += double(d.N) * win;
-    }
-    bool timed_lik = false;
-
-    // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
-    for (;;) {
-      std::vector<ChainDev> chains;
-      double tr0 = now_ms();
-      // RNG replay is serial per stream but streams are independent: one task per UTR of the wave
-      std::vector<std::vector<ChainDev>> drawn(W);
-      parallel_for(int64_t(W), h->host_threads, [&](int64_t ii) {
-        const size_t i = size_t(ii);
-        WaveUtr& w = wave[i];
-        if (w.done) return;
-        const UtrPrep& p = prep[size_t(w.u)];
-        NpRandomState& g = rng[size_t(stream_of[size_t(w.u)])];
-        std::vector<ChainDev>& mine = drawn[i];
-        mine.reserve(size_t(w.k_max - w.k_min + 1) * SCAPE_B200_NTRIAL);
-        for (int K = w.k_max; K >= w.k_min && !w.done; K--)
-          for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++) {
-            ChainInit ci;
-            int32_t rc = draw_chain(g, P, p, K, ci);
-            if (rc != kOk) {       // numpy's choice() would have raised inside the reference
-              out->status[w.u] = rc;
-              w.done = true;
-              mine.clear();
-              break;
-            }
-            ChainDev c;
-            memset(&c, 0, sizeof(c));
-            c.utr = int32_t(i); c.K = K; c.weights_only = 0;
-            memcpy(c.a_idx, ci.a_idx, sizeof(ci.a_idx));
-            memcpy(c.b_idx, ci.b_idx, sizeof(ci.b_idx));
-            memcpy(c.ws, ci.ws, sizeof(ci.ws));
-            memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
-            mine.push_back(c);
-          }
-      });
-      for (size_t i = 0; i < W; i++) chains.insert(chains.end(), drawn[i].begin(), drawn[i].end());
-      h->tm.host_rng_ms += now_ms() - tr0;
-      if (chains.empty()) break;
-      if (int rc = run_chains(h, chains, ud)) return rc;
-      if (!timed_lik) {
-        float a = 0, b = 0;
-        CU(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-        CU(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
-        h->tm.table_ms += a;
-        h->tm.tensor_ms += b;
-        timed_lik = true;
-      }
-      // ---- selection (em_optim0 :865, run :972) + pruning (rm_component :832-844) -----------------
-      std::vector<ChainDev> refits;
-      std::vector<size_t> refit_owner;
-      tr0 = now_ms();
-      size_t pos = 0;
-      for (size_t i = 0; i < W; i++) {
-        WaveUtr& w = wave[i];
-        if (w.done) continue;
-        const int nK = w.k_max - w.k_min + 1;
-        std::vector<double> bic_k(static_cast<size_t>(nK));
-        std::vector<size_t> best_k(static_cast<size_t>(nK));
-        for (int ik = 0; ik < nK; ik++) {
-          std::vector<double> b(SCAPE_B200_NTRIAL);
-          for (int t = 0; t < SCAPE_B200_NTRIAL; t++) {
-            const ChainDev& c = chains[pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(t)];
-            b[size_t(t)] = c.bic;
-            w.work += double(c.n_iter) * ud[i].N * (c.K + 1);
-            w.iters += c.n_iter;
-          }
-          int m = np_argmin(b);
-          best_k[size_t(ik)] = pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(m);
-          bic_k[size_t(ik)] = b[size_t(m)];
-        }
-        pos += size_t(nK) * SCAPE_B200_NTRIAL;
-        w.chains_run += nK * SCAPE_B200_NTRIAL;
-        w.sweeps++;
-        w.best = chains[best_k[size_t(np_argmin(bic_k))]];
-        w.k_selected = w.best.K;
-        if (!P.fixed_run_mode) {
-          int keep[SCAPE_B200_KCAP], nk = 0;
-          for (int k = 0; k < w.best.K; k++)
-            if (!(w.best.ws[k] < P.min_ws)) keep[nk++] = k;
-          if (nk < w.best.K) {
-            ChainDev c;
-            memset(&c, 0, sizeof(c));
-            c.utr = int32_t(i); c.K = nk; c.weights_only = 1;
-            for (int k = 0; k < nk; k++) { c.a_idx[k] = w.best.a_idx[keep[k]]; c.b_idx[k] = w.best.b_idx[keep[k]]; }
-            ChainInit ci;
-            ci.K = nk;
-            draw_refit(rng[size_t(stream_of[size_t(w.u)])], P, ci);
-            memcpy(c.ws, ci.ws, sizeof(ci.ws));
-            memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
-            refits.push_back(c);
-            refit_owner.push_back(i);
-          }
-        }
-      }
-      h->tm.host_rng_ms += now_ms() - tr0;
-      if (int rc = run_chains(h, refits, ud)) return rc;
-      for (size_t j = 0; j < refits.size(); j++) {
-        WaveUtr& w = wave[refit_owner[j]];
-        w.best = refits[j];
-        w.chains_run += 1;
-        w.work += double(refits[j].n_iter) * ud[refit_owner[j]].N * (refits[j].K + 1);
-        w.iters += refits[j].n_iter;
-      }
-      bool again = false;
-      for (size_t i = 0; i < W; i++) {
-        WaveUtr& w = wave[i];
-        if (w.done) continue;
-        if (!P.fixed_run_mode && P.re_run_mode && w.best.K == w.k_max) {
-          if (w.k_max + 2 > SCAPE_B200_KCAP) {
-            out->status[w.u] = kErrKcap;
-            w.done = true;
-          } else {
-            w.k_min = w.k_max;
-            w.k_max += 2;
-            again = true;
-          }
-        } else {
-          w.done = true;
-        }
-      }
-      if (!again) break;
-    }
-
-    // ---- labels (get_label :873-881) + per-read expansion (:976) --------------------------------
-    std::vector<LabelDev> jobs(W);
-    int64_t nl = 0;
-    for (size_t i = 0; i < W; i++) {
-      LabelDev& j = jobs[i];
-      memset(&j, 0, sizeof(j));
-      j.utr = int32_t(i); j.K = wave[i].best.K; j.out_off = nl;
-      memcpy(j.a_idx, wave[i].best.a_idx, sizeof(j.a_idx));
-      memcpy(j.b_idx, wave[i].best.b_idx, sizeof(j.b_idx));
-      memcpy(j.ws, wave[i].best.ws, sizeof(j.ws));
-      nl += ud[i].N;
-    }
-    CU(h->d_jobs.ensure(W));
-    CU(h->d_labels.ensure(size_t(nl)));
-    CU(cudaMemcpyAsync(h->d_jobs.p, jobs.data(), sizeof(LabelDev) * W, cudaMemcpyHostToDevice, h->st));
-    CU(cudaEventRecord(h->ev[6], h->st));
-    launch_labels(h->d_jobs.p, int64_t(W), max_n, h->d_utrs.p, h->d_tensor.p, h->tensor_f32, h->d_cnt.p, h->d_labels.p,
-                h->st);
-    CU(cudaEventRecord(h->ev[7], h->st));
-    CU(cudaGetLastError());
-    h->tm.launches += 1;
-    std::vector<int32_t> lab(static_cast<size_t>(nl));
-    CU(cudaMemcpyAsync(lab.data(), h->d_labels.p, sizeof(int32_t) * size_t(nl), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
-    h->tm.h2d_bytes += double(sizeof(LabelDev) * W);
-    h->tm.d2h_bytes += double(sizeof(int32_t) * size_t(nl));
-    {
-      float a = 0;
-      CU(cudaEventElapsedTime(&a, h->ev[6], h->ev[7]));
-      h->tm.label_ms += a;
-    }
-    for (size_t i = 0; i < W; i++) {
-      const WaveUtr& w = wave[i];
-      const UtrPrep& p = prep[size_t(w.u)];
-      const int64_t u = w.u;
-      const ChainDev& c = w.best;
-      out->K[u] = c.K;
-      for (int k = 0; k < c.K; k++) {
-        out->alpha[u * SCAPE_B200_KCAP + k] = std::nearbyint(p.theta[size_t(c.a_idx[k])]);   // np.rint (:770)
-        out->beta[u * SCAPE_B200_KCAP + k] = p.betas[size_t(c.b_idx[k])];
-      }
-      for (int k = 0; k <= c.K; k++) out->ws[u * (SCAPE_B200_KCAP + 1) + k] = c.ws[k];
-      out->bic[u] = c.bic;
-      out->n_lb[u] = c.n_iter;
-      for (int k = 0; k < c.n_iter; k++) out->lb_arr[u * SCAPE_B200_NROUND + k] = c.lb_arr[k];
-      out->path[u * 4 + 0] = w.sweeps; out->path[u * 4 + 1] = w.k_selected;
-      out->path[u * 4 + 2] = c.K; out->path[u * 4 + 3] = w.chains_run;
-      out->em_work[u * 2] = w.work; out->em_work[u * 2 + 1] = w.iters;
-      const int32_t* lb = lab.data() + jobs[i].out_off;
-      int64_t* dst = out->label + bt->read_off[u];
-      for (int64_t r = 0; r < p.n_reads; r++) dst[r] = lb[p.read_to_bin[size_t(r)]];
-    }
+  // ---- lanes: streams are dealt round-robin, every lane runs its waves in its own thread ---------
+  const int n_lanes = std::max(1, std::min(h->n_lanes, S));
+  std::vector<std::vector<int>> lane_streams(static_cast<size_t>(n_lanes));
+  for (int s = 0; s < S; s++) lane_streams[size_t(s % n_lanes)].push_back(s);
+  int total_threads = h->host_threads > 0 ? h->host_threads : int(std::thread::hardware_concurrency());
+  FitShared F{h, bt, out, &prep, &stream_utrs, &rng, &cursor, &stream_of, maxwin,
+              std::max(1, total_threads / n_lanes)};
+  for (int l = 0; l < n_lanes; l++) {
+    Lane& L = h->lanes[l];
+    memset(&L.tm, 0, sizeof(L.tm));
+    L.busy.clear();
+    L.rc = 0;
+    L.err.clear();
   }
+  {
+    std::vector<std::thread> workers;
+    for (int l = 0; l < n_lanes; l++)
+      workers.emplace_back([&, l]() {
+        Lane& L = h->lanes[l];
+        L.rc = run_lane(F, L, lane_streams[size_t(l)]);
+        if (L.rc) L.err = g_err;
+      });
+    for (auto& w : workers) w.join();
+  }
+  for (int l = 0; l < n_lanes; l++)
+    if (h->lanes[l].rc) return fail(h->lanes[l].rc, h->lanes[l].err);
+  // merge the lanes' accounting; device time = length of the union of all kernel intervals
+  std::vector<std::pair<float, float>> iv;
+  for (int l = 0; l < n_lanes; l++) {
+    const scape_b200_timing& t = h->lanes[l].tm;
+    h->tm.table_ms += t.table_ms; h->tm.tensor_ms += t.tensor_ms; h->tm.em_ms += t.em_ms; h->tm.label_ms += t.label_ms;
+    h->tm.host_rng_ms += t.host_rng_ms; h->tm.launches += t.launches; h->tm.waves += t.waves;
+    h->tm.em_grid_bytes += t.em_grid_bytes; h->tm.em_grid_flops += t.em_grid_flops; h->tm.tensor_exp += t.tensor_exp;
+    h->tm.h2d_bytes += t.h2d_bytes; h->tm.d2h_bytes += t.d2h_bytes; h->tm.em_scan_bytes += t.em_scan_bytes;
+    iv.insert(iv.end(), h->lanes[l].busy.begin(), h->lanes[l].busy.end());
+  }
+  std::sort(iv.begin(), iv.end());
+  double busy = 0, cur_a = 0, cur_b = -1;
+  for (auto& p : iv) {
+    if (p.first > cur_b) { if (cur_b > cur_a) busy += cur_b - cur_a; cur_a = p.first; cur_b = p.second; }
+    else cur_b = std::max<double>(cur_b, p.second);
+  }
+  if (cur_b > cur_a) busy += cur_b - cur_a;
+  h->tm.device_busy_ms = busy;     // device busy time: union of the kernel intervals of all lanes
   if (bt->stream_state)
     for (int s = 0; s < S; s++) {
       memcpy(bt->stream_state + size_t(s) * 625, rng[size_t(s)].key, 624 * sizeof(uint32_t));
@@ -671,6 +785,7 @@ extern "C" int scape_b200_loglik_table(scape_b200_handle* h, int64_t n_frag, con
                                        const double* r, const double* pa, int64_t n_theta, const double* theta,
                                        double* table_out) {
   if (!h) return fail(-5, "null handle");
+  Lane& L = h->lanes[0];
   CU(cudaSetDevice(h->device));
   CU(upload_model_const(h->mc));
   UtrDev d;
@@ -683,22 +798,22 @@ extern "C" int scape_b200_loglik_table(scape_b200_handle* h, int64_t n_frag, con
   std::vector<double> px(np_, 0.0), pl(np_, 0.0), pr(np_, 0.0), ppa(np_, 0.0);
   std::copy(x, x + n_frag, px.begin()); std::copy(l, l + n_frag, pl.begin());
   std::copy(r, r + n_frag, pr.begin()); std::copy(pa, pa + n_frag, ppa.begin());
-  CU(h->d_fx.ensure(np_)); CU(h->d_fl.ensure(np_)); CU(h->d_fr.ensure(np_)); CU(h->d_fpa.ensure(np_));
-  CU(h->d_theta.ensure(size_t(n_theta))); CU(h->d_table.ensure(size_t(n_theta) * np_));
-  CU(h->d_utrs.ensure(1)); CU(h->d_rows.ensure(rows.size()));
-  CU(cudaMemcpyAsync(h->d_fx.p, px.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_fl.p, pl.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_fr.p, pr.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_fpa.p, ppa.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_theta.p, theta, 8 * size_t(n_theta), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, h->st));
-  launch_table(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), d.Npad, h->d_fx.p, h->d_fl.p, h->d_fr.p, h->d_fpa.p,
-               h->d_theta.p, h->d_table.p, h->st);
+  CU(L.d_fx.ensure(np_)); CU(L.d_fl.ensure(np_)); CU(L.d_fr.ensure(np_)); CU(L.d_fpa.ensure(np_));
+  CU(L.d_theta.ensure(size_t(n_theta))); CU(L.d_table.ensure(size_t(n_theta) * np_));
+  CU(L.d_utrs.ensure(1)); CU(L.d_rows.ensure(rows.size()));
+  CU(cudaMemcpyAsync(L.d_fx.p, px.data(), 8 * np_, cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_fl.p, pl.data(), 8 * np_, cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_fr.p, pr.data(), 8 * np_, cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_fpa.p, ppa.data(), 8 * np_, cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_theta.p, theta, 8 * size_t(n_theta), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, L.st));
+  launch_table(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), d.Npad, L.d_fx.p, L.d_fl.p, L.d_fr.p, L.d_fpa.p,
+               L.d_theta.p, L.d_table.p, L.st);
   CU(cudaGetLastError());
   std::vector<double> tt(size_t(n_theta) * np_);
-  CU(cudaMemcpyAsync(tt.data(), h->d_table.p, 8 * tt.size(), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaStreamSynchronize(h->st));
+  CU(cudaMemcpyAsync(tt.data(), L.d_table.p, 8 * tt.size(), cudaMemcpyDeviceToHost, L.st));
+  CU(cudaStreamSynchronize(L.st));
   for (int64_t n = 0; n < n_frag; n++)
     for (int64_t t = 0; t < n_theta; t++) table_out[n * n_theta + t] = tt[size_t(t) * np_ + size_t(n)];
   return 0;
@@ -709,6 +824,7 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
                                           double* tensor_out) {
   if (!h) return fail(-5, "null handle");
   if (n_beta > SCAPE_B200_MAX_BETA) return fail(-5, "n_beta too large");
+  Lane& L = h->lanes[0];
   CU(cudaSetDevice(h->device));
   ModelConst mc = h->mc;
   mc.n_beta = int32_t(n_beta);
@@ -732,26 +848,26 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
   std::vector<double> tt(size_t(n_theta) * np_, 0.0);
   for (int64_t n = 0; n < n_frag; n++)
     for (int64_t t = 0; t < n_theta; t++) tt[size_t(t) * np_ + size_t(n)] = table[n * n_theta + t];
-  CU(h->d_theta.ensure(size_t(n_theta))); CU(h->d_table.ensure(tt.size()));
-  CU(h->d_tensor.ensure(size_t(d.ldR) * size_t(n_frag)));
-  CU(h->d_utrs.ensure(1)); CU(h->d_rows.ensure(rows.size()));
-  CU(cudaMemcpyAsync(h->d_theta.p, theta, 8 * size_t(n_theta), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_table.p, tt.data(), 8 * tt.size(), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, h->st));
-  launch_tensor(h->d_utrs.p, h->d_rows.p, int64_t(rows.size()), d.Npad, int(n_beta), maxwin, h->d_theta.p,
-                h->d_table.p, h->d_tensor.p, h->tensor_f32, h->st);
+  CU(L.d_theta.ensure(size_t(n_theta))); CU(L.d_table.ensure(tt.size()));
+  CU(L.d_tensor.ensure(size_t(d.ldR) * size_t(n_frag)));
+  CU(L.d_utrs.ensure(1)); CU(L.d_rows.ensure(rows.size()));
+  CU(cudaMemcpyAsync(L.d_theta.p, theta, 8 * size_t(n_theta), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_table.p, tt.data(), 8 * tt.size(), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, L.st));
+  launch_tensor(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), d.Npad, int(n_beta), maxwin, L.d_theta.p,
+                L.d_table.p, L.d_tensor.p, h->tensor_f32, L.st);
   CU(cudaGetLastError());
   const size_t Rr = size_t(n_theta) * size_t(n_beta), ldr = size_t(d.ldR);
   std::vector<double> ten(ldr * size_t(n_frag));
   if (h->tensor_f32) {
     std::vector<float> tf(ten.size());
-    CU(cudaMemcpyAsync(tf.data(), h->d_tensor.p, 4 * tf.size(), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
+    CU(cudaMemcpyAsync(tf.data(), L.d_tensor.p, 4 * tf.size(), cudaMemcpyDeviceToHost, L.st));
+    CU(cudaStreamSynchronize(L.st));
     for (size_t i = 0; i < tf.size(); i++) ten[i] = double(tf[i]);
   } else {
-    CU(cudaMemcpyAsync(ten.data(), h->d_tensor.p, 8 * ten.size(), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
+    CU(cudaMemcpyAsync(ten.data(), L.d_tensor.p, 8 * ten.size(), cudaMemcpyDeviceToHost, L.st));
+    CU(cudaStreamSynchronize(L.st));
   }
   for (size_t n = 0; n < size_t(n_frag); n++)          // device [n][t][b] -> reference [t][b][n]
     for (size_t r = 0; r < Rr; r++) tensor_out[r * size_t(n_frag) + n] = ten[n * ldr + r];
@@ -763,6 +879,7 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
                                     const double* tensor, const double* cnt, double unif_loglik, int64_t n_chains,
                                     scape_b200_chain_io* io, int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
   if (!h) return fail(-5, "null handle");
+  Lane& L = h->lanes[0];
   CU(cudaSetDevice(h->device));
   CU(upload_model_const(h->mc));
   UtrDev d;
@@ -776,17 +893,17 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
   for (size_t n = 0; n < size_t(n_frag); n++)          // reference [t][b][n] -> device [n][t][b]
     for (size_t r = 0; r < Rr; r++) ten[n * ldr + r] = tensor[r * size_t(n_frag) + n];
   std::copy(cnt, cnt + n_frag, pc.begin());
-  CU(h->d_tensor.ensure(ten.size())); CU(h->d_cnt.ensure(np_)); CU(h->d_utrs.ensure(1));
+  CU(L.d_tensor.ensure(ten.size())); CU(L.d_cnt.ensure(np_)); CU(L.d_utrs.ensure(1));
   std::vector<float> tf;
   if (h->tensor_f32) {
     tf.resize(ten.size());
     for (size_t i = 0; i < ten.size(); i++) tf[i] = float(ten[i]);
-    CU(cudaMemcpyAsync(h->d_tensor.p, tf.data(), 4 * tf.size(), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(L.d_tensor.p, tf.data(), 4 * tf.size(), cudaMemcpyHostToDevice, L.st));
   } else {
-    CU(cudaMemcpyAsync(h->d_tensor.p, ten.data(), 8 * ten.size(), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(L.d_tensor.p, ten.data(), 8 * ten.size(), cudaMemcpyHostToDevice, L.st));
   }
-  CU(cudaMemcpyAsync(h->d_cnt.p, pc.data(), 8 * np_, cudaMemcpyHostToDevice, h->st));
-  CU(cudaMemcpyAsync(h->d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(L.d_cnt.p, pc.data(), 8 * np_, cudaMemcpyHostToDevice, L.st));
+  CU(cudaMemcpyAsync(L.d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, L.st));
   std::vector<UtrDev> ud(1, d);
   std::vector<ChainDev> chains(static_cast<size_t>(n_chains));
   for (int64_t i = 0; i < n_chains; i++) {
@@ -800,7 +917,7 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
     memcpy(c.k_order, io[i].k_order, SCAPE_B200_NROUND);
   }
   const bool want_trace = trace_a && trace_b && trace_ws;
-  if (int rc = run_chains(h, chains, ud, want_trace)) return rc;
+  if (int rc = run_chains(h, L, chains, ud, want_trace)) return rc;
   for (int64_t i = 0; i < n_chains; i++) {
     const ChainDev& c = chains[size_t(i)];
     memcpy(io[i].a_idx, c.a_idx, sizeof(c.a_idx));
@@ -812,9 +929,9 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
   }
   if (want_trace) {
     const size_t tr = size_t(n_chains) * SCAPE_B200_NROUND * (SCAPE_B200_KCAP + 1);
-    CU(cudaMemcpy(trace_a, h->d_trace_a.p, 4 * tr, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(trace_b, h->d_trace_b.p, 4 * tr, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(trace_ws, h->d_trace_ws.p, 8 * tr, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(trace_a, L.d_trace_a.p, 4 * tr, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(trace_b, L.d_trace_b.p, 4 * tr, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(trace_ws, L.d_trace_ws.p, 8 * tr, cudaMemcpyDeviceToHost));
   }
   return 0;
 }
