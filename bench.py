@@ -208,30 +208,42 @@ def main():
         return
 
     K = args.steps
-    peak, peak_src = measured_peaks()
-    em_s = acc["em_ms"] / 1e3
-    achieved = acc["em_grid_bytes"] / em_s / 1e9
+    hbm_peak, hbm_src = measured_peaks()
+    fp64 = eng.fp64_peaks()                     # measured on this GPU, this run (no FP64 entry in MEASURED_PEAKS.json)
+    scan_s = acc["scan_ms"] / 1e3
+    ach_tflops = acc["em_grid_flops"] / scan_s / 1e12
     res = {
         "metric": "infer_pa_utrs_per_s", "value": utr_all * K / (dev_ms / 1e3), "unit": "UTR/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"cfg-2: synthetic {args.utrs} UTRs x {args.reads} reads per GPU, Kmax=5, "
                                f"{n_files} chunk files = RNG streams (seed 1 each)",
-                   "seed_policy": "file", "l2": "per-wave tensor working set (~0.4 GB) exceeds the 126 MB L2",
-                   "value_time": "GPU busy time = union of the CUDA-event kernel intervals of all lanes", "e2e_time": "wall clock of Engine.fit on host buffers"},
+                   "seed_policy": "file", "tensor_storage": "f32 (FP64 arithmetic)",
+                   "l2": "per-wave tensor working set (~0.26 GB) exceeds the 126 MB L2; nothing is flushed between steps, "
+                         "every step streams 100 waves x 0.26 GB",
+                   "value_time": "GPU busy time = union of the CUDA-event kernel intervals of all lanes",
+                   "e2e_time": "wall clock of Engine.fit (C ABI scape_b200_fit_batch) on host buffers"},
         "read_comp_em_iter_per_s": work_all * K / (dev_ms / 1e3),
         "read_comp_em_iter_per_s_e2e": work_all * K / wall,
         "em_iterations_per_step": iters,
         "e2e": {"value": utr_all * K / wall, "unit": "UTR/s", "h2d_bytes_per_step": acc["h2d_bytes"] / K,
                 "d2h_bytes_per_step": acc["d2h_bytes"] / K, "ms_per_step": 1e3 * wall / K},
         "gpu_launches": int(acc["launches"]),
-        "roofline": {"kernel": "em_chain_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch_group": acc["em_grid_bytes"] / K,
-                     "fp64_gflops": acc["em_grid_flops"] / em_s / 1e9,
-                     "note": "algorithmic bytes = 8*W_k*B*N per EM iteration (SURVEY 8d); the tensor is mostly L2-resident"},
-        "phases_ms_per_step": {k: acc[k] / K for k in ("table_ms", "tensor_ms", "em_ms", "label_ms", "host_prep_ms",
-                                                        "host_rng_ms", "total_ms")},
+        "roofline": {"kernel": "em_scan_kernel (max_alpha_beta grid arg-max as a blocked FP64 MMA product)",
+                     "bound": "tensor", "achieved": ach_tflops, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
+                     "frac": ach_tflops / fp64["dmma_tflops"], "traffic": None,
+                     "peak_source": "FP64 mma.m8n8k4 stream measured in this run (scape_b200_fp64_peaks); "
+                                    f"CUDA-core DFMA stream {fp64['dfma_tflops']:.1f} TFLOP/s",
+                     "algorithmic_flops_per_launch": acc["em_grid_flops"] / max(acc["scan_launches"], 1),
+                     "avg_launch_ms": acc["scan_ms"] / max(acc["scan_launches"], 1),
+                     "launches": int(acc["scan_launches"]),
+                     "share_of_gpu_time": acc["scan_ms"] / dev_ms,
+                     "hbm_view": {"algorithmic_GBps": acc["em_grid_bytes"] / scan_s / 1e9, "peak_GBps": hbm_peak,
+                                  "peak_source": hbm_src, "loaded_GBps": acc["em_scan_bytes"] / scan_s / 1e9,
+                                  "note": "SURVEY 8d algorithmic bytes = 8*W_k*B*N per chain iteration; the blocked scan "
+                                          "loads each tensor block once per step for all chains of the UTR"}},
+        "phases_ms_per_step": {k: acc[k] / K for k in ("table_ms", "tensor_ms", "em_ms", "estep_ms", "scan_ms", "label_ms",
+                                                        "host_prep_ms", "host_rng_ms", "device_busy_ms", "total_ms")},
         "tensor_exp_per_s": acc["tensor_exp"] / (acc["tensor_ms"] / 1e3),
         "waves_per_step": acc["waves"] / K,
         "clocks": clocks,

@@ -104,6 +104,8 @@ typedef struct scape_b200_timing {
   double tensor_exp;                              /* exp() evaluations of the marginal kernel  */
   double h2d_bytes, d2h_bytes;
   double em_scan_bytes;                           /* tensor bytes the grid search actually loads (fragment hull only) */
+  double estep_ms, scan_ms;                       /* em_ms split: E-step kernels / arg-max scan kernels */
+  int64_t scan_launches;
 } scape_b200_timing;
 
 typedef struct scape_b200_handle scape_b200_handle;
@@ -120,6 +122,11 @@ int scape_b200_destroy(scape_b200_handle* h);
  * rm_component, re-run loop, get_label) for every UTR of the batch. */
 int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch* batch, scape_b200_results* out);
 int scape_b200_get_timing(scape_b200_handle* h, scape_b200_timing* out);
+
+/* FP64 peak microbenchmarks on the handle's device (TFLOP/s, 2 flop per FMA): CUDA-core DFMA stream
+ * and tensor-core DMMA (mma.m8n8k4.f64) stream.  They are the roofline denominators of the EM
+ * kernels; MEASURED_PEAKS.json carries no FP64 figure. */
+int scape_b200_fp64_peaks(scape_b200_handle* h, double* dfma_tflops, double* dmma_tflops);
 
 /* Storage type of the marginal tensor in HBM: 4 = float (default; values are computed in FP64 and
  * rounded once, every sum / product stays FP64), 8 = double (strict mode).  Environment override at

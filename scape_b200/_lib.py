@@ -70,6 +70,7 @@ class Timing(C.Structure):
         ("launches", C.c_int64), ("waves", C.c_int64),
         ("em_grid_bytes", C.c_double), ("em_grid_flops", C.c_double), ("tensor_exp", C.c_double),
         ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("em_scan_bytes", C.c_double),
+        ("estep_ms", C.c_double), ("scan_ms", C.c_double), ("scan_launches", C.c_int64),
     ]
 
     def as_dict(self):
@@ -93,7 +94,7 @@ EXPORTS = [
     "scape_b200_destroy", "scape_b200_fit_batch", "scape_b200_get_timing", "scape_b200_loglik_table",
     "scape_b200_marginal_tensor", "scape_b200_em_chains", "scape_b200_bin_reads", "scape_b200_profile",
     "scape_b200_draw_chains", "scape_b200_rng_draw", "scape_b200_set_argsort_callback",
-    "scape_b200_set_tensor_dtype",
+    "scape_b200_set_tensor_dtype", "scape_b200_fp64_peaks",
 ]
 
 ARGSORT_FN = C.CFUNCTYPE(None, c_double_p, C.c_int64, c_int64_p)
@@ -129,6 +130,7 @@ def load():
     lib.scape_b200_fit_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Results)]
     lib.scape_b200_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     lib.scape_b200_set_tensor_dtype.argtypes = [C.c_void_p, C.c_int]
+    lib.scape_b200_fp64_peaks.argtypes = [C.c_void_p, c_double_p, c_double_p]
     lib.scape_b200_loglik_table.argtypes = [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
                                             C.c_int64, c_double_p, c_double_p]
     lib.scape_b200_marginal_tensor.argtypes = [C.c_void_p, C.c_int64, C.c_int64, c_double_p, C.c_int64, c_double_p,
@@ -300,6 +302,12 @@ class Engine:
         _check(self._lib.scape_b200_fit_batch(self._h, C.byref(b), C.byref(res)))
         out.timing = self.timing()
         return out
+
+    def fp64_peaks(self) -> dict:
+        """Measured FP64 TFLOP/s of this GPU: CUDA-core DFMA stream and tensor-core DMMA stream."""
+        a, b = C.c_double(), C.c_double()
+        _check(self._lib.scape_b200_fp64_peaks(self._h, C.byref(a), C.byref(b)))
+        return {"dfma_tflops": a.value, "dmma_tflops": b.value}
 
     def timing(self) -> dict:
         t = Timing()

@@ -75,6 +75,7 @@ struct Lane {
   DevBuf<double> d_partials, d_counter;
   DevBuf<LabelDev> d_jobs;
   cudaEvent_t ev[8];
+  EmStepEvents em_events;
   scape_b200_timing tm;
   std::vector<std::pair<float, float>> busy;   // kernel intervals (ms since the fit's base event)
   std::string err;
@@ -208,6 +209,15 @@ int scape_b200_set_tensor_dtype(scape_b200_handle* h, int bytes) {
   return 0;
 }
 
+int scape_b200_fp64_peaks(scape_b200_handle* h, double* dfma_tflops, double* dmma_tflops) {
+  if (!h || !dfma_tflops || !dmma_tflops) return fail(-5, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->device));
+  if (measure_fp64_peaks(prop.multiProcessorCount, dfma_tflops, dmma_tflops, h->lanes[0].st)) return fail(-100, "peak kernels failed");
+  return 0;
+}
+
 int scape_b200_get_timing(scape_b200_handle* h, scape_b200_timing* out) {
   if (!h || !out) return fail(-5, "null argument");
   *out = h->tm;
@@ -313,10 +323,12 @@ int run_chains(scape_b200_handle* h, Lane& L, std::vector<ChainDev>& chains, con
   CU(cudaMemsetAsync(L.d_counter.p, 0, sizeof(double), L.st));
   L.tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * refs.size() + 4 * (W + 1));
   CU(cudaEventRecord(L.ev[4], L.st));
-  int nl = launch_em_steps(L.d_chains.p, L.d_descs.p, L.d_chain_idx.p, n_small, n_big, any_scan, L.d_refs.p, int64_t(refs.size()),
+  bool big_k = false;
+  for (auto& c : chains) big_k = big_k || c.K > 7;
+  int nl = launch_em_steps(L.d_chains.p, L.d_descs.p, L.d_chain_idx.p, n_small, n_big, any_scan, big_k, L.d_refs.p, int64_t(refs.size()),
                            L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_lz.p,
                            L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
-                           L.d_trace_ws.p, L.st);
+                           L.d_trace_ws.p, L.st, L.em_events);
   CU(cudaGetLastError());
   CU(cudaEventRecord(L.ev[5], L.st));
   double scan_elems = 0;
@@ -329,6 +341,11 @@ int run_chains(scape_b200_handle* h, Lane& L, std::vector<ChainDev>& chains, con
   CU(cudaEventElapsedTime(&t0, h->base_ev, L.ev[4]));
   L.tm.em_ms += ms;
   L.busy.emplace_back(t0, t0 + ms);
+  double e_ms = 0, s_ms = 0;
+  em_steps_elapsed(L.em_events, &e_ms, &s_ms);
+  L.tm.estep_ms += e_ms;
+  L.tm.scan_ms += s_ms;
+  L.tm.scan_launches += L.em_events.scan_launches;
   L.tm.launches += nl;
   for (auto& c : chains) {
     const UtrDev& u = utrs_host[size_t(c.utr)];
@@ -759,6 +776,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
     h->tm.host_rng_ms += t.host_rng_ms; h->tm.launches += t.launches; h->tm.waves += t.waves;
     h->tm.em_grid_bytes += t.em_grid_bytes; h->tm.em_grid_flops += t.em_grid_flops; h->tm.tensor_exp += t.tensor_exp;
     h->tm.h2d_bytes += t.h2d_bytes; h->tm.d2h_bytes += t.d2h_bytes; h->tm.em_scan_bytes += t.em_scan_bytes;
+    h->tm.estep_ms += t.estep_ms; h->tm.scan_ms += t.scan_ms; h->tm.scan_launches += t.scan_launches;
     iv.insert(iv.end(), h->lanes[l].busy.begin(), h->lanes[l].busy.end());
   }
   std::sort(iv.begin(), iv.end());

@@ -692,9 +692,11 @@ em_estep_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ i
   }
 }
 
-// one WARP per chain (8 chains per CTA) for UTRs with few fragments: no block barriers at all
-template <typename TT>
-__global__ void __launch_bounds__(GT, 2)
+// one WARP per chain (8 chains per CTA) for UTRs with few fragments: no block barriers at all.
+// BIGK = false handles K = 1..7 (every normal run) with 4 CTAs per SM; BIGK = true handles the
+// K = 8..15 chains that only re-runs can create and may use twice the registers.
+template <typename TT, bool BIGK>
+__global__ void __launch_bounds__(GT, BIGK ? 2 : 4)
 em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ index, int n_index,
                      const UtrDev* __restrict__ utrs, const void* __restrict__ tensor,
                      const double* __restrict__ cnt_all, double* lz_all, double* v_all,
@@ -705,29 +707,36 @@ em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restric
   ChainDev& ch = chains[index[slot]];
   ScanDesc& sd = descs[index[slot]];
   if (ch.state == 0) return;
+  if ((ch.K > 7) != BIGK) return;
   const UtrDev u = utrs[ch.utr];
   if (!apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws)) return;
   const TT* A = (const TT*)tensor + u.tensor_off;
   const double* cnt = cnt_all + u.frag_off;
   double* lz = lz_all + ch.lz_off;
   double* V = v_all + ch.v_off;
-  switch (ch.K) {
-    case 1: estep_warp_run<2, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 2: estep_warp_run<3, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 3: estep_warp_run<4, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 4: estep_warp_run<5, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 5: estep_warp_run<6, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 6: estep_warp_run<7, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 7: estep_warp_run<8, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 8: estep_warp_run<9, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 9: estep_warp_run<10, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 10: estep_warp_run<11, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 11: estep_warp_run<12, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 12: estep_warp_run<13, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 13: estep_warp_run<14, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 14: estep_warp_run<15, TT>(ch, sd, u, A, cnt, lz, V); break;
-    case 15: estep_warp_run<16, TT>(ch, sd, u, A, cnt, lz, V); break;
-    default: break;
+  if (!BIGK) {
+    switch (ch.K) {
+      case 1: estep_warp_run<2, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 2: estep_warp_run<3, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 3: estep_warp_run<4, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 4: estep_warp_run<5, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 5: estep_warp_run<6, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 6: estep_warp_run<7, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 7: estep_warp_run<8, TT>(ch, sd, u, A, cnt, lz, V); break;
+      default: break;
+    }
+  } else {
+    switch (ch.K) {
+      case 8: estep_warp_run<9, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 9: estep_warp_run<10, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 10: estep_warp_run<11, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 11: estep_warp_run<12, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 12: estep_warp_run<13, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 13: estep_warp_run<14, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 14: estep_warp_run<15, TT>(ch, sd, u, A, cnt, lz, V); break;
+      case 15: estep_warp_run<16, TT>(ch, sd, u, A, cnt, lz, V); break;
+      default: break;
+    }
   }
   if ((threadIdx.x & 31) == 0 && ch.weights_only && ch.trace_off >= 0) {
     const int64_t o = ch.trace_off + (int64_t)(ch.n_iter - 1) * (SCAPE_B200_KCAP + 1);
@@ -826,7 +835,7 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __
     // B fragment of this lane: V[chain = 8*ni + g][n = k0 + q]
     const uint32_t vb = vs_base + (uint32_t)(g * SCAN_VPITCH + q) * 8u;
     // register ring: A fragments are fetched PFD k-steps (4*PFD fragments) ahead of their use
-    constexpr int PFD = 4;
+    constexpr int PFD = NG == 1 ? 12 : NG == 2 ? 8 : 4;   // fewer MMAs per k-step -> prefetch further ahead
     TT pre[PFD][4];
 #pragma unroll
     for (int p = 0; p < PFD; p++) {
@@ -952,75 +961,147 @@ em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ de
 // then the others (block-per-chain kernel).
 template <typename TT>
 static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big,
-                             bool any_scan, const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
+                             bool any_scan, bool big_k, const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
                              const int32_t* utr_chain_off_dev, const void* tensor, const double* cnt, double* lz,
                              double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
-                             double* trace_ws, cudaStream_t st) {
+                             double* trace_ws, cudaStream_t st, std::vector<cudaEvent_t>& evs,
+                             std::vector<int>& kinds, int& scan_launches) {
   const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
   cudaFuncSetAttribute(em_scan_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
-  static const bool dbg = getenv("SCAPE_B200_DBG") != nullptr;   // per-launch event timing (development aid)
-  std::vector<cudaEvent_t> evs;
-  std::vector<int> kinds;
+  static const bool dbg = getenv("SCAPE_B200_DBG") != nullptr;   // print per-launch timings (development aid)
+  // events around every launch group: [E step | scan] per step; read back by em_steps_elapsed()
+  evs.resize(size_t(2 * (SCAPE_B200_NROUND + 1) + 1));
+  for (auto& e : evs)
+    if (!e) cudaEventCreateWithFlags(&e, cudaEventDefault);
+  kinds.clear();
+  size_t ne = 0;
   auto mark = [&](int kind) {
-    if (!dbg) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, st);
-    evs.push_back(e);
+    cudaEventRecord(evs[ne++], st);
     kinds.push_back(kind);
   };
   mark(-1);
   for (int step = 0; step <= SCAPE_B200_NROUND; step++) {
     if (n_small > 0) {
-      em_estep_warp_kernel<TT><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+      em_estep_warp_kernel<TT, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
           chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
           trace_b, trace_ws);
       launches++;
-      mark(0);
+      if (big_k) {
+        em_estep_warp_kernel<TT, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+            chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
+            trace_a, trace_b, trace_ws);
+        launches++;
+      }
     }
     if (n_big > 0) {
       em_estep_kernel<TT><<<(unsigned)n_big, GT, 0, st>>>(chains_dev, descs_dev, index_dev + n_small, utrs_dev, tensor, cnt, lz,
                                                            vbuf, (const ScanPartial*)partials, trace_a, trace_b,
                                                            trace_ws);
       launches++;
-      mark(1);
     }
+    mark(0);
     if (step == SCAPE_B200_NROUND || !any_scan || n_refs == 0) continue;
     em_scan_kernel<TT><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
                                                            vbuf, (ScanPartial*)partials, scan_elems);
     launches++;
-    mark(2);
+    scan_launches++;
+    mark(1);
   }
-  if (dbg) {
-    cudaStreamSynchronize(st);
-    double tot[3] = {0, 0, 0};
-    std::string line;
-    for (size_t i = 1; i < evs.size(); i++) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, evs[i - 1], evs[i]);
-      tot[kinds[i]] += ms;
-      if (kinds[i] == 2 && any_scan) line += std::to_string((int)(ms * 1000)) + " ";
-    }
-    fprintf(stderr, "em run: chains small=%lld big=%lld refs=%lld | estep_warp %.2f ms, estep_block %.2f ms, scan %.2f ms | scan us/step: %s\n",
-            (long long)n_small, (long long)n_big, (long long)n_refs, tot[0], tot[1], tot[2], line.c_str());
-    for (auto e : evs) cudaEventDestroy(e);
-  }
+  (void)dbg;
   return launches;
 }
 
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
+                    bool big_k,
                     const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
                     const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
                     double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
-                    double* trace_ws, cudaStream_t st) {
+                    double* trace_ws, cudaStream_t st, EmStepEvents& ee) {
+  ee.scan_launches = 0;
   if (f32)
-    return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, refs_dev, n_refs, utrs_dev,
+    return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
                                     utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                    trace_ws, st);
-  return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, refs_dev, n_refs, utrs_dev,
+                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches);
+  return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
                                    utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                   trace_ws, st);
+                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches);
+}
+
+// After the stream has been synchronised: total E-step and scan kernel time of the last run.
+void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms) {
+  *estep_ms = *scan_ms = 0;
+  for (size_t i = 1; i < ee.kinds.size(); i++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ee.evs[i - 1], ee.evs[i]);
+    (ee.kinds[i] == 1 ? *scan_ms : *estep_ms) += ms;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak microbenchmarks (the roofline denominators of the EM kernels; MEASURED_PEAKS.json has
+// no FP64 entry).  Dependent-free FMA / MMA streams in registers, one CTA of 256 threads x 8 per SM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters, double seed) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = seed + threadIdx.x * 1e-9 + i;
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters, double seed) {
+  double d[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) d[i][0] = d[i][1] = seed + i;
+  const double a = 1e-3 * (threadIdx.x & 3), b = 1e-3 * (threadIdx.x >> 2);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma_8x8x4(d[i][0], d[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += d[i][0] + d[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+// returns FP64 TFLOP/s (2 flop per FMA) of CUDA-core DFMA and tensor-core DMMA streams
+int measure_fp64_peaks(int n_sm, double* dfma_tflops, double* dmma_tflops, cudaStream_t st) {
+  double* buf = nullptr;
+  if (cudaMalloc((void**)&buf, 64) != cudaSuccess) return -1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = n_sm * 8, iters = 1 << 14;
+  float best_f = 1e30f, best_m = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, st);
+    peak_dfma_kernel<<<grid, 256, 0, st>>>(buf, iters, 1.0);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep) best_f = std::min(best_f, ms);
+    cudaEventRecord(e0, st);
+    peak_dmma_kernel<<<grid, 256, 0, st>>>(buf, iters, 1.0);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep) best_m = std::min(best_m, ms);
+  }
+  *dfma_tflops = 2.0 * grid * 256.0 * 8.0 * iters / (best_f * 1e-3) / 1e12;
+  *dmma_tflops = 2.0 * grid * 8.0 /*warps*/ * 8.0 /*mma*/ * 256.0 /*fma per mma*/ * iters / (best_m * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------

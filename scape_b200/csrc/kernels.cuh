@@ -111,11 +111,20 @@ cudaError_t upload_model_const(const ModelConst& mc);
 constexpr int kScanRows = 256;    // candidate rows per scan CTA (must equal SCAN_ROWS in kernels.cu)
 constexpr int kPartialBytes = 16; // sizeof(ScanPartial)
 // returns the number of kernel launches made
+// CUDA events bracketing every launch group of one EM run (kept per lane, reused)
+struct EmStepEvents {
+  std::vector<cudaEvent_t> evs;
+  std::vector<int> kinds;
+  int scan_launches = 0;
+};
+void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms);
+int measure_fp64_peaks(int n_sm, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 constexpr int kWarpEstepMaxN = 1024;   // UTRs with at most this many fragments use the warp-per-chain E step
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
+                    bool big_k,
                     const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
                     const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
                     double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
-                    double* trace_ws, cudaStream_t st);
+                    double* trace_ws, cudaStream_t st, EmStepEvents& ee);
 
 }  // namespace scape
