@@ -12,7 +12,7 @@ DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "host_prep.
 LIB = os.path.join(HERE, "libscape_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC,-O3,-pthread", "-shared", "-cudart", "static"]
+         "-Xcompiler", "-fPIC,-O3,-pthread,-fopenmp", "-shared", "-cudart", "static", "-lgomp"]
 
 
 def needs_build() -> bool:

@@ -59,6 +59,34 @@ struct DevBuf {
   }
 };
 
+// Page-locked host staging that keeps its capacity across waves (no page faults, fast DMA).
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0, n = 0;
+  cudaError_t resize(size_t m) {
+    if (m > cap) {
+      T* q = nullptr;
+      const size_t c = m + m / 2 + 64;
+      cudaError_t e = cudaMallocHost((void**)&q, c * sizeof(T));
+      if (e != cudaSuccess) return e;
+      if (p) {
+        memcpy(q, p, n * sizeof(T));
+        cudaFreeHost(p);
+      }
+      p = q;
+      cap = c;
+    }
+    n = m;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = n = 0;
+  }
+};
+
 // Device-side state of one lane.  A fit splits its RNG streams over the lanes; every lane runs its
 // own wave loop in its own host thread on its own CUDA stream, so the host work of one lane (RNG
 // replay, model selection, result assembly) overlaps the kernels of the others.
@@ -74,6 +102,7 @@ struct Lane {
   DevBuf<int32_t> d_chain_off, d_chain_idx;
   DevBuf<double> d_partials, d_counter;
   DevBuf<LabelDev> d_jobs;
+  PinnedBuf<ChainDev> h_chains, h_refits;
   cudaEvent_t ev[8];
   EmStepEvents em_events;
   scape_b200_timing tm;
@@ -86,6 +115,7 @@ struct Lane {
     d_rows.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
     d_refs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_counter.release(); d_jobs.release();
+    h_chains.release(); h_refits.release();
   }
 };
 
@@ -96,7 +126,7 @@ struct scape_b200_handle {
   scape_b200_params P;
   ModelConst mc;
   Lane lanes[kMaxLanes];
-  int n_lanes = 2;
+  int n_lanes = 1;
   cudaEvent_t base_ev = nullptr;
   scape_b200_timing tm;
   double wave_budget_bytes = 24e9;
@@ -254,9 +284,17 @@ int np_argmin(const std::vector<double>& v) {
 
 // Upload chains, run them (NROUND bulk-synchronous steps), bring them back.  `utrs_host` is the
 // wave's UtrDev array; chains must be ordered by UTR (they are generated that way).
-int run_chains(scape_b200_handle* h, Lane& L, std::vector<ChainDev>& chains, const std::vector<UtrDev>& utrs_host,
+int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chains, const std::vector<UtrDev>& utrs_host,
                bool want_trace = false) {
-  if (chains.empty()) return 0;
+  if (n_chains == 0) return 0;
+  struct Span {
+    ChainDev* p; size_t n;
+    size_t size() const { return n; }
+    ChainDev* data() const { return p; }
+    ChainDev& operator[](size_t i) const { return p[i]; }
+    ChainDev* begin() const { return p; }
+    ChainDev* end() const { return p + n; }
+  } chains{chains_p, n_chains};
   const size_t W = utrs_host.size();
   int64_t lz = 0, vsz = 0, tr = 0, pb = 0;
   std::vector<int32_t> chain_off(W + 1, 0);
@@ -356,6 +394,8 @@ int run_chains(scape_b200_handle* h, Lane& L, std::vector<ChainDev>& chains, con
   return 0;
 }
 
+// OpenMP team per calling thread: the worker threads persist between calls, so the ~300 parallel
+// regions of a fit (3 per wave) do not pay thread creation each time.
 void parallel_for(int64_t n, int threads, const std::function<void(int64_t)>& fn) {
   if (threads <= 0) threads = int(std::thread::hardware_concurrency());
   threads = int(std::max<int64_t>(1, std::min<int64_t>(threads, n)));
@@ -363,17 +403,8 @@ void parallel_for(int64_t n, int threads, const std::function<void(int64_t)>& fn
     for (int64_t i = 0; i < n; i++) fn(i);
     return;
   }
-  std::vector<std::thread> pool;
-  std::atomic<int64_t> next(0);
-  for (int t = 0; t < threads; t++)
-    pool.emplace_back([&]() {
-      for (;;) {
-        int64_t i = next.fetch_add(1);
-        if (i >= n) break;
-        fn(i);
-      }
-    });
-  for (auto& th : pool) th.join();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int64_t i = 0; i < n; i++) fn(i);
 }
 }  // namespace
 
@@ -497,42 +528,58 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
 
     // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
     for (;;) {
-      std::vector<ChainDev> chains;
       double tr0 = now_ms();
-      // RNG replay is serial per stream but streams are independent: one task per UTR of the wave
-      std::vector<std::vector<ChainDev>> drawn(W);
+      // RNG replay is serial per stream but streams are independent: one task per UTR of the wave,
+      // each writing its chains in place into the lane's pinned staging buffer
+      std::vector<size_t> first_chain(W + 1, 0);
+      for (size_t i = 0; i < W; i++)
+        first_chain[i + 1] = first_chain[i] + (wave[i].done ? 0 : size_t(wave[i].k_max - wave[i].k_min + 1) * SCAPE_B200_NTRIAL);
+      CU(L.h_chains.resize(first_chain[W]));
+      ChainDev* chains = L.h_chains.p;
+      std::atomic<int> n_failed(0);
       parallel_for(int64_t(W), lane_threads, [&](int64_t ii) {
         const size_t i = size_t(ii);
         WaveUtr& w = wave[i];
         if (w.done) return;
         const UtrPrep& p = prep[size_t(w.u)];
         NpRandomState& g = rng[size_t(stream_of[size_t(w.u)])];
-        std::vector<ChainDev>& mine = drawn[i];
-        mine.reserve(size_t(w.k_max - w.k_min + 1) * SCAPE_B200_NTRIAL);
+        ChainDev* mine = chains + first_chain[i];
+        size_t j = 0;
         for (int K = w.k_max; K >= w.k_min && !w.done; K--)
-          for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++) {
+          for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++, j++) {
             ChainInit ci;
             int32_t rc = draw_chain(g, P, p, K, ci);
             if (rc != kOk) {       // numpy's choice() would have raised inside the reference
               out->status[w.u] = rc;
               w.done = true;
-              mine.clear();
+              n_failed++;
               break;
             }
-            ChainDev c;
+            ChainDev& c = mine[j];
             memset(&c, 0, sizeof(c));
             c.utr = int32_t(i); c.K = K; c.weights_only = 0;
             memcpy(c.a_idx, ci.a_idx, sizeof(ci.a_idx));
             memcpy(c.b_idx, ci.b_idx, sizeof(ci.b_idx));
             memcpy(c.ws, ci.ws, sizeof(ci.ws));
             memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
-            mine.push_back(c);
           }
       });
-      for (size_t i = 0; i < W; i++) chains.insert(chains.end(), drawn[i].begin(), drawn[i].end());
+      size_t n_chains = first_chain[W];
+      if (n_failed.load() > 0) {   // rare: drop the chains of UTRs whose initialisation raised
+        size_t o = 0;
+        for (size_t i = 0; i < W; i++) {
+          const size_t cnt = first_chain[i + 1] - first_chain[i];
+          if (cnt == 0) continue;
+          if (!wave[i].done) {
+            if (o != first_chain[i]) memmove(chains + o, chains + first_chain[i], cnt * sizeof(ChainDev));
+            o += cnt;
+          }
+        }
+        n_chains = o;
+      }
       L.tm.host_rng_ms += now_ms() - tr0;
-      if (chains.empty()) break;
-      if (int rc = run_chains(h, L, chains, ud)) return rc;
+      if (n_chains == 0) break;
+      if (int rc = run_chains(h, L, chains, n_chains, ud)) return rc;
       if (!timed_lik) {
         float a = 0, b = 0;
         CU(cudaEventElapsedTime(&a, L.ev[0], L.ev[1]));
@@ -545,7 +592,9 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         timed_lik = true;
       }
       // ---- selection (em_optim0 :865, run :972) + pruning (rm_component :832-844) -----------------
-      std::vector<ChainDev> refits;
+      CU(L.h_refits.resize(W));
+      ChainDev* refits = L.h_refits.p;
+      size_t n_refits = 0;
       std::vector<size_t> refit_owner;
       tr0 = now_ms();
       size_t pos = 0;
@@ -577,7 +626,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
           for (int k = 0; k < w.best.K; k++)
             if (!(w.best.ws[k] < P.min_ws)) keep[nk++] = k;
           if (nk < w.best.K) {
-            ChainDev c;
+            ChainDev& c = refits[n_refits++];
             memset(&c, 0, sizeof(c));
             c.utr = int32_t(i); c.K = nk; c.weights_only = 1;
             for (int k = 0; k < nk; k++) { c.a_idx[k] = w.best.a_idx[keep[k]]; c.b_idx[k] = w.best.b_idx[keep[k]]; }
@@ -586,14 +635,13 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
             draw_refit(rng[size_t(stream_of[size_t(w.u)])], P, ci);
             memcpy(c.ws, ci.ws, sizeof(ci.ws));
             memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
-            refits.push_back(c);
             refit_owner.push_back(i);
           }
         }
       }
       L.tm.host_rng_ms += now_ms() - tr0;
-      if (int rc = run_chains(h, L, refits, ud)) return rc;
-      for (size_t j = 0; j < refits.size(); j++) {
+      if (int rc = run_chains(h, L, refits, n_refits, ud)) return rc;
+      for (size_t j = 0; j < n_refits; j++) {
         WaveUtr& w = wave[refit_owner[j]];
         w.best = refits[j];
         w.chains_run += 1;
@@ -935,7 +983,7 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
     memcpy(c.k_order, io[i].k_order, SCAPE_B200_NROUND);
   }
   const bool want_trace = trace_a && trace_b && trace_ws;
-  if (int rc = run_chains(h, L, chains, ud, want_trace)) return rc;
+  if (int rc = run_chains(h, L, chains.data(), chains.size(), ud, want_trace)) return rc;
   for (int64_t i = 0; i < n_chains; i++) {
     const ChainDev& c = chains[size_t(i)];
     memcpy(io[i].a_idx, c.a_idx, sizeof(c.a_idx));
