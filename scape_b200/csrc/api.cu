@@ -491,7 +491,11 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     }
     CU(L.d_fx.ensure(size_t(nf))); CU(L.d_fl.ensure(size_t(nf))); CU(L.d_fr.ensure(size_t(nf)));
     CU(L.d_fpa.ensure(size_t(nf))); CU(L.d_cnt.ensure(size_t(nf))); CU(L.d_theta.ensure(size_t(nt)));
-    CU(L.d_table.ensure(size_t(ntab))); CU(L.d_tensor.ensure(size_t(nten)));
+    int64_t max_ldr = 0;
+    for (size_t i = 0; i < W; i++) max_ldr = std::max<int64_t>(max_ldr, ud[i].ldR);
+    const int64_t slack = int64_t(kTensorSlackRows) * max_ldr;     // elements; see scan_subbatch's register ring
+    CU(L.d_table.ensure(size_t(ntab))); CU(L.d_tensor.ensure(size_t(nten + slack)));
+    CU(cudaMemsetAsync((char*)L.d_tensor.p + size_t(nten) * (h->tensor_f32 ? 4 : 8), 0, size_t(slack) * (h->tensor_f32 ? 4 : 8), L.st));
     CU(L.d_utrs.ensure(W)); CU(L.d_rows.ensure(rows.size()));
     const size_t fb = sizeof(double) * size_t(nf);
     CU(cudaMemcpyAsync(L.d_fx.p, hx.data(), fb, cudaMemcpyHostToDevice, L.st));
@@ -959,7 +963,8 @@ extern "C" int scape_b200_em_chains(scape_b200_handle* h, int64_t n_frag, int64_
   for (size_t n = 0; n < size_t(n_frag); n++)          // reference [t][b][n] -> device [n][t][b]
     for (size_t r = 0; r < Rr; r++) ten[n * ldr + r] = tensor[r * size_t(n_frag) + n];
   std::copy(cnt, cnt + n_frag, pc.begin());
-  CU(L.d_tensor.ensure(ten.size())); CU(L.d_cnt.ensure(np_)); CU(L.d_utrs.ensure(1));
+  CU(L.d_tensor.ensure(ten.size() + size_t(kTensorSlackRows) * ldr)); CU(L.d_cnt.ensure(np_)); CU(L.d_utrs.ensure(1));
+  CU(cudaMemsetAsync(L.d_tensor.p, 0, (ten.size() + size_t(kTensorSlackRows) * ldr) * (h->tensor_f32 ? 4 : 8), L.st));
   std::vector<float> tf;
   if (h->tensor_f32) {
     tf.resize(ten.size());

@@ -786,7 +786,7 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __
   const int base = blk * SCAN_ROWS;
   const int blk_end = min(base + SCAN_ROWS, Rv);
   // fragment hull of this sub-batch (union over its chains) and the chains' windows
-  if (tid < SCAN_GB) {
+  if (tid < 32) {                                // one full warp (the shuffles below need all 32 lanes)
     int lo = 0, hi = 0, h0 = 1 << 30, h1 = 0;
     if (tid < cnt) {
       const ScanDesc d = descs[sh.list[first + tid]];
@@ -795,8 +795,10 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __
       sh.voff[tid] = d.v_off;
       sh.pboff[tid] = d.pb_off;
     }
-    sh.w0[tid] = lo;
-    sh.w1[tid] = hi;
+    if (tid < SCAN_GB) {
+      sh.w0[tid] = lo;
+      sh.w1[tid] = hi;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       h0 = min(h0, __shfl_xor_sync(0xffffffffu, h0, o));
@@ -834,36 +836,54 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __
     __syncthreads();
     // B fragment of this lane: V[chain = 8*ni + g][n = k0 + q]
     const uint32_t vb = vs_base + (uint32_t)(g * SCAN_VPITCH + q) * 8u;
-    // register ring: A fragments are fetched PFD k-steps (4*PFD fragments) ahead of their use
+    // A fragments are fetched PFD k-steps (4*PFD fragments) ahead through a register ring.  The ring
+    // is refilled unconditionally with plain pointer increments (no clamp, no branch: a conditional
+    // refill makes the compiler insert register moves that wait on the load just issued).  Reads may
+    // run up to 4*PFD+3 fragments past the chunk: the tensor arena carries zeroed slack for that, and
+    // V is zero-padded, so nothing past the hull contributes.
     constexpr int PFD = NG == 1 ? 12 : NG == 2 ? 8 : 4;   // fewer MMAs per k-step -> prefetch further ahead
+    const int64_t kstep = 4 * R;
+    const TT* pp[4];
     TT pre[PFD][4];
 #pragma unroll
-    for (int p = 0; p < PFD; p++) {
-      const int64_t nn = min(c0 + 4 * p + q, N - 1);       // clamped: V is zero-padded there
+    for (int mi = 0; mi < 4; mi++) pp[mi] = arow[mi] + (int64_t)(c0 + q) * R;
 #pragma unroll
-      for (int mi = 0; mi < 4; mi++) pre[p][mi] = __ldg(arow[mi] + nn * R);
-    }
-    for (int k0 = 0; k0 < len4; k0 += 4 * PFD) {
+    for (int p = 0; p < PFD; p++)
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) {
+        pre[p][mi] = __ldg(pp[mi]);
+        pp[mi] += kstep;
+      }
+    int kk = 0;
+    for (; kk + 4 * PFD <= len4; kk += 4 * PFD) {
 #pragma unroll
       for (int p = 0; p < PFD; p++) {
-        const int kk = k0 + 4 * p;
-        if (kk < len4) {                                   // uniform across the CTA
-          double a[4];
+        double a[4];
 #pragma unroll
-          for (int mi = 0; mi < 4; mi++) a[mi] = (double)pre[p][mi];
-          if (kk + 4 * PFD < len4) {
-            const int64_t nn = min(c0 + kk + 4 * PFD + q, N - 1);
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++) pre[p][mi] = __ldg(arow[mi] + nn * R);
-          }
-          double b[NG];
-#pragma unroll
-          for (int ni = 0; ni < NG; ni++) b[ni] = lds_f64(vb + (uint32_t)(ni * 8 * SCAN_VPITCH + kk) * 8u);
-#pragma unroll
-          for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-            for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        for (int mi = 0; mi < 4; mi++) {
+          a[mi] = (double)pre[p][mi];
+          pre[p][mi] = __ldg(pp[mi]);
+          pp[mi] += kstep;
         }
+        double b[NG];
+#pragma unroll
+        for (int ni = 0; ni < NG; ni++) b[ni] = lds_f64(vb + (uint32_t)(ni * 8 * SCAN_VPITCH + kk + 4 * p) * 8u);
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+          for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PFD; p++) {                        // remainder: fewer than PFD k-steps, ring already holds them
+      if (kk + 4 * p < len4) {
+        double b[NG];
+#pragma unroll
+        for (int ni = 0; ni < NG; ni++) b[ni] = lds_f64(vb + (uint32_t)(ni * 8 * SCAN_VPITCH + kk + 4 * p) * 8u);
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+          for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], (double)pre[p][mi], b[ni]);
       }
     }
   }

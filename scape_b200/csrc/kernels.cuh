@@ -108,6 +108,7 @@ void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int m
 void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
                    const double* cnt, int32_t* labels, cudaStream_t st);
 cudaError_t upload_model_const(const ModelConst& mc);
+constexpr int kTensorSlackRows = 64;   // zeroed fragment rows after the last UTR's tensor: the scan's register ring prefetches past the hull
 constexpr int kScanRows = 256;    // candidate rows per scan CTA (must equal SCAN_ROWS in kernels.cu)
 constexpr int kPartialBytes = 16; // sizeof(ScanPartial)
 // returns the number of kernel launches made
