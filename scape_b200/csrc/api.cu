@@ -415,6 +415,7 @@ struct FitShared {
   const scape_b200_batch* bt;
   scape_b200_results* out;
   std::vector<UtrPrep>* prep;
+  std::vector<std::atomic<int>>* ready;
   std::vector<std::vector<int64_t>>* stream_utrs;
   std::vector<NpRandomState>* rng;
   std::vector<size_t>* cursor;
@@ -443,6 +444,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     for (int s : my_streams) {
       while (cursor[size_t(s)] < stream_utrs[size_t(s)].size()) {
         int64_t u = stream_utrs[size_t(s)][cursor[size_t(s)]];
+        while (!(*F.ready)[size_t(u)].load(std::memory_order_acquire)) std::this_thread::yield();   // pre-pass still running
         if (prep[size_t(u)].status != kOk) { cursor[size_t(s)]++; continue; }   // the reference would have raised
         const UtrPrep& p = prep[size_t(u)];
         double need = double(p.T() * p.B() + 4) * pad4(p.n()) * (h->tensor_f32 ? 4.0 : 8.0) + double(p.T()) * pad4(p.n()) * 8.0;
@@ -744,17 +746,52 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   CU(cudaEventRecord(h->base_ev, 0));
   CU(cudaEventSynchronize(h->base_ev));
 
-  // ---- host pre-pass (RNG free), parallel over UTRs -------------------------------------------
+  // ---- host pre-pass (RNG free): background thread, parallel over UTRs in wave order -------------
+  // UTRs are prepared in the order the waves need them (position within the stream first), each
+  // one publishes a ready flag; the lanes start their first wave as soon as its UTRs are ready, so
+  // the pre-pass of later waves overlaps the kernels of earlier ones.
   std::vector<UtrPrep> prep(static_cast<size_t>(U));
-  double t0 = now_ms();
-  parallel_for(U, h->host_threads, [&](int64_t u) {
-    const int64_t a = bt->read_off[u], n = bt->read_off[u + 1] - a;
-    UtrPrep& p = prep[size_t(u)];
-    if (bin_reads(bt->x + a, bt->l + a, bt->r + a, bt->pa + a, n, p) != kOk) return;
-    if (setup_model(P, bt->x + a, bt->l + a, n, p) != kOk) return;
-    coverage_and_peaks(P, p);
+  std::vector<std::atomic<int>> ready(static_cast<size_t>(U));
+  for (auto& r : ready) r.store(0, std::memory_order_relaxed);
+  std::vector<int64_t> prep_order(static_cast<size_t>(U));
+  {
+    std::vector<int64_t> seen(size_t(std::max(1, bt->n_streams)), 0), rank(static_cast<size_t>(U));
+    for (int64_t u = 0; u < U; u++) {
+      const int s = bt->stream_id[u];
+      if (s < 0 || s >= bt->n_streams) return fail(-5, "stream_id out of range");
+      rank[size_t(u)] = seen[size_t(s)]++;
+    }
+    for (int64_t u = 0; u < U; u++) prep_order[size_t(u)] = u;
+    std::stable_sort(prep_order.begin(), prep_order.end(),
+                     [&](int64_t a, int64_t b) { return rank[size_t(a)] < rank[size_t(b)]; });
+  }
+  double prep_ms = 0;
+  std::thread prep_thread([&]() {
+    const double t0 = now_ms();
+    parallel_for(U, h->host_threads, [&](int64_t i) {
+      const int64_t u = prep_order[size_t(i)];
+      const int64_t a = bt->read_off[u], n = bt->read_off[u + 1] - a;
+      UtrPrep& p = prep[size_t(u)];
+      if (bin_reads(bt->x + a, bt->l + a, bt->r + a, bt->pa + a, n, p) == kOk &&
+          setup_model(P, bt->x + a, bt->l + a, n, p) == kOk)
+        coverage_and_peaks(P, p);
+      out->status[u] = p.status;
+      out->K[u] = 0;
+      out->L[u] = p.L;
+      out->n_frag[u] = int32_t(p.n());
+      out->n_theta[u] = int32_t(p.T());
+      out->n_lb[u] = 0;
+      out->bic[u] = NAN;
+      for (int k = 0; k < 4; k++) out->path[u * 4 + k] = 0;
+      out->em_work[u * 2] = out->em_work[u * 2 + 1] = 0;
+      ready[size_t(u)].store(1, std::memory_order_release);
+    });
+    prep_ms = now_ms() - t0;
   });
-  h->tm.host_prep_ms += now_ms() - t0;
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } prep_joiner{prep_thread};
 
   // ---- streams --------------------------------------------------------------------------------
   const int S = bt->n_streams;
@@ -778,18 +815,6 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   }
   std::vector<size_t> cursor(size_t(S), 0);
 
-  for (int64_t u = 0; u < U; u++) {
-    out->status[u] = prep[size_t(u)].status;
-    out->K[u] = 0;
-    out->L[u] = prep[size_t(u)].L;
-    out->n_frag[u] = int32_t(prep[size_t(u)].n());
-    out->n_theta[u] = int32_t(prep[size_t(u)].T());
-    out->n_lb[u] = 0;
-    out->bic[u] = NAN;
-    for (int i = 0; i < 4; i++) out->path[u * 4 + i] = 0;
-    out->em_work[u * 2] = out->em_work[u * 2 + 1] = 0;
-  }
-
   const int maxwin = max_window(P);
   std::vector<int32_t> stream_of(static_cast<size_t>(U));
   for (int64_t u = 0; u < U; u++) stream_of[size_t(u)] = bt->stream_id[u];
@@ -799,7 +824,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   std::vector<std::vector<int>> lane_streams(static_cast<size_t>(n_lanes));
   for (int s = 0; s < S; s++) lane_streams[size_t(s % n_lanes)].push_back(s);
   int total_threads = h->host_threads > 0 ? h->host_threads : int(std::thread::hardware_concurrency());
-  FitShared F{h, bt, out, &prep, &stream_utrs, &rng, &cursor, &stream_of, maxwin,
+  FitShared F{h, bt, out, &prep, &ready, &stream_utrs, &rng, &cursor, &stream_of, maxwin,
               std::max(1, total_threads / n_lanes)};
   for (int l = 0; l < n_lanes; l++) {
     Lane& L = h->lanes[l];
@@ -818,6 +843,8 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
       });
     for (auto& w : workers) w.join();
   }
+  prep_thread.join();
+  h->tm.host_prep_ms = prep_ms;
   for (int l = 0; l < n_lanes; l++)
     if (h->lanes[l].rc) return fail(h->lanes[l].rc, h->lanes[l].err);
   // merge the lanes' accounting; device time = length of the union of all kernel intervals
