@@ -989,6 +989,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
   const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
   cudaFuncSetAttribute(em_scan_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
+  static const int warp_steps = getenv("SCAPE_B200_WARP_STEPS") ? atoi(getenv("SCAPE_B200_WARP_STEPS")) : 24;
   static const bool dbg = getenv("SCAPE_B200_DBG") != nullptr;   // print per-launch timings (development aid)
   // events around every launch group: [E step | scan] per step; read back by em_steps_elapsed()
   evs.resize(size_t(2 * (SCAPE_B200_NROUND + 1) + 1));
@@ -1002,7 +1003,11 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
   };
   mark(-1);
   for (int step = 0; step <= SCAPE_B200_NROUND; step++) {
-    if (n_small > 0) {
+    // Early steps: most chains run -> one warp per chain (throughput).  Late steps: few chains run
+    // and the step time is the latency of ONE chain's E pass -> one CTA per chain (8x shorter
+    // fragment loop); CTAs of finished chains exit at once.
+    const bool wide = step < warp_steps;
+    if (n_small > 0 && wide) {
       em_estep_warp_kernel<TT, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
           chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
           trace_b, trace_ws);
@@ -1014,10 +1019,11 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
         launches++;
       }
     }
-    if (n_big > 0) {
-      em_estep_kernel<TT><<<(unsigned)n_big, GT, 0, st>>>(chains_dev, descs_dev, index_dev + n_small, utrs_dev, tensor, cnt, lz,
-                                                           vbuf, (const ScanPartial*)partials, trace_a, trace_b,
-                                                           trace_ws);
+    const int64_t n_blk = wide ? n_big : n_small + n_big;
+    if (n_blk > 0) {
+      em_estep_kernel<TT><<<(unsigned)n_blk, GT, 0, st>>>(chains_dev, descs_dev, wide ? index_dev + n_small : index_dev,
+                                                           utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
+                                                           trace_a, trace_b, trace_ws);
       launches++;
     }
     mark(0);
@@ -1028,7 +1034,16 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
     scan_launches++;
     mark(1);
   }
-  (void)dbg;
+  if (dbg) {
+    cudaStreamSynchronize(st);
+    std::string le, ls;
+    for (size_t i = 1; i < kinds.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, evs[i - 1], evs[i]);
+      (kinds[i] == 1 ? ls : le) += std::to_string((int)(ms * 1000)) + " ";
+    }
+    fprintf(stderr, "em run: small=%lld big=%lld refs=%lld\n  estep us/step: %s\n  scan us/step: %s\n", (long long)n_small, (long long)n_big, (long long)n_refs, le.c_str(), ls.c_str());
+  }
   return launches;
 }
 
