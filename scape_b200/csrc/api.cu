@@ -94,7 +94,8 @@ struct Lane {
   cudaStream_t st = nullptr;
   DevBuf<double> d_fx, d_fl, d_fr, d_fpa, d_cnt, d_theta, d_table, d_tensor, d_lz, d_v, d_trace_ws;
   DevBuf<UtrDev> d_utrs;
-  DevBuf<RowRef> d_rows;
+  DevBuf<RowRef> d_rows, d_trows;
+  DevBuf<TileRef> d_tiles;
   DevBuf<ChainDev> d_chains;
   DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
   DevBuf<ScanRef> d_refs;
@@ -112,7 +113,7 @@ struct Lane {
   void release() {
     d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
     d_table.release(); d_tensor.release(); d_lz.release(); d_v.release(); d_trace_ws.release(); d_utrs.release();
-    d_rows.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
+    d_rows.release(); d_trows.release(); d_tiles.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
     d_refs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_counter.release(); d_jobs.release();
     h_chains.release(); h_refits.release();
@@ -127,6 +128,9 @@ struct scape_b200_handle {
   ModelConst mc;
   Lane lanes[kMaxLanes];
   int n_lanes = 1;
+  bool tensor_fast = false;   // default grid shape: interior alpha rows use the constant-weight kernel
+  double tf_g[kTfB * kTfW], tf_lp[kTfB * kTfW], tf_lps[kTfB];
+  int tf_hw[kTfB];
   cudaEvent_t base_ev = nullptr;
   scape_b200_timing tm;
   double wave_budget_bytes = 24e9;
@@ -201,6 +205,31 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   h->device = device;
   h->P = *params;
   fill_model_const(h->P, h->mc);
+  {
+    // Fast marginal kernel applies to the default grid shape (13 betas, widest window 43 points):
+    // weights of the (alpha-independent) interior windows, taichi_core.py:160-169.
+    const scape_b200_params& P = h->P;
+    bool ok = !P.fixed_run_mode && P.n_beta == kTfB && max_window(P) == kTfW;
+    if (const char* s = getenv("SCAPE_B200_TENSOR_FAST")) ok = ok && atoi(s) != 0;
+    if (ok) {
+      for (int j = 0; j < kTfB; j++) {
+        const double beta = P.betas[j];
+        const int hw = int(std::floor(3 * beta / P.theta_step));
+        h->tf_hw[j] = hw;
+        double sum = 0.0;
+        for (int d = 0; d < kTfW; d++) {
+          const double x = double(P.theta_step) * (d - kTfHalf) / beta;
+          const double lp = -0.5 * (x * x) - std::log(beta) - 0.5 * std::log(2 * 3.141592653589793);
+          h->tf_lp[j * kTfW + d] = lp;
+          if (std::abs(d - kTfHalf) <= hw) sum += std::exp(lp);      // theta order, like the reference
+        }
+        h->tf_lps[j] = std::log(sum);
+        for (int d = 0; d < kTfW; d++)
+          h->tf_g[j * kTfW + d] = std::abs(d - kTfHalf) <= hw ? std::exp(h->tf_lp[j * kTfW + d] - h->tf_lps[j]) : 0.0;
+      }
+      h->tensor_fast = true;
+    }
+  }
   for (Lane& L : h->lanes) {
     CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     for (auto& e : L.ev) CU(cudaEventCreate(&e));
@@ -466,7 +495,8 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     // ---- device layout of the wave --------------------------------------------------------------
     const size_t W = wave.size();
     std::vector<UtrDev> ud(W);
-    std::vector<RowRef> rows;
+    std::vector<RowRef> rows, trows;
+    std::vector<TileRef> tiles;
     int64_t nf = 0, nt = 0, ntab = 0, nten = 0;
     int max_n = 0;
     for (size_t i = 0; i < W; i++) {
@@ -479,6 +509,13 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += d.ldR * d.N;
       max_n = std::max(max_n, d.Npad);
       for (int t = 0; t < d.T; t++) rows.push_back({int32_t(i), t});
+      // marginal tensor: interior alpha rows go to the constant-weight kernel in tiles, the rest
+      // (window clipped by the grid ends) to the generic kernel
+      const int i_lo = kTfHalf, i_hi = d.T - 1 - kTfHalf;
+      for (int t = 0; t < d.T; t++)
+        if (!h->tensor_fast || t < i_lo || t > i_hi) trows.push_back({int32_t(i), t});
+      if (h->tensor_fast)
+        for (int t = i_lo; t <= i_hi; t += kTfTile) tiles.push_back({int32_t(i), t, std::min(kTfTile, i_hi - t + 1)});
     }
     std::vector<double> hx(size_t(nf), 0.0), hl(size_t(nf), 0.0), hr(size_t(nf), 0.0), hpa(size_t(nf), 0.0),
         hc(size_t(nf), 0.0), hth(static_cast<size_t>(nt));
@@ -499,6 +536,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     CU(L.d_table.ensure(size_t(ntab))); CU(L.d_tensor.ensure(size_t(nten + slack)));
     CU(cudaMemsetAsync((char*)L.d_tensor.p + size_t(nten) * (h->tensor_f32 ? 4 : 8), 0, size_t(slack) * (h->tensor_f32 ? 4 : 8), L.st));
     CU(L.d_utrs.ensure(W)); CU(L.d_rows.ensure(rows.size()));
+    CU(L.d_trows.ensure(trows.size() + 1)); CU(L.d_tiles.ensure(tiles.size() + 1));
     const size_t fb = sizeof(double) * size_t(nf);
     CU(cudaMemcpyAsync(L.d_fx.p, hx.data(), fb, cudaMemcpyHostToDevice, L.st));
     CU(cudaMemcpyAsync(L.d_fl.p, hl.data(), fb, cudaMemcpyHostToDevice, L.st));
@@ -508,6 +546,11 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     CU(cudaMemcpyAsync(L.d_theta.p, hth.data(), sizeof(double) * size_t(nt), cudaMemcpyHostToDevice, L.st));
     CU(cudaMemcpyAsync(L.d_utrs.p, ud.data(), sizeof(UtrDev) * W, cudaMemcpyHostToDevice, L.st));
     CU(cudaMemcpyAsync(L.d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, L.st));
+    if (!trows.empty())
+      CU(cudaMemcpyAsync(L.d_trows.p, trows.data(), sizeof(RowRef) * trows.size(), cudaMemcpyHostToDevice, L.st));
+    if (!tiles.empty())
+      CU(cudaMemcpyAsync(L.d_tiles.p, tiles.data(), sizeof(TileRef) * tiles.size(), cudaMemcpyHostToDevice, L.st));
+    L.tm.h2d_bytes += double(sizeof(RowRef) * trows.size() + sizeof(TileRef) * tiles.size());
     L.tm.h2d_bytes += double(5 * fb + sizeof(double) * size_t(nt) + sizeof(UtrDev) * W + sizeof(RowRef) * rows.size());
 
     // ---- likelihood phases ----------------------------------------------------------------------
@@ -515,11 +558,13 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     launch_table(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), max_n, L.d_fx.p, L.d_fl.p, L.d_fr.p,
                  L.d_fpa.p, L.d_theta.p, L.d_table.p, L.st);
     CU(cudaEventRecord(L.ev[1], L.st));
-    launch_tensor(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), max_n, P.n_beta, maxwin, L.d_theta.p,
+    launch_tensor(L.d_utrs.p, L.d_trows.p, int64_t(trows.size()), max_n, P.n_beta, maxwin, L.d_theta.p,
                   L.d_table.p, L.d_tensor.p, h->tensor_f32, L.st);
+    launch_tensor_interior(L.d_utrs.p, L.d_tiles.p, int64_t(tiles.size()), max_n, L.d_table.p, L.d_tensor.p,
+                           h->tensor_f32, L.st);
     CU(cudaEventRecord(L.ev[2], L.st));
     CU(cudaGetLastError());
-    L.tm.launches += 2;
+    L.tm.launches += 1 + (trows.empty() ? 0 : 1) + (tiles.empty() ? 0 : 1);
     for (size_t i = 0; i < W; i++) {
       // exp() evaluations = N * sum over (t, beta) of the clipped window sizes (regular grid)
       const UtrDev& d = ud[i];
@@ -743,6 +788,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   memset(&h->tm, 0, sizeof(h->tm));
   const double t_begin = now_ms();
   CU(upload_model_const(h->mc));
+  if (h->tensor_fast) CU(upload_tensor_fast_tables(h->tf_g, h->tf_lp, h->tf_lps, h->tf_hw));
   CU(cudaEventRecord(h->base_ev, 0));
   CU(cudaEventSynchronize(h->base_ev));
 
@@ -952,9 +998,32 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
   CU(cudaMemcpyAsync(L.d_table.p, tt.data(), 8 * tt.size(), cudaMemcpyHostToDevice, L.st));
   CU(cudaMemcpyAsync(L.d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, L.st));
   CU(cudaMemcpyAsync(L.d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, L.st));
-  launch_tensor(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), d.Npad, int(n_beta), maxwin, L.d_theta.p,
-                L.d_table.p, L.d_tensor.p, h->tensor_f32, L.st);
-  CU(cudaGetLastError());
+  // same dispatch as fit_batch: interior rows of a default-shaped regular grid take the constant-weight kernel
+  bool fast = h->tensor_fast && n_beta == kTfB && maxwin == kTfW && n_theta > 2 * kTfHalf;
+  for (int j = 0; fast && j < kTfB; j++) fast = betas[j] == h->P.betas[j];
+  for (int64_t t = 1; fast && t < n_theta; t++) fast = theta[t] - theta[t - 1] == double(h->P.theta_step);
+  if (fast) {
+    CU(upload_tensor_fast_tables(h->tf_g, h->tf_lp, h->tf_lps, h->tf_hw));
+    std::vector<RowRef> edge;
+    std::vector<TileRef> tiles;
+    const int i_lo = kTfHalf, i_hi = d.T - 1 - kTfHalf;
+    for (int t = 0; t < d.T; t++)
+      if (t < i_lo || t > i_hi) edge.push_back({0, t});
+    for (int t = i_lo; t <= i_hi; t += kTfTile) tiles.push_back({0, t, std::min(kTfTile, i_hi - t + 1)});
+    CU(L.d_trows.ensure(edge.size() + 1)); CU(L.d_tiles.ensure(tiles.size() + 1));
+    CU(cudaMemcpyAsync(L.d_trows.p, edge.data(), sizeof(RowRef) * edge.size(), cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_tiles.p, tiles.data(), sizeof(TileRef) * tiles.size(), cudaMemcpyHostToDevice, L.st));
+    launch_tensor(L.d_utrs.p, L.d_trows.p, int64_t(edge.size()), d.Npad, int(n_beta), maxwin, L.d_theta.p, L.d_table.p,
+                  L.d_tensor.p, h->tensor_f32, L.st);
+    launch_tensor_interior(L.d_utrs.p, L.d_tiles.p, int64_t(tiles.size()), d.Npad, L.d_table.p, L.d_tensor.p,
+                           h->tensor_f32, L.st);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(L.st));   // the host lists above must outlive the copies
+  } else {
+    launch_tensor(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), d.Npad, int(n_beta), maxwin, L.d_theta.p,
+                  L.d_table.p, L.d_tensor.p, h->tensor_f32, L.st);
+    CU(cudaGetLastError());
+  }
   const size_t Rr = size_t(n_theta) * size_t(n_beta), ldr = size_t(d.ldR);
   std::vector<double> ten(ldr * size_t(n_frag));
   if (h->tensor_f32) {

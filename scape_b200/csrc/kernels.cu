@@ -231,6 +231,108 @@ __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3 fast path: interior alpha rows of a regular theta grid (every normal `run()`: theta_step-spaced
+// grid, the 13 default betas, windows 3..43 wide).  There the normalised window weights
+// g[j][d] = N(theta_d; alpha, beta_j) / sum depend on (j, d) only, not on alpha, so they live in
+// constant memory and enter the FMAs as constant operands (no shared-memory broadcast), and a thread
+// (= one fragment) takes exp() of each table entry ONCE for a tile of TI consecutive alpha rows:
+// (TI + 42) / TI = 6.25 exp per (fragment, alpha) instead of 307 in the reference.
+// Rows whose widest window is clipped by the grid ends, irregular (fixed-mode) grids and any other
+// parameter set go through tensor_kernel above.
+// ------------------------------------------------------------------------------------------------
+constexpr int TF_B = 13, TF_W = 43, TF_HALF = 21, TF_TI = 8, TF_COLS = TF_TI + TF_W - 1;
+constexpr int TF_THREADS = 64;   // small CTAs: fragments are sorted by read start, so whole warps exit on the
+                                 // all-sentinel fast path; small CTAs free their shared memory sooner
+__constant__ double c_tf_g[TF_B * TF_W];     // weights on the widest window, 0 outside beta_j's own window
+__constant__ double c_tf_lp[TF_B * TF_W];    // log pdf (for the exact fallback)
+__constant__ double c_tf_lps[TF_B];
+__constant__ int c_tf_hw[TF_B];              // half width of beta_j's window in grid points
+
+cudaError_t upload_tensor_fast_tables(const double* g, const double* lp, const double* lps, const int* hw) {
+  cudaError_t e = cudaMemcpyToSymbol(c_tf_g, g, sizeof(double) * TF_B * TF_W);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_tf_lp, lp, sizeof(double) * TF_B * TF_W);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_tf_lps, lps, sizeof(double) * TF_B);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_tf_hw, hw, sizeof(int) * TF_B);
+  return e;
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(TF_THREADS) tensor_interior_kernel(const UtrDev* __restrict__ utrs,
+                                                              const TileRef* __restrict__ tiles,
+                                                              const double* __restrict__ table,
+                                                              TT* __restrict__ tensor) {
+  extern __shared__ double sm_e[];             // [TF_COLS][TF_THREADS]: this thread's exp(table - M) column
+  const TileRef tr = tiles[blockIdx.x];
+  const UtrDev u = utrs[tr.utr];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y * blockDim.x + tid;
+  if (n >= u.N) return;                        // no barrier below: every thread only touches its own column
+  const int64_t ld = u.Npad;
+  const double* tab = table + u.table_off + n + (int64_t)(tr.i0 - TF_HALF) * ld;
+  const int cols = tr.cnt + TF_W - 1;
+  double M = tab[0];
+  for (int c = 1; c < cols; c++) M = fmax(M, tab[(int64_t)c * ld]);
+  TT* out = tensor + u.tensor_off + (int64_t)n * u.ldR + (int64_t)tr.i0 * TF_B;
+  if (M < -1e30) {                             // incompatible with every theta of the tile: all sentinel
+    for (int e = 0; e < tr.cnt * TF_B; e++) out[e] = TT(SCAPE_SENTINEL);
+    return;
+  }
+  for (int c = 0; c < cols; c++) {
+    const double a = tab[(int64_t)c * ld] - M;
+    sm_e[c * TF_THREADS + tid] = (a > -746.0) ? exp(a) : 0.0;
+  }
+  for (int ii = 0; ii < tr.cnt; ii++) {
+    double acc[TF_B];
+#pragma unroll
+    for (int j = 0; j < TF_B; j++) acc[j] = 0.0;
+#pragma unroll
+    for (int d = 0; d < TF_W; d++) {
+      const double e = sm_e[(ii + d) * TF_THREADS + tid];
+#pragma unroll
+      for (int j = 0; j < TF_B; j++) acc[j] = fma(e, c_tf_g[j * TF_W + d], acc[j]);   // constant operand
+    }
+#pragma unroll
+    for (int j = 0; j < TF_B; j++) {
+      double res;
+      if (acc[j] > 1e-290) {
+        res = log(acc[j]) + M;
+      } else {
+        // exact two-pass log-sum-exp over beta_j's own window (taichi_core.py:41-54, 172-179)
+        const int hw = c_tf_hw[j];
+        const double* col = tab + (int64_t)(ii + TF_HALF - hw) * ld;
+        const double* lp = c_tf_lp + j * TF_W + (TF_HALF - hw);
+        const double lps = c_tf_lps[j];
+        double m = (col[0] + lp[0]) - lps;
+        for (int d = 1; d <= 2 * hw; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
+        if (m < -1e30) {
+          res = SCAPE_SENTINEL;                // log(w) + sentinel == sentinel in FP64
+        } else {
+          double sum = 0.0;
+          for (int d = 0; d <= 2 * hw; d++) {
+            const double a = ((col[(int64_t)d * ld] + lp[d]) - lps) - m;
+            if (a > -746.0) sum += exp(a);
+          }
+          res = log(sum) + m;
+        }
+      }
+      out[ii * TF_B + j] = TT(res);
+    }
+  }
+}
+
+void launch_tensor_interior(const UtrDev* utrs, const TileRef* tiles, int64_t n_tiles, int max_n, const double* table,
+                            void* tensor, bool f32, cudaStream_t st) {
+  if (n_tiles <= 0) return;
+  dim3 grid((unsigned)n_tiles, (unsigned)((max_n + TF_THREADS - 1) / TF_THREADS));
+  const size_t smem = (size_t)TF_COLS * TF_THREADS * sizeof(double);
+  if (f32) {
+    tensor_interior_kernel<float><<<grid, TF_THREADS, smem, st>>>(utrs, tiles, table, (float*)tensor);
+  } else {
+    tensor_interior_kernel<double><<<grid, TF_THREADS, smem, st>>>(utrs, tiles, table, (double*)tensor);
+  }
+}
+
 void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, int n_beta, int max_win,
                    const double* theta, const double* table, void* tensor, bool f32, cudaStream_t st) {
   if (n_rows <= 0) return;

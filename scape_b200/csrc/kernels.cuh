@@ -100,6 +100,16 @@ struct RowRef {
   int32_t t;
 };
 
+// tile of consecutive interior alpha rows for the fast marginal kernel
+struct TileRef {
+  int32_t utr;
+  int32_t i0;
+  int32_t cnt;
+};
+constexpr int kTfB = 13, kTfW = 43, kTfHalf = 21, kTfTile = 8;
+cudaError_t upload_tensor_fast_tables(const double* g, const double* lp, const double* lps, const int* hw);
+void launch_tensor_interior(const UtrDev* utrs, const TileRef* tiles, int64_t n_tiles, int max_n, const double* table,
+                            void* tensor, bool f32, cudaStream_t st);
 void launch_table(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, const double* fx,
                   const double* fl, const double* fr, const double* fpa, const double* theta, double* table,
                   cudaStream_t st);

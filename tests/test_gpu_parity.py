@@ -74,6 +74,24 @@ def test_theta_table_with_known_polya_lengths(engine):
     assert _rel_err_on_finite(got, want) < 1e-12
 
 
+def test_marginal_fast_and_generic_kernels_agree(engine):
+    """Interior alpha rows of the default grid go through tensor_interior_kernel (constant weights,
+    one exp per table entry and tile); SCAPE_B200_TENSOR_FAST=0 engines use the generic kernel for
+    every row.  Both must match the oracle, including a long UTR with many tiles."""
+    import os
+    m = _model(synth.make_utr(22, 2500, long_utr=True))
+    fast = engine.marginal_tensor(m.theta, m.betas, m.table)
+    assert _rel_err_on_finite(fast, m.tensor) < TOL[engine.dtype]["tensor"]
+    os.environ["SCAPE_B200_TENSOR_FAST"] = "0"
+    try:
+        with _lib.Engine(_lib.make_params(), tensor_dtype=engine.dtype) as slow_engine:
+            slow = slow_engine.marginal_tensor(m.theta, m.betas, m.table)
+    finally:
+        del os.environ["SCAPE_B200_TENSOR_FAST"]
+    assert _rel_err_on_finite(slow, m.tensor) < TOL[engine.dtype]["tensor"]
+    assert np.array_equal(fast > -1e30, slow > -1e30)
+
+
 def test_marginal_tensor_on_irregular_fixed_mode_grid(engine):
     m = _model(synth.make_utr(3, 300), with_tensor=False)
     keep = np.r_[10:60, 100:131, 180:200]
