@@ -797,7 +797,7 @@ em_estep_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ i
 // one WARP per chain (8 chains per CTA) for UTRs with few fragments: no block barriers at all.
 // BIGK = false handles K = 1..7 (every normal run) with 4 CTAs per SM; BIGK = true handles the
 // K = 8..15 chains that only re-runs can create and may use twice the registers.
-template <typename TT, bool BIGK>
+template <typename TT, bool BIGK, bool LOOP>
 __global__ void __launch_bounds__(GT, BIGK ? 2 : 4)
 em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ index, int n_index,
                      const UtrDev* __restrict__ utrs, const void* __restrict__ tensor,
@@ -816,35 +816,41 @@ em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restric
   const double* cnt = cnt_all + u.frag_off;
   double* lz = lz_all + ch.lz_off;
   double* V = v_all + ch.v_off;
-  if (!BIGK) {
-    switch (ch.K) {
-      case 1: estep_warp_run<2, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 2: estep_warp_run<3, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 3: estep_warp_run<4, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 4: estep_warp_run<5, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 5: estep_warp_run<6, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 6: estep_warp_run<7, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 7: estep_warp_run<8, TT>(ch, sd, u, A, cnt, lz, V); break;
-      default: break;
+  // LOOP: weights-only chains (prune refits) never wait for a scan, so the whole chain runs to
+  // convergence inside one launch instead of one launch per iteration.
+  do {
+    if (!BIGK) {
+      switch (ch.K) {
+        case 1: estep_warp_run<2, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 2: estep_warp_run<3, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 3: estep_warp_run<4, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 4: estep_warp_run<5, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 5: estep_warp_run<6, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 6: estep_warp_run<7, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 7: estep_warp_run<8, TT>(ch, sd, u, A, cnt, lz, V); break;
+        default: break;
+      }
+    } else {
+      switch (ch.K) {
+        case 8: estep_warp_run<9, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 9: estep_warp_run<10, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 10: estep_warp_run<11, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 11: estep_warp_run<12, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 12: estep_warp_run<13, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 13: estep_warp_run<14, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 14: estep_warp_run<15, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 15: estep_warp_run<16, TT>(ch, sd, u, A, cnt, lz, V); break;
+        default: break;
+      }
     }
-  } else {
-    switch (ch.K) {
-      case 8: estep_warp_run<9, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 9: estep_warp_run<10, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 10: estep_warp_run<11, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 11: estep_warp_run<12, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 12: estep_warp_run<13, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 13: estep_warp_run<14, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 14: estep_warp_run<15, TT>(ch, sd, u, A, cnt, lz, V); break;
-      case 15: estep_warp_run<16, TT>(ch, sd, u, A, cnt, lz, V); break;
-      default: break;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && ch.weights_only && ch.trace_off >= 0) {
+      const int64_t o = ch.trace_off + (int64_t)(ch.n_iter - 1) * (SCAPE_B200_KCAP + 1);
+      for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
+      for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
     }
-  }
-  if ((threadIdx.x & 31) == 0 && ch.weights_only && ch.trace_off >= 0) {
-    const int64_t o = ch.trace_off + (int64_t)(ch.n_iter - 1) * (SCAPE_B200_KCAP + 1);
-    for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
-    for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
-  }
+    __syncwarp();
+  } while (LOOP && ch.weights_only && ch.state == 1 && ch.n_iter < SCAPE_B200_NROUND);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1104,18 +1110,32 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
     kinds.push_back(kind);
   };
   mark(-1);
-  for (int step = 0; step <= SCAPE_B200_NROUND; step++) {
+  const bool loop_only = !any_scan && n_big == 0;     // prune refits: whole chains inside one launch
+  if (loop_only) {
+    em_estep_warp_kernel<TT, false, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+        chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
+        trace_b, trace_ws);
+    launches++;
+    if (big_k) {
+      em_estep_warp_kernel<TT, true, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+          chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
+          trace_b, trace_ws);
+      launches++;
+    }
+    mark(0);
+  }
+  for (int step = 0; !loop_only && step <= SCAPE_B200_NROUND; step++) {
     // Early steps: most chains run -> one warp per chain (throughput).  Late steps: few chains run
     // and the step time is the latency of ONE chain's E pass -> one CTA per chain (8x shorter
     // fragment loop); CTAs of finished chains exit at once.
     const bool wide = step < warp_steps;
     if (n_small > 0 && wide) {
-      em_estep_warp_kernel<TT, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+      em_estep_warp_kernel<TT, false, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
           chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
           trace_b, trace_ws);
       launches++;
       if (big_k) {
-        em_estep_warp_kernel<TT, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+        em_estep_warp_kernel<TT, true, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
             chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
             trace_a, trace_b, trace_ws);
         launches++;
