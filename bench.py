@@ -47,6 +47,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def scan_traffic():
+    """DRAM bytes per em_scan_kernel launch from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
+    if not os.path.exists(p):
+        return None, "no ncu capture committed"
+    with open(p) as fh:
+        d = json.load(fh)
+    return float(d["dram_bytes_per_launch"]), d.get("source", "profiles/r01_scan_traffic.json")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -189,6 +199,14 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+    # One extra, untimed pass with the wave pipelining off: every kernel then has the GPU to itself,
+    # which is what the per-kernel roofline needs (in the timed passes the next wave's table/tensor
+    # kernels share the SMs with the EM kernels, so their event times overlap).
+    alone = None
+    if rank == 0:
+        eng.set_overlap(False)
+        alone = eng.fit(off, x, l, r, pa, sid, seeds).timing
+        eng.set_overlap(True)
     dev_ms = acc["device_busy_ms"]        # union of the kernel intervals of all lanes (CUDA events)
     work = float(out.em_work[:, 0].sum())          # sum N*(K+1) over chains and iterations, one step
     iters = float(out.em_work[:, 1].sum())
@@ -210,8 +228,9 @@ def main():
     K = args.steps
     hbm_peak, hbm_src = measured_peaks()
     fp64 = eng.fp64_peaks()                     # measured on this GPU, this run (no FP64 entry in MEASURED_PEAKS.json)
-    scan_s = acc["scan_ms"] / 1e3
-    ach_tflops = acc["em_grid_flops"] / scan_s / 1e12
+    scan_s = alone["scan_ms"] / 1e3
+    ach_tflops = alone["em_grid_flops"] / scan_s / 1e12
+    traffic, traffic_src = scan_traffic()
     res = {
         "metric": "infer_pa_utrs_per_s", "value": utr_all * K / (dev_ms / 1e3), "unit": "UTR/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
@@ -221,7 +240,8 @@ def main():
                    "seed_policy": "file", "tensor_storage": "f32 (FP64 arithmetic)",
                    "l2": "per-wave tensor working set (~0.26 GB) exceeds the 126 MB L2; nothing is flushed between steps, "
                          "every step streams 100 waves x 0.26 GB",
-                   "value_time": "GPU busy time = union of the CUDA-event kernel intervals of all lanes",
+                   "value_time": "GPU busy time = union of the CUDA-event kernel intervals (EM stream and the "
+                                 "likelihood stream that works one wave ahead)",
                    "e2e_time": "wall clock of Engine.fit (C ABI scape_b200_fit_batch) on host buffers"},
         "read_comp_em_iter_per_s": work_all * K / (dev_ms / 1e3),
         "read_comp_em_iter_per_s_e2e": work_all * K / wall,
@@ -231,20 +251,24 @@ def main():
         "gpu_launches": int(acc["launches"]),
         "roofline": {"kernel": "em_scan_kernel (max_alpha_beta grid arg-max as a blocked FP64 MMA product)",
                      "bound": "tensor", "achieved": ach_tflops, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
-                     "frac": ach_tflops / fp64["dmma_tflops"], "traffic": None,
+                     "frac": ach_tflops / fp64["dmma_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                     "timing": "CUDA events around every scan launch of one extra pass with wave pipelining off "
+                               "(kernel alone on the GPU)",
                      "peak_source": "FP64 mma.m8n8k4 stream measured in this run (scape_b200_fp64_peaks); "
                                     f"CUDA-core DFMA stream {fp64['dfma_tflops']:.1f} TFLOP/s",
-                     "algorithmic_flops_per_launch": acc["em_grid_flops"] / max(acc["scan_launches"], 1),
-                     "avg_launch_ms": acc["scan_ms"] / max(acc["scan_launches"], 1),
-                     "launches": int(acc["scan_launches"]),
-                     "share_of_gpu_time": acc["scan_ms"] / dev_ms,
-                     "hbm_view": {"algorithmic_GBps": acc["em_grid_bytes"] / scan_s / 1e9, "peak_GBps": hbm_peak,
-                                  "peak_source": hbm_src, "loaded_GBps": acc["em_scan_bytes"] / scan_s / 1e9,
+                     "algorithmic_flops_per_launch": alone["em_grid_flops"] / max(alone["scan_launches"], 1),
+                     "avg_launch_ms": alone["scan_ms"] / max(alone["scan_launches"], 1),
+                     "launches": int(alone["scan_launches"]),
+                     "share_of_gpu_time": alone["scan_ms"] / alone["device_busy_ms"],
+                     "hbm_view": {"algorithmic_GBps": alone["em_grid_bytes"] / scan_s / 1e9, "peak_GBps": hbm_peak,
+                                  "peak_source": hbm_src, "loaded_GBps": alone["em_scan_bytes"] / scan_s / 1e9,
                                   "note": "SURVEY 8d algorithmic bytes = 8*W_k*B*N per chain iteration; the blocked scan "
                                           "loads each tensor block once per step for all chains of the UTR"}},
         "phases_ms_per_step": {k: acc[k] / K for k in ("table_ms", "tensor_ms", "em_ms", "estep_ms", "scan_ms", "label_ms",
                                                         "host_prep_ms", "host_rng_ms", "device_busy_ms", "total_ms")},
-        "tensor_exp_per_s": acc["tensor_exp"] / (acc["tensor_ms"] / 1e3),
+        "phases_alone_ms": {k: alone[k] for k in ("table_ms", "tensor_ms", "em_ms", "estep_ms", "scan_ms", "label_ms",
+                                                  "device_busy_ms", "total_ms")},
+        "tensor_exp_per_s": alone["tensor_exp"] / (alone["tensor_ms"] / 1e3),
         "waves_per_step": acc["waves"] / K,
         "clocks": clocks,
     }

@@ -133,6 +133,12 @@ int scape_b200_fp64_peaks(scape_b200_handle* h, double* dfma_tflops, double* dmm
  * create time: SCAPE_B200_TENSOR=f64. */
 int scape_b200_set_tensor_dtype(scape_b200_handle* h, int bytes);
 
+/* Wave pipelining: 1 (default) = the likelihood phase (uploads, table, marginal tensor) of wave w+1
+ * runs on a second stream under the EM of wave w; 0 = strictly one phase at a time (per-kernel
+ * timings are then taken with the kernel alone on the GPU).  Results are identical either way.
+ * Environment override at create time: SCAPE_B200_OVERLAP=0. */
+int scape_b200_set_overlap(scape_b200_handle* h, int on);
+
 /* ---- kernel-seam entry points (parity tests; reference seam B3, apa_core.py:23) ------------- */
 
 /* loglik_xlr_t over a theta list (apa_core.py:620-640, taichi_core.py:183-215):

@@ -90,8 +90,28 @@ struct PinnedBuf {
 // Device-side state of one lane.  A fit splits its RNG streams over the lanes; every lane runs its
 // own wave loop in its own host thread on its own CUDA stream, so the host work of one lane (RNG
 // replay, model selection, result assembly) overlaps the kernels of the others.
+// Likelihood-phase arrays of the wave AFTER the one whose EM is running: the table and the marginal
+// tensor depend on the data only (no RNG), so they are produced one wave ahead on a second,
+// low-priority stream and fill the SMs the latency-bound EM steps leave idle.
+struct StagedBufs {
+  DevBuf<double> d_fx, d_fl, d_fr, d_fpa, d_cnt, d_theta, d_table, d_tensor;
+  DevBuf<UtrDev> d_utrs;
+  DevBuf<RowRef> d_rows, d_trows;
+  DevBuf<TileRef> d_tiles;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // before table, before tensor, after tensor
+  void release() {
+    d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
+    d_table.release(); d_tensor.release(); d_utrs.release(); d_rows.release(); d_trows.release(); d_tiles.release();
+  }
+};
+
 struct Lane {
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;       // EM, labels (high priority)
+  cudaStream_t st_lik = nullptr;   // uploads, table, tensor of the staged wave (low priority)
+  StagedBufs staged;
+  PinnedBuf<char> h_stage[2];      // pinned upload staging of the staged wave, alternating per wave
+  cudaEvent_t ev_mid = nullptr;    // recorded on `st` where the next wave's likelihood phase may start
+  int stage_step = 40;
   DevBuf<double> d_fx, d_fl, d_fr, d_fpa, d_cnt, d_theta, d_table, d_tensor, d_lz, d_v, d_trace_ws;
   DevBuf<UtrDev> d_utrs;
   DevBuf<RowRef> d_rows, d_trows;
@@ -117,6 +137,16 @@ struct Lane {
     d_refs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_counter.release(); d_jobs.release();
     h_chains.release(); h_refits.release();
+    h_stage[0].release(); h_stage[1].release();
+    staged.release();
+  }
+  // the staged wave becomes the current one (pointer swaps only)
+  void adopt_staged() {
+    std::swap(d_fx, staged.d_fx); std::swap(d_fl, staged.d_fl); std::swap(d_fr, staged.d_fr);
+    std::swap(d_fpa, staged.d_fpa); std::swap(d_cnt, staged.d_cnt); std::swap(d_theta, staged.d_theta);
+    std::swap(d_table, staged.d_table); std::swap(d_tensor, staged.d_tensor); std::swap(d_utrs, staged.d_utrs);
+    std::swap(d_rows, staged.d_rows); std::swap(d_trows, staged.d_trows); std::swap(d_tiles, staged.d_tiles);
+    for (int i = 0; i < 3; i++) std::swap(ev[i], staged.ev[i]);
   }
 };
 
@@ -136,6 +166,7 @@ struct scape_b200_handle {
   double wave_budget_bytes = 24e9;
   bool tensor_f32 = true;   // tensor storage: FP32 (default) or FP64; all arithmetic is FP64 either way
   int host_threads = 0;
+  bool overlap = true;      // likelihood phase of wave w+1 runs under the EM of wave w
 };
 
 static double now_ms() {
@@ -230,9 +261,15 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
       h->tensor_fast = true;
     }
   }
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (Lane& L : h->lanes) {
-    CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio_hi));
+    CU(cudaStreamCreateWithPriority(&L.st_lik, cudaStreamNonBlocking, prio_lo));
     for (auto& e : L.ev) CU(cudaEventCreate(&e));
+    for (auto& e : L.staged.ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&L.ev_mid, cudaEventDisableTiming));
+    if (const char* s = getenv("SCAPE_B200_STAGE_STEP")) L.stage_step = atoi(s);
     memset(&L.tm, 0, sizeof(L.tm));
   }
   CU(cudaEventCreate(&h->base_ev));
@@ -242,6 +279,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   if (const char* s = getenv("SCAPE_B200_WAVE_GB")) h->wave_budget_bytes = atof(s) * 1e9;
   if (const char* s = getenv("SCAPE_B200_THREADS")) h->host_threads = atoi(s);
   if (const char* s = getenv("SCAPE_B200_TENSOR")) h->tensor_f32 = (strcmp(s, "f64") != 0);
+  if (const char* s = getenv("SCAPE_B200_OVERLAP")) h->overlap = atoi(s) != 0;
   if (const char* s = getenv("SCAPE_B200_LANES")) h->n_lanes = std::max(1, std::min(kMaxLanes, atoi(s)));
   *out = h;
   return 0;
@@ -252,9 +290,13 @@ int scape_b200_destroy(scape_b200_handle* h) {
   cudaSetDevice(h->device);
   for (Lane& L : h->lanes) {
     cudaStreamSynchronize(L.st);
+    cudaStreamSynchronize(L.st_lik);
     L.release();
     for (auto& e : L.ev) cudaEventDestroy(e);
+    for (auto& e : L.staged.ev) cudaEventDestroy(e);
+    cudaEventDestroy(L.ev_mid);
     cudaStreamDestroy(L.st);
+    cudaStreamDestroy(L.st_lik);
   }
   cudaEventDestroy(h->base_ev);
   delete h;
@@ -265,6 +307,12 @@ int scape_b200_set_tensor_dtype(scape_b200_handle* h, int bytes) {
   if (!h) return fail(-5, "null handle");
   if (bytes != 4 && bytes != 8) return fail(-5, "tensor dtype must be 4 (float) or 8 (double) bytes");
   h->tensor_f32 = (bytes == 4);
+  return 0;
+}
+
+int scape_b200_set_overlap(scape_b200_handle* h, int on) {
+  if (!h) return fail(-5, "null handle");
+  h->overlap = on != 0;
   return 0;
 }
 
@@ -469,9 +517,22 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
   std::vector<int32_t>& stream_of = *F.stream_of;
   const int maxwin = F.maxwin, lane_threads = F.lane_threads;
   CU(cudaSetDevice(h->device));
-  for (;;) {
+  const bool overlap = h->overlap;
+  const size_t esz = h->tensor_f32 ? 4 : 8;
+
+  // Pick the next wave and put its likelihood phase (uploads, table, tensor) on the lane's second
+  // stream, into the staged buffer set.  Nothing here depends on the RNG, so it runs one wave ahead.
+  std::vector<WaveUtr> st_wave;
+  std::vector<UtrDev> st_ud;
+  int st_max_n = 0;
+  unsigned stage_no = 0;
+  auto stage = [&]() -> int {
+    StagedBufs& S = L.staged;
+    cudaStream_t sq = L.st_lik;
     // ---- pick the wave: next UTR of every stream, within the memory budget ---------------------
-    std::vector<WaveUtr> wave;
+    st_wave.clear();
+    st_ud.clear();
+    st_max_n = 0;
     double bytes = 0;
     for (int s : my_streams) {
       while (cursor[size_t(s)] < stream_utrs[size_t(s)].size()) {
@@ -479,31 +540,31 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         while (!(*F.ready)[size_t(u)].load(std::memory_order_acquire)) std::this_thread::yield();   // pre-pass still running
         if (prep[size_t(u)].status != kOk) { cursor[size_t(s)]++; continue; }   // the reference would have raised
         const UtrPrep& p = prep[size_t(u)];
-        double need = double(p.T() * p.B() + 4) * pad4(p.n()) * (h->tensor_f32 ? 4.0 : 8.0) + double(p.T()) * pad4(p.n()) * 8.0;
-        if (!wave.empty() && bytes + need > h->wave_budget_bytes) break;
+        double need = double(p.T() * p.B() + 4) * pad4(p.n()) * double(esz) + double(p.T()) * pad4(p.n()) * 8.0;
+        if (!st_wave.empty() && bytes + need > h->wave_budget_bytes) break;
         bytes += need;
         WaveUtr w;
         w.u = u;
         w.k_max = P.fixed_run_mode ? P.pre_K : P.n_max_apa;
         w.k_min = P.fixed_run_mode ? P.pre_K : P.n_min_apa;
         memset(&w.best, 0, sizeof(ChainDev));
-        wave.push_back(w);
+        st_wave.push_back(w);
         cursor[size_t(s)]++;
         break;
       }
     }
-    if (wave.empty()) break;
+    if (st_wave.empty()) return 0;
     L.tm.waves++;
 
     // ---- device layout of the wave --------------------------------------------------------------
-    const size_t W = wave.size();
-    std::vector<UtrDev> ud(W);
-    std::vector<RowRef> rows, trows;
-    std::vector<TileRef> tiles;
-    int64_t nf = 0, nt = 0, ntab = 0, nten = 0;
+    const size_t W = st_wave.size();
+    std::vector<UtrDev>& ud = st_ud;
+    ud.resize(W);
+    int64_t nf = 0, nt = 0, ntab = 0, nten = 0, n_rows = 0, n_trows = 0, n_tiles = 0;
     int max_n = 0;
+    const int i_lo = kTfHalf;
     for (size_t i = 0; i < W; i++) {
-      const UtrPrep& p = prep[size_t(wave[i].u)];
+      const UtrPrep& p = prep[size_t(st_wave[i].u)];
       UtrDev& d = ud[i];
       d.N = int32_t(p.n()); d.Npad = pad4(p.n()); d.T = int32_t(p.T()); d.B = int32_t(p.B());
       d.ldR = pad4(int64_t(d.T) * d.B);
@@ -511,63 +572,88 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       d.unif_loglik = p.unif_loglik;
       nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += d.ldR * d.N;
       max_n = std::max(max_n, d.Npad);
-      for (int t = 0; t < d.T; t++) rows.push_back({int32_t(i), t});
       // marginal tensor: interior alpha rows go to the constant-weight kernel in tiles, the rest
       // (window clipped by the grid ends) to the generic kernel
-      const int i_lo = kTfHalf, i_hi = d.T - 1 - kTfHalf;
-      for (int t = 0; t < d.T; t++)
-        if (!h->tensor_fast || t < i_lo || t > i_hi) trows.push_back({int32_t(i), t});
-      if (h->tensor_fast)
-        for (int t = i_lo; t <= i_hi; t += kTfTile) tiles.push_back({int32_t(i), t, std::min(kTfTile, i_hi - t + 1)});
+      const int n_int = h->tensor_fast ? std::max(0, d.T - 2 * kTfHalf) : 0;
+      n_rows += d.T;
+      n_trows += d.T - n_int;
+      n_tiles += (n_int + kTfTile - 1) / kTfTile;
     }
-    std::vector<double> hx(size_t(nf), 0.0), hl(size_t(nf), 0.0), hr(size_t(nf), 0.0), hpa(size_t(nf), 0.0),
-        hc(size_t(nf), 0.0), hth(static_cast<size_t>(nt));
-    for (size_t i = 0; i < W; i++) {
-      const UtrPrep& p = prep[size_t(wave[i].u)];
-      std::copy(p.x.begin(), p.x.end(), hx.begin() + ud[i].frag_off);
-      std::copy(p.l.begin(), p.l.end(), hl.begin() + ud[i].frag_off);
-      std::copy(p.r.begin(), p.r.end(), hr.begin() + ud[i].frag_off);
-      std::copy(p.pa.begin(), p.pa.end(), hpa.begin() + ud[i].frag_off);
-      std::copy(p.cnt.begin(), p.cnt.end(), hc.begin() + ud[i].frag_off);
-      std::copy(p.theta.begin(), p.theta.end(), hth.begin() + ud[i].theta_off);
+    st_max_n = max_n;
+    // one pinned blob per wave parity: the uploads are truly asynchronous (a pageable source would
+    // make cudaMemcpyAsync wait for the stream, which is parked behind the EM steps of this wave)
+    PinnedBuf<char>& blob = L.h_stage[stage_no++ & 1];
+    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t fb = sizeof(double) * size_t(nf);
+    size_t o_x = 0, o_l = o_x + up16(fb), o_r = o_l + up16(fb), o_pa = o_r + up16(fb), o_c = o_pa + up16(fb),
+           o_th = o_c + up16(fb), o_ud = o_th + up16(8 * size_t(nt)), o_rows = o_ud + up16(sizeof(UtrDev) * W),
+           o_trows = o_rows + up16(sizeof(RowRef) * size_t(n_rows)),
+           o_tiles = o_trows + up16(sizeof(RowRef) * size_t(n_trows)),
+           o_end = o_tiles + up16(sizeof(TileRef) * size_t(n_tiles));
+    CU(blob.resize(o_end));
+    double *hx = (double*)(blob.p + o_x), *hl = (double*)(blob.p + o_l), *hr = (double*)(blob.p + o_r),
+           *hpa = (double*)(blob.p + o_pa), *hc = (double*)(blob.p + o_c), *hth = (double*)(blob.p + o_th);
+    UtrDev* hud = (UtrDev*)(blob.p + o_ud);
+    RowRef *rows = (RowRef*)(blob.p + o_rows), *trows = (RowRef*)(blob.p + o_trows);
+    TileRef* tiles = (TileRef*)(blob.p + o_tiles);
+    memset(blob.p, 0, o_th);     // fragment columns are padded with zeros
+    {
+      int64_t ir = 0, it = 0, il = 0;
+      for (size_t i = 0; i < W; i++) {
+        const UtrPrep& p = prep[size_t(st_wave[i].u)];
+        const UtrDev& d = ud[i];
+        std::copy(p.x.begin(), p.x.end(), hx + d.frag_off);
+        std::copy(p.l.begin(), p.l.end(), hl + d.frag_off);
+        std::copy(p.r.begin(), p.r.end(), hr + d.frag_off);
+        std::copy(p.pa.begin(), p.pa.end(), hpa + d.frag_off);
+        std::copy(p.cnt.begin(), p.cnt.end(), hc + d.frag_off);
+        std::copy(p.theta.begin(), p.theta.end(), hth + d.theta_off);
+        hud[i] = d;
+        const int i_hi = d.T - 1 - kTfHalf;
+        for (int t = 0; t < d.T; t++) rows[ir++] = {int32_t(i), t};
+        for (int t = 0; t < d.T; t++)
+          if (!h->tensor_fast || t < i_lo || t > i_hi) trows[it++] = {int32_t(i), t};
+        if (h->tensor_fast)
+          for (int t = i_lo; t <= i_hi; t += kTfTile) tiles[il++] = {int32_t(i), t, std::min(kTfTile, i_hi - t + 1)};
+      }
+      if (ir != n_rows || it != n_trows || il != n_tiles) return fail(-5, "internal: wave row lists out of step");
     }
-    CU(L.d_fx.ensure(size_t(nf))); CU(L.d_fl.ensure(size_t(nf))); CU(L.d_fr.ensure(size_t(nf)));
-    CU(L.d_fpa.ensure(size_t(nf))); CU(L.d_cnt.ensure(size_t(nf))); CU(L.d_theta.ensure(size_t(nt)));
+    CU(S.d_fx.ensure(size_t(nf))); CU(S.d_fl.ensure(size_t(nf))); CU(S.d_fr.ensure(size_t(nf)));
+    CU(S.d_fpa.ensure(size_t(nf))); CU(S.d_cnt.ensure(size_t(nf))); CU(S.d_theta.ensure(size_t(nt)));
     int64_t max_ldr = 0;
     for (size_t i = 0; i < W; i++) max_ldr = std::max<int64_t>(max_ldr, ud[i].ldR);
     const int64_t slack = int64_t(kTensorSlackRows) * max_ldr;     // elements; see scan_subbatch's register ring
-    CU(L.d_table.ensure(size_t(ntab))); CU(L.d_tensor.ensure(size_t(nten + slack)));
-    CU(cudaMemsetAsync((char*)L.d_tensor.p + size_t(nten) * (h->tensor_f32 ? 4 : 8), 0, size_t(slack) * (h->tensor_f32 ? 4 : 8), L.st));
-    CU(L.d_utrs.ensure(W)); CU(L.d_rows.ensure(rows.size()));
-    CU(L.d_trows.ensure(trows.size() + 1)); CU(L.d_tiles.ensure(tiles.size() + 1));
-    const size_t fb = sizeof(double) * size_t(nf);
-    CU(cudaMemcpyAsync(L.d_fx.p, hx.data(), fb, cudaMemcpyHostToDevice, L.st));
-    CU(cudaMemcpyAsync(L.d_fl.p, hl.data(), fb, cudaMemcpyHostToDevice, L.st));
-    CU(cudaMemcpyAsync(L.d_fr.p, hr.data(), fb, cudaMemcpyHostToDevice, L.st));
-    CU(cudaMemcpyAsync(L.d_fpa.p, hpa.data(), fb, cudaMemcpyHostToDevice, L.st));
-    CU(cudaMemcpyAsync(L.d_cnt.p, hc.data(), fb, cudaMemcpyHostToDevice, L.st));
-    CU(cudaMemcpyAsync(L.d_theta.p, hth.data(), sizeof(double) * size_t(nt), cudaMemcpyHostToDevice, L.st));
-    CU(cudaMemcpyAsync(L.d_utrs.p, ud.data(), sizeof(UtrDev) * W, cudaMemcpyHostToDevice, L.st));
-    CU(cudaMemcpyAsync(L.d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, L.st));
-    if (!trows.empty())
-      CU(cudaMemcpyAsync(L.d_trows.p, trows.data(), sizeof(RowRef) * trows.size(), cudaMemcpyHostToDevice, L.st));
-    if (!tiles.empty())
-      CU(cudaMemcpyAsync(L.d_tiles.p, tiles.data(), sizeof(TileRef) * tiles.size(), cudaMemcpyHostToDevice, L.st));
-    L.tm.h2d_bytes += double(sizeof(RowRef) * trows.size() + sizeof(TileRef) * tiles.size());
-    L.tm.h2d_bytes += double(5 * fb + sizeof(double) * size_t(nt) + sizeof(UtrDev) * W + sizeof(RowRef) * rows.size());
+    CU(S.d_table.ensure(size_t(ntab))); CU(S.d_tensor.ensure(size_t(nten + slack)));
+    CU(cudaMemsetAsync((char*)S.d_tensor.p + size_t(nten) * esz, 0, size_t(slack) * esz, sq));
+    CU(S.d_utrs.ensure(W)); CU(S.d_rows.ensure(size_t(n_rows)));
+    CU(S.d_trows.ensure(size_t(n_trows) + 1)); CU(S.d_tiles.ensure(size_t(n_tiles) + 1));
+    CU(cudaMemcpyAsync(S.d_fx.p, hx, fb, cudaMemcpyHostToDevice, sq));
+    CU(cudaMemcpyAsync(S.d_fl.p, hl, fb, cudaMemcpyHostToDevice, sq));
+    CU(cudaMemcpyAsync(S.d_fr.p, hr, fb, cudaMemcpyHostToDevice, sq));
+    CU(cudaMemcpyAsync(S.d_fpa.p, hpa, fb, cudaMemcpyHostToDevice, sq));
+    CU(cudaMemcpyAsync(S.d_cnt.p, hc, fb, cudaMemcpyHostToDevice, sq));
+    CU(cudaMemcpyAsync(S.d_theta.p, hth, sizeof(double) * size_t(nt), cudaMemcpyHostToDevice, sq));
+    CU(cudaMemcpyAsync(S.d_utrs.p, hud, sizeof(UtrDev) * W, cudaMemcpyHostToDevice, sq));
+    CU(cudaMemcpyAsync(S.d_rows.p, rows, sizeof(RowRef) * size_t(n_rows), cudaMemcpyHostToDevice, sq));
+    if (n_trows > 0)
+      CU(cudaMemcpyAsync(S.d_trows.p, trows, sizeof(RowRef) * size_t(n_trows), cudaMemcpyHostToDevice, sq));
+    if (n_tiles > 0)
+      CU(cudaMemcpyAsync(S.d_tiles.p, tiles, sizeof(TileRef) * size_t(n_tiles), cudaMemcpyHostToDevice, sq));
+    L.tm.h2d_bytes += double(sizeof(RowRef) * size_t(n_trows) + sizeof(TileRef) * size_t(n_tiles));
+    L.tm.h2d_bytes += double(5 * fb + sizeof(double) * size_t(nt) + sizeof(UtrDev) * W + sizeof(RowRef) * size_t(n_rows));
 
     // ---- likelihood phases ----------------------------------------------------------------------
-    CU(cudaEventRecord(L.ev[0], L.st));
-    launch_table(L.d_utrs.p, L.d_rows.p, int64_t(rows.size()), max_n, L.d_fx.p, L.d_fl.p, L.d_fr.p,
-                 L.d_fpa.p, L.d_theta.p, L.d_table.p, L.st);
-    CU(cudaEventRecord(L.ev[1], L.st));
-    launch_tensor(L.d_utrs.p, L.d_trows.p, int64_t(trows.size()), max_n, P.n_beta, maxwin, L.d_theta.p,
-                  L.d_table.p, L.d_tensor.p, h->tensor_f32, L.st);
-    launch_tensor_interior(L.d_utrs.p, L.d_tiles.p, int64_t(tiles.size()), max_n, L.d_table.p, L.d_tensor.p,
-                           h->tensor_f32, L.st);
-    CU(cudaEventRecord(L.ev[2], L.st));
+    CU(cudaEventRecord(S.ev[0], sq));
+    launch_table(S.d_utrs.p, S.d_rows.p, n_rows, max_n, S.d_fx.p, S.d_fl.p, S.d_fr.p,
+                 S.d_fpa.p, S.d_theta.p, S.d_table.p, sq);
+    CU(cudaEventRecord(S.ev[1], sq));
+    launch_tensor(S.d_utrs.p, S.d_trows.p, n_trows, max_n, P.n_beta, maxwin, S.d_theta.p,
+                  S.d_table.p, S.d_tensor.p, h->tensor_f32, sq);
+    launch_tensor_interior(S.d_utrs.p, S.d_tiles.p, n_tiles, max_n, S.d_table.p, S.d_tensor.p,
+                           h->tensor_f32, sq);
+    CU(cudaEventRecord(S.ev[2], sq));
     CU(cudaGetLastError());
-    L.tm.launches += 1 + (trows.empty() ? 0 : 1) + (tiles.empty() ? 0 : 1);
+    L.tm.launches += 1 + (n_trows == 0 ? 0 : 1) + (n_tiles == 0 ? 0 : 1);
     for (size_t i = 0; i < W; i++) {
       // exp() evaluations = N * sum over (t, beta) of the clipped window sizes (regular grid)
       const UtrDev& d = ud[i];
@@ -577,6 +663,27 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         for (int t = 0; t < d.T; t++) win += std::min(d.T - 1, t + half) - std::max(0, t - half) + 1;
       }
       L.tm.tensor_exp += double(d.N) * win;
+    }
+    return 0;
+  };
+
+  if (int rc = stage()) return rc;
+  for (;;) {
+    if (st_wave.empty()) break;
+    // the staged wave becomes the current one; the EM stream waits for its tensor
+    std::vector<WaveUtr> wave = std::move(st_wave);
+    const std::vector<UtrDev> ud = std::move(st_ud);
+    const int max_n = st_max_n;
+    const size_t W = wave.size();
+    L.adopt_staged();
+    CU(cudaStreamWaitEvent(L.st, L.ev[2], 0));
+    // The next wave's likelihood phase is slotted under this wave's EM: from step `stage_step` on
+    // (most chains have converged by then and the step kernels leave SMs idle), or right away.
+    bool next_staged = false;
+    int stage_rc = 0;
+    if (overlap && L.stage_step < 0) {
+      if (int rc = stage()) return rc;
+      next_staged = true;
     }
     bool timed_lik = false;
 
@@ -633,7 +740,21 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       }
       L.tm.host_rng_ms += now_ms() - tr0;
       if (n_chains == 0) break;
-      if (int rc = run_chains(h, L, chains, n_chains, ud)) return rc;
+      if (overlap && !next_staged) {
+        L.em_events.hook_step = std::min(L.stage_step, SCAPE_B200_NROUND - 1);
+        L.em_events.hook = [&]() {
+          cudaEventRecord(L.ev_mid, L.st);
+          cudaStreamWaitEvent(L.st_lik, L.ev_mid, 0);
+          stage_rc = stage();
+          next_staged = true;
+        };
+      }
+      {
+        const int rc = run_chains(h, L, chains, n_chains, ud);
+        L.em_events.hook = nullptr;
+        if (rc) return rc;
+        if (stage_rc) return stage_rc;
+      }
       if (!timed_lik) {
         float a = 0, b = 0;
         CU(cudaEventElapsedTime(&a, L.ev[0], L.ev[1]));
@@ -777,6 +898,8 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       int64_t* dst = out->label + bt->read_off[u];
       for (int64_t r = 0; r < p.n_reads; r++) dst[r] = lb[p.read_to_bin[size_t(r)]];
     }
+    if (!next_staged)
+      if (int rc = stage()) return rc;
   }
   return 0;
 }

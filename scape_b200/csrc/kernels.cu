@@ -1093,7 +1093,8 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
                              const int32_t* utr_chain_off_dev, const void* tensor, const double* cnt, double* lz,
                              double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
                              double* trace_ws, cudaStream_t st, std::vector<cudaEvent_t>& evs,
-                             std::vector<int>& kinds, int& scan_launches) {
+                             std::vector<int>& kinds, int& scan_launches, const std::function<void()>& hook,
+                             int hook_step) {
   const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
   cudaFuncSetAttribute(em_scan_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
@@ -1155,6 +1156,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
     launches++;
     scan_launches++;
     mark(1);
+    if (hook && step == hook_step) hook();
   }
   if (dbg) {
     cudaStreamSynchronize(st);
@@ -1179,10 +1181,10 @@ int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* in
   if (f32)
     return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
                                     utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches);
+                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step);
   return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
                                    utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches);
+                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step);
 }
 
 // After the stream has been synchronised: total E-step and scan kernel time of the last run.

@@ -21,6 +21,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <functional>
 #include <vector>
 
 #include "../../include/scape_b200.h"
@@ -127,6 +128,10 @@ struct EmStepEvents {
   std::vector<cudaEvent_t> evs;
   std::vector<int> kinds;
   int scan_launches = 0;
+  // called once, on the host, after the launches of step `hook_step` have been issued (the wave
+  // scheduler uses it to slot the next wave's likelihood phase under the thinly filled late steps)
+  std::function<void()> hook;
+  int hook_step = 0;
 };
 void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms);
 int measure_fp64_peaks(int n_sm, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
