@@ -7,12 +7,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "host_prep.hpp", "np_rng.hpp")] + \
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "host_prep.hpp", "np_rng.hpp", "work_pool.hpp")] + \
     [os.path.join(os.path.dirname(HERE), "include", "scape_b200.h")]
 LIB = os.path.join(HERE, "libscape_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC,-O3,-pthread,-fopenmp", "-shared", "-cudart", "static", "-lgomp"]
+         "-Xcompiler", "-fPIC,-O3,-pthread", "-shared", "-cudart", "static"]
 
 
 def needs_build() -> bool:

@@ -18,11 +18,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <memory>
 #include <thread>
 #include <vector>
 
 #include "host_prep.hpp"
 #include "kernels.cuh"
+#include "work_pool.hpp"
 
 using namespace scape;
 
@@ -109,6 +111,7 @@ struct Lane {
   cudaStream_t st = nullptr;       // EM, labels (high priority)
   cudaStream_t st_lik = nullptr;   // uploads, table, tensor of the staged wave (low priority)
   StagedBufs staged;
+  std::unique_ptr<WorkPool> pool;  // host workers of this lane's wave loop (sleep between regions)
   PinnedBuf<char> h_stage[2];      // pinned upload staging of the staged wave, alternating per wave
   cudaEvent_t ev_mid = nullptr;    // recorded on `st` where the next wave's likelihood phase may start
   int stage_step = 40;
@@ -165,7 +168,8 @@ struct scape_b200_handle {
   scape_b200_timing tm;
   double wave_budget_bytes = 24e9;
   bool tensor_f32 = true;   // tensor storage: FP32 (default) or FP64; all arithmetic is FP64 either way
-  int host_threads = 0;
+  int host_threads = 0;     // 0 = CPUs of this process / ranks sharing the host
+  std::unique_ptr<WorkPool> prep_pool;
   bool overlap = true;      // likelihood phase of wave w+1 runs under the EM of wave w
 };
 
@@ -474,18 +478,6 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   return 0;
 }
 
-// OpenMP team per calling thread: the worker threads persist between calls, so the ~300 parallel
-// regions of a fit (3 per wave) do not pay thread creation each time.
-void parallel_for(int64_t n, int threads, const std::function<void(int64_t)>& fn) {
-  if (threads <= 0) threads = int(std::thread::hardware_concurrency());
-  threads = int(std::max<int64_t>(1, std::min<int64_t>(threads, n)));
-  if (threads == 1) {
-    for (int64_t i = 0; i < n; i++) fn(i);
-    return;
-  }
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
-  for (int64_t i = 0; i < n; i++) fn(i);
-}
 }  // namespace
 
 namespace {
@@ -501,7 +493,6 @@ struct FitShared {
   std::vector<size_t>* cursor;
   std::vector<int32_t>* stream_of;
   int maxwin;
-  int lane_threads;
 };
 
 // The wave loop of one lane over its own streams.
@@ -515,7 +506,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
   std::vector<NpRandomState>& rng = *F.rng;
   std::vector<size_t>& cursor = *F.cursor;
   std::vector<int32_t>& stream_of = *F.stream_of;
-  const int maxwin = F.maxwin, lane_threads = F.lane_threads;
+  const int maxwin = F.maxwin;
   CU(cudaSetDevice(h->device));
   const bool overlap = h->overlap;
   const size_t esz = h->tensor_f32 ? 4 : 8;
@@ -537,7 +528,8 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     for (int s : my_streams) {
       while (cursor[size_t(s)] < stream_utrs[size_t(s)].size()) {
         int64_t u = stream_utrs[size_t(s)][cursor[size_t(s)]];
-        while (!(*F.ready)[size_t(u)].load(std::memory_order_acquire)) std::this_thread::yield();   // pre-pass still running
+        while (!(*F.ready)[size_t(u)].load(std::memory_order_acquire))      // pre-pass still running
+          std::this_thread::sleep_for(std::chrono::microseconds(50));
         if (prep[size_t(u)].status != kOk) { cursor[size_t(s)]++; continue; }   // the reference would have raised
         const UtrPrep& p = prep[size_t(u)];
         double need = double(p.T() * p.B() + 4) * pad4(p.n()) * double(esz) + double(p.T()) * pad4(p.n()) * 8.0;
@@ -698,7 +690,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       CU(L.h_chains.resize(first_chain[W]));
       ChainDev* chains = L.h_chains.p;
       std::atomic<int> n_failed(0);
-      parallel_for(int64_t(W), lane_threads, [&](int64_t ii) {
+      L.pool->run(int64_t(W), [&](int64_t ii) {
         const size_t i = size_t(ii);
         WaveUtr& w = wave[i];
         if (w.done) return;
@@ -772,15 +764,26 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       size_t n_refits = 0;
       std::vector<size_t> refit_owner;
       tr0 = now_ms();
-      size_t pos = 0;
-      for (size_t i = 0; i < W; i++) {
+      std::vector<size_t> pos_of(W, 0);
+      {
+        size_t pos = 0;
+        for (size_t i = 0; i < W; i++)
+          if (!wave[i].done) {
+            pos_of[i] = pos;
+            pos += size_t(wave[i].k_max - wave[i].k_min + 1) * SCAPE_B200_NTRIAL;
+          }
+      }
+      std::vector<char> need_refit(W, 0);
+      L.pool->run(int64_t(W), [&](int64_t ii) {     // one task per UTR: its own chains, its own RNG stream
+        const size_t i = size_t(ii);
         WaveUtr& w = wave[i];
-        if (w.done) continue;
+        if (w.done) return;
+        const size_t pos = pos_of[i];
         const int nK = w.k_max - w.k_min + 1;
         std::vector<double> bic_k(static_cast<size_t>(nK));
         std::vector<size_t> best_k(static_cast<size_t>(nK));
+        std::vector<double> b(SCAPE_B200_NTRIAL);
         for (int ik = 0; ik < nK; ik++) {
-          std::vector<double> b(SCAPE_B200_NTRIAL);
           for (int t = 0; t < SCAPE_B200_NTRIAL; t++) {
             const ChainDev& c = chains[pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(t)];
             b[size_t(t)] = c.bic;
@@ -791,7 +794,6 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
           best_k[size_t(ik)] = pos + size_t(ik) * SCAPE_B200_NTRIAL + size_t(m);
           bic_k[size_t(ik)] = b[size_t(m)];
         }
-        pos += size_t(nK) * SCAPE_B200_NTRIAL;
         w.chains_run += nK * SCAPE_B200_NTRIAL;
         w.sweeps++;
         w.best = chains[best_k[size_t(np_argmin(bic_k))]];
@@ -801,7 +803,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
           for (int k = 0; k < w.best.K; k++)
             if (!(w.best.ws[k] < P.min_ws)) keep[nk++] = k;
           if (nk < w.best.K) {
-            ChainDev& c = refits[n_refits++];
+            ChainDev& c = refits[i];          // slot i; compacted below
             memset(&c, 0, sizeof(c));
             c.utr = int32_t(i); c.K = nk; c.weights_only = 1;
             for (int k = 0; k < nk; k++) { c.a_idx[k] = w.best.a_idx[keep[k]]; c.b_idx[k] = w.best.b_idx[keep[k]]; }
@@ -810,10 +812,16 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
             draw_refit(rng[size_t(stream_of[size_t(w.u)])], P, ci);
             memcpy(c.ws, ci.ws, sizeof(ci.ws));
             memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
-            refit_owner.push_back(i);
+            need_refit[i] = 1;
           }
         }
-      }
+      });
+      for (size_t i = 0; i < W; i++)
+        if (need_refit[i]) {
+          if (n_refits != i) refits[n_refits] = refits[i];
+          refit_owner.push_back(i);
+          n_refits++;
+        }
       L.tm.host_rng_ms += now_ms() - tr0;
       if (int rc = run_chains(h, L, refits, n_refits, ud)) return rc;
       for (size_t j = 0; j < n_refits; j++) {
@@ -938,9 +946,14 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
                      [&](int64_t a, int64_t b) { return rank[size_t(a)] < rank[size_t(b)]; });
   }
   double prep_ms = 0;
+  {
+    const int nt = h->host_threads > 0 ? h->host_threads : default_host_threads();
+    if (!h->prep_pool || h->prep_pool->threads() != nt) h->prep_pool.reset(new WorkPool(nt, true));
+  }
   std::thread prep_thread([&]() {
+    WorkPool::lower_priority();
     const double t0 = now_ms();
-    parallel_for(U, h->host_threads, [&](int64_t i) {
+    h->prep_pool->run(U, [&](int64_t i) {
       const int64_t u = prep_order[size_t(i)];
       const int64_t a = bt->read_off[u], n = bt->read_off[u + 1] - a;
       UtrPrep& p = prep[size_t(u)];
@@ -995,9 +1008,11 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   const int n_lanes = std::max(1, std::min(h->n_lanes, S));
   std::vector<std::vector<int>> lane_streams(static_cast<size_t>(n_lanes));
   for (int s = 0; s < S; s++) lane_streams[size_t(s % n_lanes)].push_back(s);
-  int total_threads = h->host_threads > 0 ? h->host_threads : int(std::thread::hardware_concurrency());
-  FitShared F{h, bt, out, &prep, &ready, &stream_utrs, &rng, &cursor, &stream_of, maxwin,
-              std::max(1, total_threads / n_lanes)};
+  const int total_threads = h->host_threads > 0 ? h->host_threads : default_host_threads();
+  const int per_lane = std::max(1, total_threads / n_lanes);
+  for (int l = 0; l < n_lanes; l++)
+    if (!h->lanes[l].pool || h->lanes[l].pool->threads() != per_lane) h->lanes[l].pool.reset(new WorkPool(per_lane));
+  FitShared F{h, bt, out, &prep, &ready, &stream_utrs, &rng, &cursor, &stream_of, maxwin};
   for (int l = 0; l < n_lanes; l++) {
     Lane& L = h->lanes[l];
     memset(&L.tm, 0, sizeof(L.tm));
