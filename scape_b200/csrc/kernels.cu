@@ -272,7 +272,12 @@ __global__ void __launch_bounds__(TF_THREADS) tensor_interior_kernel(const UtrDe
   const double* tab = table + u.table_off + n + (int64_t)(tr.i0 - TF_HALF) * ld;
   const int cols = tr.cnt + TF_W - 1;
   double M = tab[0];
-  for (int c = 1; c < cols; c++) M = fmax(M, tab[(int64_t)c * ld]);
+  uint64_t live = tab[0] > -1e30 ? 1ull : 0ull;        // bit c: theta column c is compatible with this fragment
+  for (int c = 1; c < cols; c++) {
+    const double v = tab[(int64_t)c * ld];
+    M = fmax(M, v);
+    live |= (v > -1e30 ? 1ull : 0ull) << c;
+  }
   TT* out = tensor + u.tensor_off + (int64_t)n * u.ldR + (int64_t)tr.i0 * TF_B;
   if (M < -1e30) {                             // incompatible with every theta of the tile: all sentinel
     for (int e = 0; e < tr.cnt * TF_B; e++) out[e] = TT(SCAPE_SENTINEL);
@@ -295,11 +300,15 @@ __global__ void __launch_bounds__(TF_THREADS) tensor_interior_kernel(const UtrDe
 #pragma unroll
     for (int j = 0; j < TF_B; j++) {
       double res;
+      const int hw = c_tf_hw[j];
       if (acc[j] > 1e-290) {
         res = log(acc[j]) + M;
+      } else if ((live & (((2ull << (2 * hw)) - 1ull) << (ii + TF_HALF - hw))) == 0ull) {
+        // beta_j's own window holds incompatible thetas only (the common case at the edge of the
+        // fragment's compatible range): the exact path below would return the sentinel
+        res = SCAPE_SENTINEL;
       } else {
         // exact two-pass log-sum-exp over beta_j's own window (taichi_core.py:41-54, 172-179)
-        const int hw = c_tf_hw[j];
         const double* col = tab + (int64_t)(ii + TF_HALF - hw) * ld;
         const double* lp = c_tf_lp + j * TF_W + (TF_HALF - hw);
         const double lps = c_tf_lps[j];
