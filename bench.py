@@ -98,22 +98,23 @@ def pack(utrs):
 
 
 def _cpu_fit_one(args):
-    idx, reads = args
+    idx, reads = args[0], args[1]
     from oracle import scape_oracle as so
     from scape_b200 import synth
-    u = synth.make_utr(idx, reads)
+    u = synth.make_utr(idx, reads, long_utr=bool(args[2]) if len(args) > 2 else False)
     t = time.perf_counter()
     res = so.fit_utr(u.x, u.l, u.r, u.pa, np.random.RandomState(1))
     return time.perf_counter() - t, res.n_frag, res.K
 
 
-def cpu_sample(first, count, reads, cores):
-    """Oracle port on `cores` processes over UTRs [first, first+count) of the workload; wall clock."""
+def cpu_sample(first, count, reads, cores, jobs=None):
+    """Oracle port on `cores` processes over UTRs [first, first+count) of the workload (or the explicit
+    (index, reads, long_utr) job list); wall clock."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        rows = pool.map(_cpu_fit_one, [(first + i, reads) for i in range(count)], chunksize=1)
+        rows = pool.map(_cpu_fit_one, jobs or [(first + i, reads) for i in range(count)], chunksize=1)
     wall = time.perf_counter() - t0
     return count / wall, wall, rows
 
@@ -154,6 +155,9 @@ def main():
     ap.add_argument("--reads", type=int, default=READS)
     ap.add_argument("--per-file", type=int, default=PER_FILE)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[1..4]; cfg2 is the benchmark line, the others are reported beside it")
+    ap.add_argument("--kmax", type=int, default=5, help="n_max_apa (cfg5 sweeps it)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -168,13 +172,44 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from scape_b200 import _lib, synth
-    utrs = synth.make_batch(args.utrs, args.reads, first=rank * args.utrs)
+    from scape_b200 import _lib, shard, synth
+    scaling = "weak"
+    pre_para = None
+    if args.workload == "cfg2":
+        utrs = synth.make_batch(args.utrs, args.reads, first=rank * args.utrs)
+        label = (f"cfg-2: synthetic {args.utrs} UTRs x {args.reads} reads per GPU, Kmax={args.kmax}, "
+                 f"{(args.utrs + args.per_file - 1) // args.per_file} chunk files = RNG streams (seed 1 each)")
+    elif args.workload in ("cfg3", "cfg4"):
+        # 20k heavy-tailed UTRs in TOTAL (strong scaling): chunk files are bin-packed over the ranks
+        # by the a-priori cost model (scape_b200/shard.py), every rank generates and fits only its own
+        total = args.utrs if args.utrs != N_UTR else 20000
+        counts = synth.heavy_tail_read_counts(total)
+        cut = np.quantile(synth.heavy_tail_read_counts(max(total, 1000)), 0.99)
+        files = [list(range(f, min(f + args.per_file, total))) for f in range(0, total, args.per_file)]
+        costs = shard.stream_costs([[counts[i] for i in f] for f in files],
+                                   [[20000 if counts[i] >= cut else 2000 for i in f] for f in files])
+        mine = shard.lpt_partition(costs, world)[rank]
+        utrs = [synth.make_utr(i, int(counts[i]), long_utr=bool(counts[i] >= cut)) for f in mine for i in files[f]]
+        scaling = "strong"
+        label = (f"cfg-3: synthetic {total} UTRs in total, heavy-tailed reads per UTR (10..200k, median 600), "
+                 f"{len(files)} chunk files cost-balanced (LPT) over {world} GPU(s), Kmax={args.kmax}")
+        if args.workload == "cfg4":
+            class _Pre:           # what --pre_para_pkl_file supplies: first Parameters object of the file
+                alpha_arr = np.array([500, 900, 1400]); beta_arr = np.array([20.0, 35.0, 30.0]); K = 3; L = 21000
+            pre_para = _Pre
+            label = label.replace("cfg-3", "cfg-4 (pre_para fixed mode, K=3, restricted theta grid)")
+        args.utrs = len(utrs)
+    else:
+        # cfg-5 point: 256 independent UTRs (one stream each, so all of them are one wave)
+        args.utrs = min(args.utrs, 256)
+        args.per_file = 1
+        utrs = synth.make_batch(args.utrs, args.reads, first=rank * args.utrs)
+        label = f"cfg-5 point: {args.utrs} UTRs x {args.reads} reads, n_max_apa={args.kmax}, one stream per UTR"
     off, x, l, r, pa = pack(utrs)
     n_files = (args.utrs + args.per_file - 1) // args.per_file
     sid = (np.arange(args.utrs) // args.per_file).astype(np.int32)
     seeds = np.ones(n_files, np.uint32)
-    eng = _lib.Engine(_lib.make_params(), device=local)
+    eng = _lib.Engine(_lib.make_params(pre_para=pre_para, n_max_apa=args.kmax), device=local)
 
     def barrier():
         if dist is not None:
@@ -234,9 +269,8 @@ def main():
     res = {
         "metric": "infer_pa_utrs_per_s", "value": utr_all * K / (dev_ms / 1e3), "unit": "UTR/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg-2: synthetic {args.utrs} UTRs x {args.reads} reads per GPU, Kmax=5, "
-                               f"{n_files} chunk files = RNG streams (seed 1 each)",
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label,
                    "seed_policy": "file", "tensor_storage": "f32 (FP64 arithmetic)",
                    "l2": "per-wave tensor working set (~0.26 GB) exceeds the 126 MB L2; nothing is flushed between steps, "
                          "every step streams 100 waves x 0.26 GB",
@@ -275,9 +309,19 @@ def main():
     if not args.no_cpu:
         cores = os.cpu_count() or 1
         n = cores * 2
-        v, wall_cpu, rows = cpu_sample(0, n, args.reads, cores)
-        res["cpu_baseline"] = {"value": v, "unit": "UTR/s", "cores": cores, "kind": "port",
-                               "sample": f"first {n} UTRs of the workload, oracle port, {wall_cpu:.1f} s wall"}
+        if args.workload == "cfg3":
+            # bounded sample: the first 2*cores UTRs of the set with at most 5000 reads (a 100k-read UTR
+            # alone takes the oracle minutes); it therefore flatters the CPU arm on this workload
+            jobs = [(i, int(c), bool(c >= cut)) for i, c in enumerate(counts) if c <= 5000][:n]
+            v, wall_cpu, rows = cpu_sample(0, n, args.reads, cores, jobs=jobs)
+            sample = f"first {len(jobs)} UTRs with <= 5000 reads of the heavy-tailed set, oracle port, {wall_cpu:.1f} s wall"
+        elif args.workload == "cfg2":
+            v, wall_cpu, rows = cpu_sample(0, n, args.reads, cores)
+            sample = f"first {n} UTRs of the workload, oracle port, {wall_cpu:.1f} s wall"
+        else:
+            v = None
+        if v is not None:
+            res["cpu_baseline"] = {"value": v, "unit": "UTR/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(res))
     if dist is not None:
         dist.destroy_process_group()
