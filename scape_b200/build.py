@@ -23,15 +23,34 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the translation units in parallel (objects under csrc/_obj/), then link."""
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRC
+    obj_dir = os.path.join(HERE, "csrc", "_obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    cflags = [f for f in FLAGS if f not in ("-shared",)] + (["-Xptxas", "-v"] if verbose else [])
+    procs = []
+    for src in SRC:
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        fresh = (not force and os.path.exists(obj) and
+                 all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in DEPS))
+        cmd = [NVCC] + cflags + ["-c", "-o", obj, src]
+        procs.append((obj, cmd, None if fresh else subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                                                    stderr=subprocess.STDOUT, text=True)))
+    for obj, cmd, pr in procs:
+        if pr is None:
+            continue
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        if verbose:
+            sys.stderr.write(out)
+    cmd = [NVCC] + FLAGS + ["-o", LIB] + [o for o, _, _ in procs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc link failed: " + " ".join(cmd))
     return LIB
 
 

@@ -157,6 +157,7 @@ constexpr int kMaxLanes = 4;
 
 struct scape_b200_handle {
   int device = 0;
+  int n_sm = 148;
   scape_b200_params P;
   ModelConst mc;
   Lane lanes[kMaxLanes];
@@ -238,6 +239,11 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   CU(cudaSetDevice(device));
   scape_b200_handle* h = new scape_b200_handle();
   h->device = device;
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->n_sm = prop.multiProcessorCount;
+  }
   h->P = *params;
   fill_model_const(h->P, h->mc);
   {
@@ -407,21 +413,65 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   for (size_t i = 0; i < W; i++) chain_off[i + 1] += chain_off[i];
   std::vector<int32_t> index;
   index.reserve(chains.size());
+  static const int warp_max_n = getenv("SCAPE_B200_WARP_MAXN") ? atoi(getenv("SCAPE_B200_WARP_MAXN")) : kWarpEstepMaxN;
   for (size_t i = 0; i < chains.size(); i++)
-    if (utrs_host[size_t(chains[i].utr)].N <= kWarpEstepMaxN) index.push_back(int32_t(i));
+    if (utrs_host[size_t(chains[i].utr)].N <= warp_max_n) index.push_back(int32_t(i));
   const int64_t n_small = int64_t(index.size());
   // same-K chains next to each other: the warps resident on an SM then run the same template
-  // instantiation of the E step (instruction-cache locality; 24 % 'no instruction' stalls otherwise)
-  std::stable_sort(index.begin(), index.end(), [&](int32_t a, int32_t b) { return chains[size_t(a)].K > chains[size_t(b)].K; });
+  // instantiation of the E step (instruction-cache locality; 24 % 'no instruction' stalls otherwise);
+  // within one K the chains with the longest fragment loop go first (a warp's time is ~ N / 32
+  // fragment passes, the launch ends with the slowest warp)
+  std::stable_sort(index.begin(), index.end(), [&](int32_t a, int32_t b) {
+    const ChainDev &ca = chains[size_t(a)], &cb = chains[size_t(b)];
+    if (ca.K != cb.K) return ca.K > cb.K;
+    return utrs_host[size_t(ca.utr)].N > utrs_host[size_t(cb.utr)].N;
+  });
   for (size_t i = 0; i < chains.size(); i++)
-    if (utrs_host[size_t(chains[i].utr)].N > kWarpEstepMaxN) index.push_back(int32_t(i));
+    if (utrs_host[size_t(chains[i].utr)].N > warp_max_n) index.push_back(int32_t(i));
   const int64_t n_big = int64_t(index.size()) - n_small;
+  // Scan work items.  A CTA's cost is (fragments of the UTR) x (chains it multiplies); the step ends
+  // with the slowest CTA.  UTRs whose single-CTA cost is above half of an even share of the wave's
+  // work over the resident CTA slots get their chain sub-batches narrowed (32 -> 16 -> 8 chains) and
+  // dealt to separate CTAs (the tensor block is then re-read from L2, which a big UTR can afford).
+  // Items are issued most expensive first.
   std::vector<ScanRef> refs;
-  for (size_t i = 0; i < W; i++)
-    if (scans[i]) {
-      const int32_t n_blk = int32_t((int64_t(utrs_host[i].T) * utrs_host[i].B + kScanRows - 1) / kScanRows);
-      for (int32_t b = 0; b < n_blk; b++) refs.push_back(ScanRef{int32_t(i), b});
+  {
+    static const int split_mode = getenv("SCAPE_B200_SCAN_SPLIT") ? atoi(getenv("SCAPE_B200_SCAN_SPLIT")) : 1;
+    const double slots = 2.0 * h->n_sm;
+    double total = 0;
+    for (size_t i = 0; i < W; i++)
+      if (scans[i]) {
+        const UtrDev& u = utrs_host[i];
+        const double n_blk = double((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
+        total += n_blk * u.N * double(chain_off[i + 1] - chain_off[i]);
+      }
+    const double limit = std::max(0.5 * total / slots, 2048.0);
+    std::vector<double> cost;
+    for (size_t i = 0; i < W; i++)
+      if (scans[i]) {
+        const UtrDev& u = utrs_host[i];
+        const int32_t n_blk = int32_t((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
+        const int C = chain_off[i + 1] - chain_off[i];
+        int gb = 32, nsb = 1;
+        if (split_mode && double(u.N) * C > limit) {
+          while (gb > 8 && double(u.N) * std::min(gb, C) > limit) gb /= 2;
+          nsb = (C + gb - 1) / gb;
+        }
+        for (int32_t b = 0; b < n_blk; b++)
+          for (int s = 0; s < nsb; s++) {
+            refs.push_back(ScanRef{int32_t(i), b, int16_t(s), int16_t(nsb), int16_t(gb), 0});
+            cost.push_back(double(u.N) * std::min(nsb == 1 ? C : gb, C));
+          }
+      }
+    if (split_mode) {
+      std::vector<size_t> ord(refs.size());
+      for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+      std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
+      std::vector<ScanRef> sorted(refs.size());
+      for (size_t i = 0; i < ord.size(); i++) sorted[i] = refs[ord[i]];
+      refs.swap(sorted);
     }
+  }
   CU(L.d_lz.ensure(size_t(lz)));
   CU(L.d_v.ensure(size_t(vsz + 8)));
   CU(L.d_chains.ensure(chains.size()));

@@ -1068,22 +1068,25 @@ em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ de
   }
   __syncthreads();
   const int n_list = min(sh.n_list, SCAN_MAXCH);
-  if (n_list == 0) return;
-  // deterministic sub-batches: order the list by chain index (tiny insertion sort by one thread)
-  if (tid == 0) {
-    for (int i = 1; i < n_list; i++) {
-      const int v = sh.list[i];
-      int j = i - 1;
-      while (j >= 0 && sh.list[j] > v) { sh.list[j + 1] = sh.list[j]; j--; }
-      sh.list[j + 1] = v;
+  if (ref.sb * ref.gb >= n_list) return;                          // nothing (left) for this CTA's share
+  // deterministic sub-batches: order the list by chain index (rank sort, one thread per entry;
+  // the indices are distinct, so the ranks are a permutation)
+  {
+    int mine = 0, rank = 0;
+    if (tid < n_list) {
+      mine = sh.list[tid];
+      for (int i = 0; i < n_list; i++) rank += sh.list[i] < mine;
     }
+    __syncthreads();
+    if (tid < n_list) sh.list[rank] = mine;
+    __syncthreads();
   }
-  __syncthreads();
   double* Vs = sm_dyn;                                           // [SCAN_GB][SCAN_VPITCH]
   const TT* A = (const TT*)tensor + u.tensor_off;
 #define SCAN_CALL(G) scan_subbatch<G, TT>(sh, descs, u, A, v_all, partials, first, cnt, ref.blk, Vs, scan_elems)
-  for (int first = 0; first < n_list; first += SCAN_GB) {
-    const int cnt = min(SCAN_GB, n_list - first);
+  const int gb = ref.gb;
+  for (int first = ref.sb * gb; first < n_list; first += ref.nsb * gb) {
+    const int cnt = min(gb, n_list - first);
     if (cnt <= 8) SCAN_CALL(1);
     else if (cnt <= 16) SCAN_CALL(2);
     else if (cnt <= 24) SCAN_CALL(3);

@@ -80,10 +80,15 @@ struct ScanDesc {
   int64_t v_off, pb_off;
 };
 
-// (UTR, block of candidate rows) work item of the scan kernel
+// (UTR, block of candidate rows, share of the chain sub-batches) work item of the scan kernel.
+// The CTA lists the chains that need the block, cuts the list into sub-batches of `gb` chains and
+// takes sub-batches sb, sb + nsb, sb + 2 nsb ...  nsb = 1 means one CTA does them all.  Big UTRs
+// (long fragment loop, few row blocks) are cut finer by the host so that one step's work spreads
+// over all SMs instead of a handful (the step time is the slowest CTA).
 struct ScanRef {
   int32_t utr;
   int32_t blk;
+  int16_t sb, nsb, gb, pad;
 };
 
 struct LabelDev {
@@ -135,7 +140,7 @@ struct EmStepEvents {
 };
 void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms);
 int measure_fp64_peaks(int n_sm, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
-constexpr int kWarpEstepMaxN = 1024;   // UTRs with at most this many fragments use the warp-per-chain E step
+constexpr int kWarpEstepMaxN = 384;    // UTRs with at most this many fragments use the warp-per-chain E step (a warp needs ~4 us per 32 fragments: above this the launch is bound by its longest warp)
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
                     bool big_k,
                     const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
