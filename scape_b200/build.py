@@ -32,8 +32,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SRC:
         obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        deps = [src] + [d for d in DEPS if not d.endswith(".cu")]
         fresh = (not force and os.path.exists(obj) and
-                 all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in DEPS))
+                 all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps))
         cmd = [NVCC] + cflags + ["-c", "-o", obj, src]
         procs.append((obj, cmd, None if fresh else subprocess.Popen(cmd, stdout=subprocess.PIPE,
                                                                     stderr=subprocess.STDOUT, text=True)))
@@ -46,11 +47,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
         if verbose:
             sys.stderr.write(out)
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + [o for o, _, _ in procs]
+    tmp = LIB + ".tmp%d" % os.getpid()      # link beside the target, then rename: the .so is never half-written
+    cmd = [NVCC] + FLAGS + ["-o", tmp] + [o for o, _, _ in procs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc link failed: " + " ".join(cmd))
+    os.replace(tmp, LIB)
     return LIB
 
 

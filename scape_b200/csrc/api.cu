@@ -123,7 +123,7 @@ struct Lane {
   DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
   DevBuf<ScanRef> d_refs;
   DevBuf<ScanDesc> d_descs;
-  DevBuf<int32_t> d_chain_off, d_chain_idx;
+  DevBuf<int32_t> d_chain_off, d_chain_idx, d_lists, d_counts;
   DevBuf<double> d_partials, d_counter;
   DevBuf<LabelDev> d_jobs;
   PinnedBuf<ChainDev> h_chains, h_refits;
@@ -138,6 +138,7 @@ struct Lane {
     d_table.release(); d_tensor.release(); d_lz.release(); d_v.release(); d_trace_ws.release(); d_utrs.release();
     d_rows.release(); d_trows.release(); d_tiles.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
     d_refs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
+    d_lists.release(); d_counts.release();
     d_counter.release(); d_jobs.release();
     h_chains.release(); h_refits.release();
     h_stage[0].release(); h_stage[1].release();
@@ -497,10 +498,26 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   CU(cudaEventRecord(L.ev[4], L.st));
   bool big_k = false;
   for (auto& c : chains) big_k = big_k || c.K > 7;
+  EstepPlan plan;
+  {
+    static const bool group_steps = getenv("SCAPE_B200_ESTEP") && atoi(getenv("SCAPE_B200_ESTEP")) != 0;
+    static const bool warp_pf = getenv("SCAPE_B200_WARP_PF") ? atoi(getenv("SCAPE_B200_WARP_PF")) != 0 : true;
+    static const int g_env = getenv("SCAPE_B200_ESTEP_G") ? atoi(getenv("SCAPE_B200_ESTEP_G")) : 0;
+    CU(L.d_lists.ensure(2 * chains.size() + 2));
+    CU(L.d_counts.ensure(2 * (SCAPE_B200_NROUND + 2)));
+    plan.lists = L.d_lists.p;
+    plan.counts = L.d_counts.p;
+    plan.n_sm = h->n_sm;
+    plan.group_steps = group_steps;
+    plan.warp_prefetch = warp_pf;
+    // 4 warps per chain for the small class whatever else is in the wave: a chain's sums must not
+    // depend on the composition of its wave
+    plan.g_small = (g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) ? g_env : 4;
+  }
   int nl = launch_em_steps(L.d_chains.p, L.d_descs.p, L.d_chain_idx.p, n_small, n_big, any_scan, big_k, L.d_refs.p, int64_t(refs.size()),
                            L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_lz.p,
                            L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
-                           L.d_trace_ws.p, L.st, L.em_events);
+                           L.d_trace_ws.p, L.st, L.em_events, plan);
   CU(cudaGetLastError());
   CU(cudaEventRecord(L.ev[5], L.st));
   double scan_elems = 0;
@@ -709,6 +726,75 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     return 0;
   };
 
+  // RNG replay of the initial chains of a wave (apa_core.py:781-829, 655-677): serial per stream,
+  // streams are independent -> one task per UTR of the wave, each writing its chains in place into
+  // the lane's pinned staging buffer.  Returns the number of chains (UTRs whose initialisation
+  // raised inside the reference are marked done and their chains dropped).
+  auto draw_wave = [&](std::vector<WaveUtr>& wv, size_t& n_chains_out) -> int {
+    const size_t W = wv.size();
+    std::vector<size_t> first_chain(W + 1, 0);
+    for (size_t i = 0; i < W; i++)
+      first_chain[i + 1] = first_chain[i] + (wv[i].done ? 0 : size_t(wv[i].k_max - wv[i].k_min + 1) * SCAPE_B200_NTRIAL);
+    CU(L.h_chains.resize(first_chain[W]));
+    ChainDev* chains = L.h_chains.p;
+    std::atomic<int> n_failed(0);
+    L.pool->run(int64_t(W), [&](int64_t ii) {
+      const size_t i = size_t(ii);
+      WaveUtr& w = wv[i];
+      if (w.done) return;
+      const UtrPrep& p = prep[size_t(w.u)];
+      NpRandomState& g = rng[size_t(stream_of[size_t(w.u)])];
+      ChainDev* mine = chains + first_chain[i];
+      size_t j = 0;
+      for (int K = w.k_max; K >= w.k_min && !w.done; K--)
+        for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++, j++) {
+          ChainInit ci;
+          int32_t rc = draw_chain(g, P, p, K, ci);
+          if (rc != kOk) {       // numpy's choice() would have raised inside the reference
+            out->status[w.u] = rc;
+            w.done = true;
+            n_failed++;
+            break;
+          }
+          ChainDev& c = mine[j];
+          memset(&c, 0, sizeof(c));
+          c.utr = int32_t(i); c.K = K; c.weights_only = 0;
+          memcpy(c.a_idx, ci.a_idx, sizeof(ci.a_idx));
+          memcpy(c.b_idx, ci.b_idx, sizeof(ci.b_idx));
+          memcpy(c.ws, ci.ws, sizeof(ci.ws));
+          memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
+        }
+    });
+    size_t n_chains = first_chain[W];
+    if (n_failed.load() > 0) {   // rare: drop the chains of UTRs whose initialisation raised
+      size_t o = 0;
+      for (size_t i = 0; i < W; i++) {
+        const size_t cnt = first_chain[i + 1] - first_chain[i];
+        if (cnt == 0) continue;
+        if (!wv[i].done) {
+          if (o != first_chain[i]) memmove(chains + o, chains + first_chain[i], cnt * sizeof(ChainDev));
+          o += cnt;
+        }
+      }
+      n_chains = o;
+    }
+    n_chains_out = n_chains;
+    return 0;
+  };
+  // The initial chains of the NEXT wave are drawn by a helper thread while the GPU runs this wave's
+  // prune refits and labels: once a wave's selection is done and no UTR of it re-runs, the RNG
+  // streams are where the next UTRs start.
+  static const bool predraw_on = getenv("SCAPE_B200_PREDRAW") ? atoi(getenv("SCAPE_B200_PREDRAW")) != 0 : true;
+  std::thread predraw_thread;
+  struct Joiner {            // no early return may leave the helper running
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } predraw_joiner{predraw_thread};
+  bool predrawn = false;
+  size_t predrawn_chains = 0;
+  int predraw_rc = 0;
+  double predraw_ms = 0;
+
   if (int rc = stage()) return rc;
   for (;;) {
     if (st_wave.empty()) break;
@@ -732,54 +818,14 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
     for (;;) {
       double tr0 = now_ms();
-      // RNG replay is serial per stream but streams are independent: one task per UTR of the wave,
-      // each writing its chains in place into the lane's pinned staging buffer
-      std::vector<size_t> first_chain(W + 1, 0);
-      for (size_t i = 0; i < W; i++)
-        first_chain[i + 1] = first_chain[i] + (wave[i].done ? 0 : size_t(wave[i].k_max - wave[i].k_min + 1) * SCAPE_B200_NTRIAL);
-      CU(L.h_chains.resize(first_chain[W]));
-      ChainDev* chains = L.h_chains.p;
-      std::atomic<int> n_failed(0);
-      L.pool->run(int64_t(W), [&](int64_t ii) {
-        const size_t i = size_t(ii);
-        WaveUtr& w = wave[i];
-        if (w.done) return;
-        const UtrPrep& p = prep[size_t(w.u)];
-        NpRandomState& g = rng[size_t(stream_of[size_t(w.u)])];
-        ChainDev* mine = chains + first_chain[i];
-        size_t j = 0;
-        for (int K = w.k_max; K >= w.k_min && !w.done; K--)
-          for (int trial = 0; trial < SCAPE_B200_NTRIAL; trial++, j++) {
-            ChainInit ci;
-            int32_t rc = draw_chain(g, P, p, K, ci);
-            if (rc != kOk) {       // numpy's choice() would have raised inside the reference
-              out->status[w.u] = rc;
-              w.done = true;
-              n_failed++;
-              break;
-            }
-            ChainDev& c = mine[j];
-            memset(&c, 0, sizeof(c));
-            c.utr = int32_t(i); c.K = K; c.weights_only = 0;
-            memcpy(c.a_idx, ci.a_idx, sizeof(ci.a_idx));
-            memcpy(c.b_idx, ci.b_idx, sizeof(ci.b_idx));
-            memcpy(c.ws, ci.ws, sizeof(ci.ws));
-            memcpy(c.k_order, ci.k_order, SCAPE_B200_NROUND);
-          }
-      });
-      size_t n_chains = first_chain[W];
-      if (n_failed.load() > 0) {   // rare: drop the chains of UTRs whose initialisation raised
-        size_t o = 0;
-        for (size_t i = 0; i < W; i++) {
-          const size_t cnt = first_chain[i + 1] - first_chain[i];
-          if (cnt == 0) continue;
-          if (!wave[i].done) {
-            if (o != first_chain[i]) memmove(chains + o, chains + first_chain[i], cnt * sizeof(ChainDev));
-            o += cnt;
-          }
-        }
-        n_chains = o;
+      size_t n_chains = 0;
+      if (predrawn) {            // drawn while the previous wave finished on the GPU
+        predrawn = false;
+        n_chains = predrawn_chains;
+      } else if (int rc = draw_wave(wave, n_chains)) {
+        return rc;
       }
+      ChainDev* chains = L.h_chains.p;
       L.tm.host_rng_ms += now_ms() - tr0;
       if (n_chains == 0) break;
       if (overlap && !next_staged) {
@@ -873,7 +919,23 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
           n_refits++;
         }
       L.tm.host_rng_ms += now_ms() - tr0;
-      if (int rc = run_chains(h, L, refits, n_refits, ud)) return rc;
+      {
+        bool any_rerun = false;
+        for (size_t i = 0; i < W; i++)
+          if (!wave[i].done && !need_refit[i] && !P.fixed_run_mode && P.re_run_mode && wave[i].best.K == wave[i].k_max)
+            any_rerun = true;
+        if (predraw_on && !any_rerun && next_staged && !st_wave.empty() && !predraw_thread.joinable()) {
+          predraw_thread = std::thread([&]() {
+            const double t0 = now_ms();
+            predraw_rc = draw_wave(st_wave, predrawn_chains);
+            predraw_ms = now_ms() - t0;
+          });
+        }
+      }
+      if (int rc = run_chains(h, L, refits, n_refits, ud)) {
+        if (predraw_thread.joinable()) predraw_thread.join();
+        return rc;
+      }
       for (size_t j = 0; j < n_refits; j++) {
         WaveUtr& w = wave[refit_owner[j]];
         w.best = refits[j];
@@ -955,6 +1017,12 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       const int32_t* lb = lab.data() + jobs[i].out_off;
       int64_t* dst = out->label + bt->read_off[u];
       for (int64_t r = 0; r < p.n_reads; r++) dst[r] = lb[p.read_to_bin[size_t(r)]];
+    }
+    if (predraw_thread.joinable()) {
+      predraw_thread.join();
+      if (predraw_rc) return predraw_rc;
+      predrawn = true;
+      L.tm.host_rng_ms += predraw_ms;
     }
     if (!next_staged)
       if (int rc = stage()) return rc;

@@ -575,18 +575,51 @@ __device__ __forceinline__ void estep_epilogue(ChainDev& ch, ScanDesc& sd, const
 }
 
 // One fragment of the E pass (shared by the warp- and the block-per-chain kernels).
+// What one fragment of the E pass reads from HBM / L2: its count, its tensor entry for the refreshed
+// component (a strided gather: DRAM latency) and the stale log_zmat columns.  Kept apart from the
+// arithmetic so that a caller can fetch the next fragment while it computes the current one.
+template <int NK, typename TT>
+struct FragIn {
+  double c;
+  TT a;
+  double lz[NK];
+};
+template <int NK, typename TT>
+__device__ __forceinline__ void estep_load(FragIn<NK, TT>& f, int n, int k, int64_t rk, int npad, int64_t R,
+                                           const TT* __restrict__ A, const double* __restrict__ cnt,
+                                           const double* __restrict__ lz) {
+  f.c = cnt[n];
+  f.a = A[(int64_t)n * R + rk];
+#pragma unroll
+  for (int j = 0; j < NK; j++) f.lz[j] = (j == k) ? 0.0 : lz[(int64_t)j * npad + n];
+}
+
+template <int NK, typename TT>
+__device__ __forceinline__ void estep_compute(const FragIn<NK, TT>& f, int n, int k, double lwk, bool guard, int npad,
+                                              double* __restrict__ lz, double* __restrict__ V, double (&red)[NK + 3],
+                                              int& h_lo, int& h_hi);
+
 template <int NK, typename TT>
 __device__ __forceinline__ void estep_fragment(int n, int k, double lwk, int64_t rk, bool guard, int npad, int64_t R,
                                                const TT* __restrict__ A, const double* __restrict__ cnt,
                                                double* __restrict__ lz, double* __restrict__ V, double (&red)[NK + 3],
                                                int& h_lo, int& h_hi) {
-  const double c = cnt[n];
-  const double fresh = lwk + (double)A[(int64_t)n * R + rk];
+  FragIn<NK, TT> f;
+  estep_load<NK, TT>(f, n, k, rk, npad, R, A, cnt, lz);
+  estep_compute<NK, TT>(f, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
+}
+
+template <int NK, typename TT>
+__device__ __forceinline__ void estep_compute(const FragIn<NK, TT>& f, int n, int k, double lwk, bool guard, int npad,
+                                              double* __restrict__ lz, double* __restrict__ V, double (&red)[NK + 3],
+                                              int& h_lo, int& h_hi) {
+  const double c = f.c;
+  const double fresh = lwk + (double)f.a;
   double z[NK], lzv[NK];
   double m = -CUDART_INF;
 #pragma unroll
   for (int j = 0; j < NK; j++) {
-    lzv[j] = (j == k) ? fresh : lz[(int64_t)j * npad + n];
+    lzv[j] = (j == k) ? fresh : f.lz[j];
     m = fmax(m, lzv[j]);
   }
   lz[(int64_t)k * npad + n] = fresh;
@@ -644,7 +677,7 @@ __device__ __forceinline__ void estep_fragment(int n, int k, double lwk, int64_t
 }
 
 // Warp-per-chain E step (small fragment counts): no block barriers, reductions by shuffles.
-template <int NK, typename TT>
+template <int NK, typename TT, bool PF>
 __device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, const TT* __restrict__ A,
                                const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ V) {
   constexpr int K = NK - 1;
@@ -678,7 +711,23 @@ __device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, cons
     for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
     h_lo = N;
     h_hi = -1;
-    for (int n = lane; n < N; n += 32) estep_fragment<NK, TT>(n, k, lwk, rk, guard, npad, R, A, cnt, lz, V, red, h_lo, h_hi);
+    if (PF) {
+      // software pipeline: the next fragment's loads (a strided tensor gather and the stale columns,
+      // DRAM / L2 latency) are in flight while this one is computed -- ncu: 54 % of the stall
+      // samples of the unpipelined loop sit on the first use of those loads
+      FragIn<NK, TT> cur, nxt;
+      int n = lane;
+      if (n < N) estep_load<NK, TT>(cur, n, k, rk, npad, R, A, cnt, lz);
+      while (n < N) {
+        const int nn = n + 32;
+        if (nn < N) estep_load<NK, TT>(nxt, nn, k, rk, npad, R, A, cnt, lz);
+        estep_compute<NK, TT>(cur, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
+        cur = nxt;
+        n = nn;
+      }
+    } else {
+      for (int n = lane; n < N; n += 32) estep_fragment<NK, TT>(n, k, lwk, rk, guard, npad, R, A, cnt, lz, V, red, h_lo, h_hi);
+    }
 #pragma unroll
     for (int j = 0; j < NK + 3; j++) {
       double x = red[j];
@@ -806,8 +855,8 @@ em_estep_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ i
 // one WARP per chain (8 chains per CTA) for UTRs with few fragments: no block barriers at all.
 // BIGK = false handles K = 1..7 (every normal run) with 4 CTAs per SM; BIGK = true handles the
 // K = 8..15 chains that only re-runs can create and may use twice the registers.
-template <typename TT, bool BIGK, bool LOOP>
-__global__ void __launch_bounds__(GT, BIGK ? 2 : 4)
+template <typename TT, bool BIGK, bool PF>
+__global__ void __launch_bounds__(GT, BIGK ? 2 : (PF ? 3 : 4))
 em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ index, int n_index,
                      const UtrDev* __restrict__ utrs, const void* __restrict__ tensor,
                      const double* __restrict__ cnt_all, double* lz_all, double* v_all,
@@ -825,30 +874,28 @@ em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restric
   const double* cnt = cnt_all + u.frag_off;
   double* lz = lz_all + ch.lz_off;
   double* V = v_all + ch.v_off;
-  // LOOP: weights-only chains (prune refits) never wait for a scan, so the whole chain runs to
-  // convergence inside one launch instead of one launch per iteration.
-  do {
+  {
     if (!BIGK) {
       switch (ch.K) {
-        case 1: estep_warp_run<2, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 2: estep_warp_run<3, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 3: estep_warp_run<4, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 4: estep_warp_run<5, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 5: estep_warp_run<6, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 6: estep_warp_run<7, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 7: estep_warp_run<8, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 1: estep_warp_run<2, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 2: estep_warp_run<3, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 3: estep_warp_run<4, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 4: estep_warp_run<5, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 5: estep_warp_run<6, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 6: estep_warp_run<7, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 7: estep_warp_run<8, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
         default: break;
       }
     } else {
       switch (ch.K) {
-        case 8: estep_warp_run<9, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 9: estep_warp_run<10, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 10: estep_warp_run<11, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 11: estep_warp_run<12, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 12: estep_warp_run<13, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 13: estep_warp_run<14, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 14: estep_warp_run<15, TT>(ch, sd, u, A, cnt, lz, V); break;
-        case 15: estep_warp_run<16, TT>(ch, sd, u, A, cnt, lz, V); break;
+        case 8: estep_warp_run<9, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 9: estep_warp_run<10, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 10: estep_warp_run<11, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 11: estep_warp_run<12, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 12: estep_warp_run<13, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 13: estep_warp_run<14, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 14: estep_warp_run<15, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 15: estep_warp_run<16, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
         default: break;
       }
     }
@@ -859,7 +906,182 @@ em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restric
       for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
     }
     __syncwarp();
-  } while (LOOP && ch.weights_only && ch.state == 1 && ch.n_iter < SCAPE_B200_NROUND);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E step, group kernel: G warps (1, 2, 4 or 8) per chain, 8 / G chains per CTA, persistent CTAs over a
+// device-side list of the chains that are still running.
+//   * a chain's E pass is a serial loop of ~1 us fragment passes per lane; G warps cut the loop to
+//     N / (32 G) passes, so the step is no longer bound by one warp walking a whole UTR, and the
+//     jobs are short enough to pack the SMs evenly;
+//   * every launch appends the chains that continue to the next step's list, so the late steps
+//     launch work for the few running chains only (an all-chains grid costs ~18 us of empty CTAs).
+// Groups synchronise with named barriers (bar.sync id, 32 G); __syncthreads() is never used here.
+// ------------------------------------------------------------------------------------------------
+struct EGroupShared {
+  double red[GW][SCAPE_B200_KCAP + 4];
+  double tot[SCAPE_B200_KCAP + 4];
+  double lwk;
+  long long rk;
+  int k, go, hull[2];
+};
+
+__device__ __forceinline__ void group_sync(int gid, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(nthreads) : "memory");
+}
+
+template <int NV>
+__device__ __forceinline__ void group_reduce_sum(double (&val)[NV], EGroupShared& sh, int G, int gid, int tig) {
+  const int lane = tig & 31, wig = tig >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    double x = val[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh.red[wig][i] = x;
+  }
+  group_sync(gid, 32 * G);
+  if (tig < NV) {
+    double acc = 0.0;
+    for (int w = 0; w < G; w++) acc += sh.red[w][tig];
+    sh.tot[tig] = acc;
+  }
+  group_sync(gid, 32 * G);
+}
+
+template <int NK, typename TT>
+__device__ __noinline__ void estep_group_run(EGroupShared& sh, int G, int gid, int tig, ChainDev& ch, ScanDesc& sd, const UtrDev& u,
+                                const TT* __restrict__ A, const double* __restrict__ cnt, double* __restrict__ lz,
+                                double* __restrict__ V) {
+  constexpr int K = NK - 1;
+  const int gthreads = 32 * G;
+  const int N = u.N, npad = u.Npad, B = u.B;
+  const int64_t R = u.ldR;
+  const int it = ch.n_iter;
+  if (it == 0) {
+    // initial log_zmat: all K+1 columns (em_algo :722-724)
+    for (int j = 0; j < NK; j++) {
+      const double w = ch.ws[j];
+      const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
+      if (tig == 0) ch.lw[j] = lw;
+      if (j < K) {
+        const int64_t rj = (int64_t)ch.a_idx[j] * B + ch.b_idx[j];
+        for (int n = tig; n < N; n += gthreads) lz[(int64_t)j * npad + n] = lw + (double)A[(int64_t)n * R + rj];
+      } else {
+        const double val = lw + u.unif_loglik;
+        for (int n = tig; n < N; n += gthreads) lz[(int64_t)j * npad + n] = val;
+      }
+    }
+  }
+  if (tig == 0) {
+    const int k = ch.k_order[it];
+    sh.k = k;
+    sh.lwk = ch.lw[k];
+    sh.rk = (long long)ch.a_idx[k] * B + ch.b_idx[k];
+  }
+  group_sync(gid, gthreads);
+  const int k = sh.k;
+  const double lwk = sh.lwk;
+  const int64_t rk = sh.rk;
+  bool guard = false;
+  double red[NK + 3];
+  while (true) {
+#pragma unroll
+    for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
+    int h_lo = N, h_hi = -1;
+    if (tig == 0) { sh.hull[0] = N; sh.hull[1] = -1; }
+    {
+      // software pipeline: the next fragment's loads are in flight while this one is computed
+      FragIn<NK, TT> cur, nxt;
+      int n = tig;
+      if (n < N) estep_load<NK, TT>(cur, n, k, rk, npad, R, A, cnt, lz);
+      while (n < N) {
+        const int nn = n + gthreads;
+        if (nn < N) estep_load<NK, TT>(nxt, nn, k, rk, npad, R, A, cnt, lz);
+        estep_compute<NK, TT>(cur, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
+        cur = nxt;
+        n = nn;
+      }
+    }
+    group_sync(gid, gthreads);
+    if (h_hi >= 0) { atomicMin(&sh.hull[0], h_lo); atomicMax(&sh.hull[1], h_hi); }
+    group_reduce_sum<NK + 3>(red, sh, G, gid, tig);
+    if (!guard && sh.tot[NK] < 1e-8) {       // mstep guard (:526-529); uniform across the group
+      guard = true;
+      group_sync(gid, gthreads);
+      continue;
+    }
+    break;
+  }
+  if (tig == 0) estep_epilogue<NK>(ch, sd, u, sh.tot, k, it, sh.hull[0], sh.hull[1]);
+}
+
+// list_in / n_in: the chains to step (n_host >= 0: the host knows the count, else *n_in);
+// list_out / n_out: the chains that still run after this step, appended here.
+template <typename TT>
+__global__ void __launch_bounds__(GT, 2)
+em_estep_group_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ list_in, const int32_t* n_in,
+                      int n_host, int32_t* list_out, int32_t* n_out, int G, int loop, const UtrDev* __restrict__ utrs,
+                      const void* __restrict__ tensor, const double* __restrict__ cnt_all, double* lz_all,
+                      double* v_all, const ScanPartial* __restrict__ partials, int32_t* trace_a, int32_t* trace_b,
+                      double* trace_ws) {
+  __shared__ EGroupShared shg[GW];
+  const int gthreads = 32 * G;
+  const int gid = threadIdx.x / gthreads, tig = threadIdx.x - gid * gthreads;
+  const int gpc = GW / G;
+  EGroupShared& sh = shg[gid];
+  const int n_jobs = n_host >= 0 ? n_host : *n_in;
+  for (int job = blockIdx.x * gpc + gid; job < n_jobs; job += gridDim.x * gpc) {
+    const int ci = list_in[job];
+    ChainDev& ch = chains[ci];
+    ScanDesc& sd = descs[ci];
+    if (ch.state == 0) continue;                       // group-uniform (nobody writes this chain meanwhile)
+    const UtrDev u = utrs[ch.utr];
+    if (tig < 32) {
+      const int go = apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws);
+      if (tig == 0) sh.go = go;
+    }
+    group_sync(gid, gthreads);
+    const bool go = sh.go != 0;
+    if (go) {
+      const TT* A = (const TT*)tensor + u.tensor_off;
+      const double* cnt = cnt_all + u.frag_off;
+      double* lz = lz_all + ch.lz_off;
+      double* V = v_all + ch.v_off;
+      bool again;
+      do {
+        switch (ch.K) {
+          case 1: estep_group_run<2, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 2: estep_group_run<3, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 3: estep_group_run<4, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 4: estep_group_run<5, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 5: estep_group_run<6, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 6: estep_group_run<7, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 7: estep_group_run<8, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 8: estep_group_run<9, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 9: estep_group_run<10, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 10: estep_group_run<11, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 11: estep_group_run<12, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 12: estep_group_run<13, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 13: estep_group_run<14, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 14: estep_group_run<15, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          case 15: estep_group_run<16, TT>(sh, G, gid, tig, ch, sd, u, A, cnt, lz, V); break;
+          default: break;
+        }
+        if (tig == 0 && ch.weights_only && ch.trace_off >= 0) {   // weights-only chains never wait for a scan
+          const int64_t o = ch.trace_off + (int64_t)(ch.n_iter - 1) * (SCAPE_B200_KCAP + 1);
+          for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
+          for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
+        }
+        group_sync(gid, gthreads);                     // the epilogue's writes to the chain are visible
+        // weights-only chains (prune refits) never wait for a scan: run them to convergence here
+        again = loop && ch.weights_only && ch.state == 1 && ch.n_iter < SCAPE_B200_NROUND;
+      } while (again);
+    }
+    if (tig == 0 && ch.state != 0) list_out[atomicAdd(n_out, 1)] = ci;
+    group_sync(gid, gthreads);                         // sh is reused by the next job
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1106,7 +1328,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
                              double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
                              double* trace_ws, cudaStream_t st, std::vector<cudaEvent_t>& evs,
                              std::vector<int>& kinds, int& scan_launches, const std::function<void()>& hook,
-                             int hook_step) {
+                             int hook_step, const EstepPlan& plan) {
   const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
   cudaFuncSetAttribute(em_scan_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
@@ -1123,32 +1345,67 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
     kinds.push_back(kind);
   };
   mark(-1);
-  const bool loop_only = !any_scan && n_big == 0;     // prune refits: whole chains inside one launch
-  if (loop_only) {
-    em_estep_warp_kernel<TT, false, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
-        chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
-        trace_b, trace_ws);
-    launches++;
-    if (big_k) {
-      em_estep_warp_kernel<TT, true, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
-          chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
-          trace_b, trace_ws);
-      launches++;
+  const bool group = plan.group_steps || !any_scan;
+  if (group) {
+    // ---- group E step: persistent CTAs over device-side lists of the running chains ---------------
+    int32_t* Ls[2] = {plan.lists, plan.lists + n_small};
+    int32_t* Lb[2] = {plan.lists + 2 * n_small, plan.lists + 2 * n_small + n_big};
+    int32_t* cs = plan.counts;
+    int32_t* cb = plan.counts + (SCAPE_B200_NROUND + 2);
+    cudaMemsetAsync(plan.counts, 0, sizeof(int32_t) * 2 * (SCAPE_B200_NROUND + 2), st);
+    const int Gs = plan.g_small, Gb = GW;
+    const unsigned max_grid = (unsigned)(plan.n_sm * 2);
+    const unsigned grid_s = (unsigned)std::min<int64_t>((n_small + GW / Gs - 1) / (GW / Gs), max_grid);
+    const unsigned grid_b = (unsigned)std::min<int64_t>(n_big, max_grid);
+    auto estep = [&](int step, int loop) {
+      if (n_small > 0) {
+        em_estep_group_kernel<TT><<<grid_s, GT, 0, st>>>(
+            chains_dev, descs_dev, step == 0 ? index_dev : Ls[step & 1], cs + step, step == 0 ? (int)n_small : -1,
+            Ls[(step + 1) & 1], cs + step + 1, Gs, loop, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
+            trace_a, trace_b, trace_ws);
+        launches++;
+      }
+      if (n_big > 0) {
+        em_estep_group_kernel<TT><<<grid_b, GT, 0, st>>>(
+            chains_dev, descs_dev, step == 0 ? index_dev + n_small : Lb[step & 1], cb + step, step == 0 ? (int)n_big : -1,
+            Lb[(step + 1) & 1], cb + step + 1, Gb, loop, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
+            trace_a, trace_b, trace_ws);
+        launches++;
+      }
+      mark(0);
+    };
+    if (!any_scan) {                                   // prune refits: whole chains inside one launch
+      estep(0, 1);
+    } else {
+      for (int step = 0; step <= SCAPE_B200_NROUND; step++) {
+        estep(step, 0);
+        if (step == SCAPE_B200_NROUND || n_refs == 0) continue;
+        em_scan_kernel<TT><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
+                                                               vbuf, (ScanPartial*)partials, scan_elems);
+        launches++;
+        scan_launches++;
+        mark(1);
+        if (hook && step == hook_step) hook();
+      }
     }
-    mark(0);
   }
-  for (int step = 0; !loop_only && step <= SCAPE_B200_NROUND; step++) {
+  for (int step = 0; !group && step <= SCAPE_B200_NROUND; step++) {
     // Early steps: most chains run -> one warp per chain (throughput).  Late steps: few chains run
     // and the step time is the latency of ONE chain's E pass -> one CTA per chain (8x shorter
     // fragment loop); CTAs of finished chains exit at once.
     const bool wide = step < warp_steps;
     if (n_small > 0 && wide) {
-      em_estep_warp_kernel<TT, false, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
-          chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
-          trace_b, trace_ws);
+      if (plan.warp_prefetch)
+        em_estep_warp_kernel<TT, false, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+            chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
+            trace_b, trace_ws);
+      else
+        em_estep_warp_kernel<TT, false, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+            chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
+            trace_b, trace_ws);
       launches++;
       if (big_k) {
-        em_estep_warp_kernel<TT, true, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
+        em_estep_warp_kernel<TT, true, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
             chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
             trace_a, trace_b, trace_ws);
         launches++;
@@ -1188,15 +1445,15 @@ int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* in
                     const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
                     const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
                     double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
-                    double* trace_ws, cudaStream_t st, EmStepEvents& ee) {
+                    double* trace_ws, cudaStream_t st, EmStepEvents& ee, const EstepPlan& plan) {
   ee.scan_launches = 0;
   if (f32)
     return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
                                     utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step);
+                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step, plan);
   return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
                                    utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step);
+                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step, plan);
 }
 
 // After the stream has been synchronised: total E-step and scan kernel time of the last run.

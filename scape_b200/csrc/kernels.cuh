@@ -141,11 +141,25 @@ struct EmStepEvents {
 void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms);
 int measure_fp64_peaks(int n_sm, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 constexpr int kWarpEstepMaxN = 384;    // UTRs with at most this many fragments use the warp-per-chain E step (a warp needs ~4 us per 32 fragments: above this the launch is bound by its longest warp)
+// How the E step is launched.  Runs of weights-only chains (prune refits) always use the group
+// kernel (g_small warps per chain for the chains with few fragments, a whole CTA for the others;
+// persistent CTAs over device-side lists of running chains; every chain iterates to convergence
+// inside one launch).  Runs with a grid search use the warp-per-chain / CTA-per-chain kernels over
+// the full chain index (group_steps = true switches them to the group kernel too; measured slower).
+// lists = 2 * n_chains ints, counts = 2 * (NROUND + 2) ints.
+struct EstepPlan {
+  int32_t* lists = nullptr;
+  int32_t* counts = nullptr;
+  int g_small = 4;
+  int n_sm = 148;
+  bool group_steps = false;
+  bool warp_prefetch = true;
+};
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
                     bool big_k,
                     const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
                     const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
                     double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
-                    double* trace_ws, cudaStream_t st, EmStepEvents& ee);
+                    double* trace_ws, cudaStream_t st, EmStepEvents& ee, const EstepPlan& plan);
 
 }  // namespace scape

@@ -207,6 +207,29 @@ def test_ragged_and_tiny_utrs():
         assert len(g.label_arr) == u.n_reads and g.label_arr.dtype == np.int64
 
 
+def test_heavy_tailed_waves_do_not_depend_on_their_composition():
+    """cfg-3 shape: the scan cuts big UTRs into narrower chain sub-batches, dealt to separate CTAs,
+    depending on what else is in the wave.  That may not change a single bit: every chain's sum
+    runs over the same fragments in the same order.  Two heavy-tailed chunks fitted together == fitted one by one == one UTR at a time."""
+    counts = np.minimum(synth.heavy_tail_read_counts(4000)[3000:3020], 40000)
+    counts[3] = 25000
+    counts[11] = 9000
+    chunks = [[synth.make_utr(7000 + 10 * f + i, int(counts[10 * f + i])) for i in range(10)] for f in range(2)]
+    frames = [[(u.gene_info_str, synth.to_dataframe(u)) for u in c] for c in chunks]
+    together = fit_chunks(frames, seeds=[1, 1])
+    for f in range(2):
+        alone = fit_chunks([frames[f]], seeds=[1])[0]
+        for a, b in zip(together[f], alone):
+            assert a.K == b.K and np.array_equal(a.alpha_arr, b.alpha_arr) and np.array_equal(a.beta_arr, b.beta_arr)
+            assert np.array_equal(a.ws, b.ws) and a.lb_arr == b.lb_arr and a.bic == b.bic
+            assert np.array_equal(a.label_arr, b.label_arr)
+    # first UTR of each chunk starts from the fresh seed: a single-UTR call must reproduce it exactly
+    for f in range(2):
+        one = fit_chunks([[frames[f][0]]], seeds=[1])[0][0]
+        a = together[f][0]
+        assert a.K == one.K and np.array_equal(a.ws, one.ws) and a.lb_arr == one.lb_arr
+
+
 def test_global_numpy_rng_is_consumed_like_the_reference():
     """subsample_run / infer use np.random's global legacy stream (apa_core.py:125); afterwards the
     stream must be where the reference would have left it."""
