@@ -49,9 +49,11 @@ def measured_peaks():
 
 def scan_traffic():
     """DRAM bytes per em_scan_kernel launch from the committed ncu capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
-    if not os.path.exists(p):
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_scan_traffic.json")))
+    if not found:
         return None, "no ncu capture committed"
+    p = found[-1]                      # the latest capture (names sort by round)
     with open(p) as fh:
         d = json.load(fh)
     return float(d["dram_bytes_per_launch"]), d.get("source", "profiles/r01_scan_traffic.json")

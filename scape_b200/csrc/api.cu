@@ -510,6 +510,8 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     plan.n_sm = h->n_sm;
     plan.group_steps = group_steps;
     plan.warp_prefetch = warp_pf;
+    static const int stage_chain = getenv("SCAPE_B200_STAGE_CHAIN") ? atoi(getenv("SCAPE_B200_STAGE_CHAIN")) : 1;
+    plan.stage_chain = stage_chain;
     // 4 warps per chain for the small class whatever else is in the wave: a chain's sums must not
     // depend on the composition of its wave
     plan.g_small = (g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) ? g_env : 4;

@@ -805,24 +805,45 @@ __device__ void estep_run(EShared& sh, ChainDev& ch, ScanDesc& sd, const UtrDev&
   if (tid == 0) estep_epilogue<NK>(ch, sd, u, sh.tot, k, it, sh.hull[0], sh.hull[1]);
 }
 
+// A chain's record (944 bytes over 8 cache lines) is read field by field through several dependent
+// steps of an E pass (state -> window -> k_order -> log w, alpha, beta ...): staged once into shared
+// memory by a coalesced copy, worked on there and copied back, the pass pays one global round trip
+// for it instead of one per step.
+static_assert(sizeof(ChainDev) % 8 == 0, "ChainDev is copied in 8-byte words");
+__device__ __forceinline__ void copy_chain(ChainDev* dst, const ChainDev* src, int t, int nt) {
+  const double* s = reinterpret_cast<const double*>(src);
+  double* d = reinterpret_cast<double*>(dst);
+  for (int i = t; i < (int)(sizeof(ChainDev) / 8); i += nt) d[i] = s[i];
+}
+
 // one CTA per chain; `chains` are the wave's chains in launch order
 template <typename TT>
 __global__ void __launch_bounds__(GT, 2)
 em_estep_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ index, const UtrDev* __restrict__ utrs,
                 const void* __restrict__ tensor, const double* __restrict__ cnt_all, double* lz_all, double* v_all,
-                const ScanPartial* __restrict__ partials, int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
+                const ScanPartial* __restrict__ partials, int32_t* trace_a, int32_t* trace_b, double* trace_ws,
+                int stage) {
   __shared__ EShared sh;
-  ChainDev& ch = chains[index[blockIdx.x]];
+  __shared__ ChainDev s_ch;
+  ChainDev& gch = chains[index[blockIdx.x]];
   ScanDesc& sd = descs[index[blockIdx.x]];
-  if (ch.state == 0) return;
-  const UtrDev u = utrs[ch.utr];
+  if (gch.state == 0) return;
   const int tid = threadIdx.x;
+  if (stage) {
+    copy_chain(&s_ch, &gch, tid, GT);
+    __syncthreads();
+  }
+  ChainDev& ch = stage ? s_ch : gch;
+  const UtrDev u = utrs[ch.utr];
   if (tid < 32) {
     const int go = apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws);
     if (tid == 0) sh.go = go;
   }
   __syncthreads();
-  if (!sh.go) return;
+  if (!sh.go) {
+    if (stage) copy_chain(&gch, &s_ch, tid, GT);
+    return;
+  }
   const TT* A = (const TT*)tensor + u.tensor_off;
   const double* cnt = cnt_all + u.frag_off;
   double* lz = lz_all + ch.lz_off;
@@ -850,6 +871,10 @@ em_estep_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ i
     for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
     for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
   }
+  if (stage) {
+    __syncthreads();
+    copy_chain(&gch, &s_ch, tid, GT);
+  }
 }
 
 // one WARP per chain (8 chains per CTA) for UTRs with few fragments: no block barriers at all.
@@ -861,15 +886,24 @@ em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restric
                      const UtrDev* __restrict__ utrs, const void* __restrict__ tensor,
                      const double* __restrict__ cnt_all, double* lz_all, double* v_all,
                      const ScanPartial* __restrict__ partials, int32_t* trace_a, int32_t* trace_b,
-                     double* trace_ws) {
+                     double* trace_ws, int stage) {
+  __shared__ ChainDev s_ch[GW];
   const int slot = blockIdx.x * GW + (threadIdx.x >> 5);
   if (slot >= n_index) return;
-  ChainDev& ch = chains[index[slot]];
+  ChainDev& gch = chains[index[slot]];
   ScanDesc& sd = descs[index[slot]];
-  if (ch.state == 0) return;
-  if ((ch.K > 7) != BIGK) return;
+  if (gch.state == 0) return;
+  if ((gch.K > 7) != BIGK) return;
+  ChainDev& ch = stage ? s_ch[threadIdx.x >> 5] : gch;
+  if (stage) {
+    copy_chain(&ch, &gch, threadIdx.x & 31, 32);
+    __syncwarp();
+  }
   const UtrDev u = utrs[ch.utr];
-  if (!apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws)) return;
+  if (!apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws)) {
+    if (stage) { __syncwarp(); copy_chain(&gch, &ch, threadIdx.x & 31, 32); }
+    return;
+  }
   const TT* A = (const TT*)tensor + u.tensor_off;
   const double* cnt = cnt_all + u.frag_off;
   double* lz = lz_all + ch.lz_off;
@@ -907,6 +941,7 @@ em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restric
     }
     __syncwarp();
   }
+  if (stage) copy_chain(&gch, &ch, threadIdx.x & 31, 32);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1398,16 +1433,16 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
       if (plan.warp_prefetch)
         em_estep_warp_kernel<TT, false, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
             chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
-            trace_b, trace_ws);
+            trace_b, trace_ws, plan.stage_chain);
       else
         em_estep_warp_kernel<TT, false, false><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
             chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
-            trace_b, trace_ws);
+            trace_b, trace_ws, plan.stage_chain);
       launches++;
       if (big_k) {
         em_estep_warp_kernel<TT, true, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
             chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
-            trace_a, trace_b, trace_ws);
+            trace_a, trace_b, trace_ws, plan.stage_chain);
         launches++;
       }
     }
@@ -1415,7 +1450,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
     if (n_blk > 0) {
       em_estep_kernel<TT><<<(unsigned)n_blk, GT, 0, st>>>(chains_dev, descs_dev, wide ? index_dev + n_small : index_dev,
                                                            utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
-                                                           trace_a, trace_b, trace_ws);
+                                                           trace_a, trace_b, trace_ws, plan.stage_chain);
       launches++;
     }
     mark(0);

@@ -154,6 +154,7 @@ struct EstepPlan {
   int n_sm = 148;
   bool group_steps = false;
   bool warp_prefetch = true;
+  int stage_chain = 1;          // E-step kernels work on a shared-memory copy of the chain record
 };
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
                     bool big_k,
