@@ -360,20 +360,23 @@ void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int m
 // K4: EM, bulk-synchronous.  All chains of a wave advance one coordinate-EM iteration per step; a
 // step is two launches:
 //
-//   em_estep_kernel   one CTA per chain.  (0) applies the arg-max the previous scan found for this
-//                     chain (alpha_k, beta_k update, trace, finalisation of converged chains), then
-//                     (1) column refresh (cal_z_k :473-488), count-tempered softmax (norm_z :490-495),
-//                     weight update (maximize_ws :498-505, mstep guard :526-529), ELBO (:559-573) and
-//                     the convergence test (:743).  Z is never materialised; the pass leaves
-//                     v[n] = Z[n,k] cnt[n] in the chain's row of V.
-//   em_scan_kernel    max_alpha_beta (:507-523) as a blocked product: one CTA per (UTR, block of 512
-//                     candidate rows) computes scores[row][chain] = sum_n tensor[n][row] * V[chain][n]
-//                     for EVERY running chain of that UTR whose window touches the block (all K, all
-//                     restarts), so a tensor block is fetched once per step however many chains
-//                     need it, and the step's work is spread over all SMs (no long-tailed CTAs).
-//                     Tensor rows stream through a TMA (1-D bulk copy) + mbarrier ring; thread <->
-//                     2 rows; V is staged in shared memory per sub-batch of <= 8 chains; FP64 FMAs.
-//                     Each (chain, block) leaves its first-maximum (score, row) in a partials array.
+//   E step            em_estep_warp_kernel (one warp per chain, few fragments, early steps),
+//                     em_estep_kernel (one CTA per chain) or em_estep_group_kernel (G warps per chain,
+//                     device-side work lists; prune refits).  (0) applies the arg-max the previous scan
+//                     found for this chain (alpha_k, beta_k update, trace, finalisation of converged
+//                     chains), then (1) column refresh (cal_z_k :473-488), count-tempered softmax
+//                     (norm_z :490-495), weight update (maximize_ws :498-505, mstep guard :526-529),
+//                     ELBO (:559-573) and the convergence test (:743).  Z is never materialised; the
+//                     pass leaves v[n] = Z[n,k] cnt[n] in the chain's row of V.
+//   em_scan_kernel    max_alpha_beta (:507-523) as a blocked product on the FP64 tensor cores (DMMA
+//                     m8n8k4): one CTA per (UTR, block of 256 candidate rows, share of the chain
+//                     sub-batches) computes scores[row][chain] = sum_n tensor[n][row] * V[chain][n]
+//                     for the running chains of that UTR whose window touches the block (all K, all
+//                     restarts), so a tensor block is fetched once per step however many chains need
+//                     it, and the step's work is spread over all SMs.  Tensor rows come straight from
+//                     HBM / L2 through a branch-free register ring; V is staged in shared memory per
+//                     sub-batch of <= 32 chains.  Each (chain, block) leaves its first-maximum
+//                     (score, row) in a partials array.
 // Only the hull of fragments with v != 0 is visited (other terms are exactly +-0 in the reference's
 // sum).  BIC at the end (:702-706).
 // ------------------------------------------------------------------------------------------------
@@ -384,9 +387,6 @@ constexpr int SCAN_GB = 32;                // chains per register sub-batch (32 
 constexpr int SCAN_MAXCH = 160;            // running chains of one UTR a scan CTA can list
 constexpr int SCAN_VCHUNK = 256;           // fragments of V staged per chunk
 constexpr int SCAN_VPITCH = SCAN_VCHUNK + 4;  // pitch = 4 mod 16 doubles: the 8x4 B-fragment loads are bank-conflict free
-constexpr int RING_STAGES = 3;             // TMA ring: stages in flight
-constexpr int RING_CH = 8;                 // fragments (tensor n-rows) per stage
-constexpr int RING_PITCH = SCAN_ROWS + 8;  // elements per staged n-row (up to 3 + 3 elements of 16-byte alignment slack)
 
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   double2 v;
@@ -405,32 +405,6 @@ template <> __device__ __forceinline__ double lds_elem<float>(uint32_t addr) {
   return (double)v;
 }
 template <> __device__ __forceinline__ double lds_elem<double>(uint32_t addr) { return lds_f64(addr); }
-
-// ---- TMA (1-D bulk async copy) + mbarrier, raw PTX ------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // E step

@@ -1,9 +1,11 @@
 // sm_100a CUDA kernels of the infer_pa path.  All arithmetic is FP64 like the reference
-// (taichi_core.py:11 `default_fp=ti.f64`); no tensor cores (the path is not a dense contraction).
+// (taichi_core.py:11 `default_fp=ti.f64`).  The grid arg-max, batched over the chains of a UTR, is a
+// dense FP64 product and runs on the FP64 tensor cores (mma.sync m8n8k4 -- FP64 has no tcgen05 path);
+// everything else is CUDA-core FP64.
 //
 //   table_kernel    K2  loglik_xlr_t for every (fragment, theta)         apa_core.py:620-640, taichi_core.py:101-157
 //   tensor_kernel   K3  marginal log-likelihood tensor[t][b][n]          taichi_core.py:160-179, 218-246
-//   em_estep_kernel + em_scan_kernel  K4  bulk-synchronous EM iterations    apa_core.py:473-573, 702-779
+//   em_estep_{warp,,group}_kernel + em_scan_kernel  K4  bulk-synchronous EM iterations    apa_core.py:473-573, 702-779
 //   label_kernel    K5  full E-step + row arg-max                        apa_core.py:873-881
 //
 // HBM layout (per wave of UTRs, one arena):
