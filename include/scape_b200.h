@@ -202,7 +202,8 @@ typedef void (*scape_b200_argsort_fn)(const double* values, int64_t n, int64_t* 
 int scape_b200_set_argsort_callback(scape_b200_argsort_fn fn);
 
 /* Raw generator access for the RNG tests: fills out[n] with RandomState(seed).random_sample(n)
- * (kind 0), .randint(0, arg, n) (kind 1), .permutation(arg) (kind 2, n == arg). */
+ * (kind 0), .randint(0, arg, n) (kind 1), .permutation(arg) (kind 2, n == arg), or the n
+ * .random_sample() values that FOLLOW a .permutation(arg) (kind 3: state continuity). */
 int scape_b200_rng_draw(uint32_t seed, int kind, int64_t arg, int64_t n, double* out);
 
 #ifdef __cplusplus

@@ -1448,6 +1448,10 @@ extern "C" int scape_b200_rng_draw(uint32_t seed, int kind, int64_t arg, int64_t
     std::vector<int64_t> p;
     g.permutation(arg, p);
     for (int64_t i = 0; i < n && i < arg; i++) out[i] = double(p[size_t(i)]);
+  } else if (kind == 3) {      // the stream AFTER a permutation(arg): state continuity across the shuffle
+    std::vector<int64_t> p;
+    g.permutation(arg, p);
+    for (int64_t i = 0; i < n; i++) out[i] = g.next_double();
   } else {
     return fail(-5, "unknown kind");
   }

@@ -293,7 +293,7 @@ inline void draw_component_order(NpRandomState& rng, int K, uint8_t* out) {
     for (int i = 0; i < SCAPE_B200_NROUND; i++) out[i] = 0;
     return;
   }
-  std::vector<int64_t> arr;
+  static thread_local std::vector<int64_t> arr;
   rng.permutation(K, arr);
   int pos = 0;
   for (int i = 0; i < SCAPE_B200_NROUND; i++) {
@@ -310,16 +310,16 @@ inline void draw_component_order(NpRandomState& rng, int K, uint8_t* out) {
 inline int32_t draw_chain(NpRandomState& rng, const scape_b200_params& P, const UtrPrep& u, int K, ChainInit& c) {
   c.K = K;
   const int64_t n_peak = int64_t(u.peak_idx.size());
-  std::vector<double> picked(static_cast<size_t>(K));
+  double picked[SCAPE_B200_KCAP];
   if (K <= n_peak) {
     int64_t nz = 0;
     for (double v : u.peak_w) nz += (v > 0);
     if (nz < K) return kErrNoPeakMass;
-    std::vector<int64_t> found;
+    static thread_local std::vector<int64_t> found;
     rng.choice_weighted_noreplace(u.peak_w.data(), n_peak, K, found);
     for (int i = 0; i < K; i++) picked[size_t(i)] = double(u.peak_idx[size_t(found[size_t(i)])] - 100);
   } else {
-    std::vector<int64_t> perm;
+    static thread_local std::vector<int64_t> perm;    // reused: L entries, every chain with K > n_peak
     rng.permutation(u.L, perm);                       // choice(L, size, replace=False) == permutation(L)[:size]
     for (int64_t i = 0; i < n_peak; i++) picked[size_t(i)] = double(u.peak_idx[size_t(i)] - 100);
     for (int64_t i = n_peak; i < K; i++) picked[size_t(i)] = double(perm[size_t(i - n_peak)]);
@@ -329,7 +329,7 @@ inline int32_t draw_chain(NpRandomState& rng, const scape_b200_params& P, const 
     double uni = 0.0 + (1.0 - 0.0) * rng.next_double();
     picked[size_t(i)] += std::nearbyint(amp * (2 * uni - 1));
   }
-  std::sort(picked.begin(), picked.end());
+  std::sort(picked, picked + K);
   for (int i = 0; i < K; i++) c.a_idx[i] = int32_t(snap_to_grid(u.theta, picked[size_t(i)]));
   for (int i = 0; i < K; i++) c.b_idx[i] = int32_t(rng.randint_below(u.B()));
   draw_weights(rng, K, P.max_unif_ws, c.ws);

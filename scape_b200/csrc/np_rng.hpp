@@ -38,25 +38,20 @@ struct NpRandomState {
     uint32_t y;
     for (i = 0; i < N - M; i++) {
       y = (key[i] & UPPER) | (key[i + 1] & LOWER);
-      key[i] = key[i + M] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+      key[i] = key[i + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & MAT);
     }
     for (; i < N - 1; i++) {
       y = (key[i] & UPPER) | (key[i + 1] & LOWER);
-      key[i] = key[i + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+      key[i] = key[i + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & MAT);
     }
     y = (key[N - 1] & UPPER) | (key[0] & LOWER);
-    key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+    key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & MAT);
     pos = 0;
   }
 
   inline uint32_t next_u32() {
     if (pos == N) refill();
-    uint32_t y = key[pos++];
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
+    return temper(key[pos++]);
   }
 
   // mt19937_next_double(): 53-bit double from two 32-bit draws.
@@ -80,12 +75,53 @@ struct NpRandomState {
     return v;
   }
 
-  // RandomState.shuffle on a 1-d array: Fisher-Yates from the top.
+  static inline uint32_t temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+
+  // RandomState.shuffle on a 1-d array: Fisher-Yates from the top, j = random_interval(i) per step.
+  // This is the hot loop of the chain initialisation (choice(L, size, replace=False) shuffles all L
+  // positions of the UTR), so the masked rejection is written without an unpredictable branch: a
+  // rejected draw swaps a[i] with itself and leaves i where it is; the mask (smallest 2^k - 1 >= i)
+  // is carried along instead of being rebuilt per step.  Same draws, same swaps, same final state.
   template <class T>
   void shuffle(T* a, int64_t n) {
-    for (int64_t i = n - 1; i >= 1; i--) {
-      int64_t j = int64_t(interval(uint64_t(i)));
-      std::swap(a[i], a[j]);
+    int64_t i = n - 1;
+    if (i < 1) return;
+    if (n <= 32 || uint64_t(i) > 0xffffffffull) {   // tiny arrays (gen_k_arr shuffles K entries) / 64-bit draws: the plain loop
+      for (; i >= 1; i--) std::swap(a[i], a[int64_t(interval(uint64_t(i)))]);
+      return;
+    }
+    uint32_t mask = uint32_t(i);
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    // phase 1: the accepted draws j_i for i = n-1 .. 1 (register-only loop-carried state)
+    static thread_local std::vector<uint32_t> js;
+    js.resize(size_t(n));
+    uint32_t* jp = js.data();
+    while (i >= 1) {
+      if (pos == N) refill();
+      int p = pos;
+      while (p < N && i >= 1) {
+        const uint32_t lo = mask >> 1;              // the mask holds while i is in (lo, mask]
+        while (p < N && uint32_t(i) > lo) {
+          const uint32_t v = temper(key[p++]) & mask;
+          jp[i] = v;                                // overwritten until a draw is accepted for this i
+          i -= (v <= uint32_t(i));
+        }
+        if (uint32_t(i) <= lo) mask = lo;
+      }
+      pos = p;
+    }
+    // phase 2: the swaps, in the same order
+    for (i = n - 1; i >= 1; i--) {
+      const uint32_t j = jp[i];
+      const T t = a[i];
+      a[i] = a[j];
+      a[j] = t;
     }
   }
 
@@ -105,10 +141,12 @@ struct NpRandomState {
 
   // RandomState.choice(pop, size, replace=False, p=p) -> indices into the population.
   void choice_weighted_noreplace(const double* p, int64_t pop, int64_t size, std::vector<int64_t>& found) {
-    std::vector<double> pw(p, p + pop), cdf(size_t(pop), 0.0), x;
+    static thread_local std::vector<double> pw, cdf, x;      // scratch reused across calls (hot path)
+    static thread_local std::vector<int64_t> fresh;
+    pw.assign(p, p + pop);
+    cdf.assign(size_t(pop), 0.0);
     found.assign(size_t(size), 0);
     int64_t n_uniq = 0;
-    std::vector<int64_t> fresh;
     while (n_uniq < size) {
       int64_t m = size - n_uniq;
       x.resize(size_t(m));

@@ -14,9 +14,12 @@ def test_mt19937_streams(seed):
     assert np.array_equal(rs.random_sample(1500), _lib.rng_draw(seed, 0, 0, 1500))
     rs = np.random.RandomState(seed)
     assert np.array_equal(rs.randint(0, 13, size=700), _lib.rng_draw(seed, 1, 13, 700))
-    for n in (2, 5, 2000, 4370):
+    # the shuffle is the hot loop of the chain initialisation and is written without the rejection
+    # branch (np_rng.hpp): every mask boundary, the 624-word refill boundary, and the stream after it
+    for n in (1, 2, 3, 4, 5, 7, 8, 9, 16, 17, 31, 32, 33, 623, 624, 625, 1000, 2000, 4370, 70000):
         rs = np.random.RandomState(seed)
         assert np.array_equal(rs.permutation(n), _lib.rng_draw(seed, 2, n, n))
+        assert np.array_equal(rs.random_sample(40), _lib.rng_draw(seed, 3, n, 40))
 
 
 def _oracle_model(u, **kw):
