@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -178,6 +179,54 @@ inline int32_t setup_model(const scape_b200_params& P, const double* x_raw, cons
 }
 
 // ---- coverage profile, smoothing, peaks --------------------------------------------------------
+// ker_smooth for the positions whose window is not clipped by the ends of the profile, four
+// positions at a time.  Every position runs numpy's pairwise summation for 8 <= n <= 128 exactly as
+// np_pairwise_sum does (8 running lanes over blocks of 8, the fixed combine tree, the tail added in
+// order); the SIMD lanes are four neighbouring POSITIONS, so the order of operations of each sum is
+// untouched.  Products are rounded before they are added (no FMA: the targets below have none).
+typedef double v4d_t __attribute__((vector_size(32)));
+__attribute__((always_inline)) inline void smooth_interior_impl(const double* w, int64_t nw, double wsum, const double* y,
+                                                                int64_t half, int64_t lo, int64_t hi, double* out) {
+  const int64_t nb = nw - (nw % 8);
+  for (int64_t i = lo; i + 4 <= hi; i += 4) {
+    const double* yy = y + (i - half);
+    v4d_t r[8];
+    for (int j = 0; j < 8; j++) {
+      v4d_t v;
+      __builtin_memcpy(&v, yy + j, sizeof(v));
+      const v4d_t wv = {w[j], w[j], w[j], w[j]};
+      r[j] = wv * v;
+    }
+    for (int64_t b = 8; b < nb; b += 8)
+      for (int j = 0; j < 8; j++) {
+        v4d_t v;
+        __builtin_memcpy(&v, yy + b + j, sizeof(v));
+        const v4d_t wv = {w[b + j], w[b + j], w[b + j], w[b + j]};
+        const v4d_t prod = wv * v;
+        r[j] = r[j] + prod;
+      }
+    v4d_t res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (int64_t t = nb; t < nw; t++) {
+      v4d_t v;
+      __builtin_memcpy(&v, yy + t, sizeof(v));
+      const v4d_t wv = {w[t], w[t], w[t], w[t]};
+      const v4d_t prod = wv * v;
+      res = res + prod;
+    }
+    const v4d_t den = {wsum, wsum, wsum, wsum};
+    res = res / den;
+    __builtin_memcpy(out + i, &res, sizeof(res));
+  }
+}
+__attribute__((target("avx2"))) inline void smooth_interior_avx2(const double* w, int64_t nw, double wsum, const double* y,
+                                                                 int64_t half, int64_t lo, int64_t hi, double* out) {
+  smooth_interior_impl(w, nw, wsum, y, half, lo, hi, out);
+}
+inline void smooth_interior_base(const double* w, int64_t nw, double wsum, const double* y, int64_t half, int64_t lo,
+                                 int64_t hi, double* out) {
+  smooth_interior_impl(w, nw, wsum, y, half, lo, hi, out);
+}
+
 inline void coverage_and_peaks(const scape_b200_params& P, UtrPrep& u) {
   if (u.status != kOk) return;
   const int64_t L = u.L, ny = L + 200;
@@ -202,7 +251,16 @@ inline void coverage_and_peaks(const scape_b200_params& P, UtrPrep& u) {
   // prefix count of non-zero coverage so all-zero windows are skipped (0/wsum == 0 exactly)
   std::vector<int32_t> nzp(size_t(ny) + 1, 0);
   for (int64_t i = 0; i < ny; i++) nzp[size_t(i + 1)] = nzp[size_t(i)] + (y[size_t(i)] != 0.0);
+  // interior positions (full window) in blocks of four; the ends and the remainder below
+  int64_t blk_lo = half, blk_hi = half;
+  if (nw >= 8 && nw <= 128 && ny - half > half + 4) {
+    blk_hi = half + (ny - half - half) / 4 * 4;
+    static const bool has_avx2 = __builtin_cpu_supports("avx2") && !getenv("SCAPE_B200_NO_AVX2");
+    if (has_avx2) smooth_interior_avx2(w, nw, wsum, y.data(), half, blk_lo, blk_hi, u.prof_y.data());
+    else smooth_interior_base(w, nw, wsum, y.data(), half, blk_lo, blk_hi, u.prof_y.data());
+  }
   for (int64_t i = 0; i < ny; i++) {
+    if (i == blk_lo && blk_hi > blk_lo) { i = blk_hi - 1; continue; }
     int64_t st = std::max<int64_t>(0, i - half), en = std::min<int64_t>(ny - 1, i + half);
     if (nzp[size_t(en + 1)] == nzp[size_t(st)]) continue;
     int64_t w0 = st - (i - half), m = en - st + 1;

@@ -49,6 +49,46 @@ def test_binning_profile_peaks(ui, reads):
     assert np.array_equal(pr["peak_w"], m.peak_w)
 
 
+@pytest.mark.parametrize("beta_step", [2, 3, 10])
+def test_smoothing_window_sizes(beta_step):
+    """ker_smooth's window is 6 * 3 * beta_step + 1 taps: 37 and 55 go through the four-positions-at-a-time
+    path (numpy pairwise order for 8 <= n <= 128), 181 through the recursive pairwise sum; profile, peaks
+    and peak weights must stay bit-identical to numpy / scipy either way."""
+    for ui, reads in ((0, 300), (3, 2000)):
+        u = synth.make_utr(ui, reads)
+        m = _oracle_model(u, beta_step=beta_step, max_beta=70)
+        pr = _lib.profile(_lib.make_params(beta_step=beta_step, max_beta=70), u.x, u.l, u.r, u.pa)
+        assert np.array_equal(pr["prof_y"], m.prof_y)
+        assert np.array_equal(pr["peak_idx"], m.peak_idx)
+        assert np.array_equal(pr["peak_w"], m.peak_w)
+
+
+def test_smoothing_without_avx2_is_the_same():
+    """The smoothing kernel is compiled for AVX2 and for baseline x86-64 and picked at run time; the
+    baseline build must give the same bits (own process: the choice is made once)."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, hashlib, numpy as np; sys.path.insert(0, %r)\n"
+            "from scape_b200 import _lib, synth\n"
+            "h = hashlib.sha256()\n"
+            "for ui, reads in ((0, 300), (1, 3000), (22, 20000)):\n"
+            "    u = synth.make_utr(ui, reads)\n"
+            "    pr = _lib.profile(_lib.make_params(), u.x, u.l, u.r, u.pa)\n"
+            "    h.update(pr['prof_y'].tobytes()); h.update(pr['peak_w'].tobytes())\n"
+            "print('DIGEST', h.hexdigest())\n") % root
+    outs = []
+    for extra in ({}, {"SCAPE_B200_NO_AVX2": "1"}):
+        env = dict(os.environ)
+        env.update(extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1])
+    assert outs[0] == outs[1]
+
+
 def test_binning_with_polya_lengths_and_nan_columns():
     rng = np.random.default_rng(3)
     n = 400
