@@ -134,8 +134,19 @@ inline std::vector<double> int_arange(int64_t lo, int64_t hi, int64_t step) {
 }
 
 // find_nearest (apa_core.py:537-549) for one value: nearest grid point, ties go up.
-inline int64_t snap_to_grid(const std::vector<double>& g, double v) {
-  int64_t p = int64_t(std::lower_bound(g.begin(), g.end(), v) - g.begin());
+// `step` > 0: the grid is known to be g[0] + t * step (the full theta grid), so searchsorted's
+// position is guessed arithmetically and only corrected by comparisons against the grid itself.
+inline int64_t snap_to_grid(const std::vector<double>& g, double v, double step = 0.0) {
+  int64_t p;
+  if (step > 0.0 && !g.empty()) {
+    const int64_t n = int64_t(g.size());
+    const double q = std::ceil((v - g[0]) / step);
+    p = q <= 0.0 ? 0 : (q >= double(n) ? n : int64_t(q));
+    while (p > 0 && g[size_t(p - 1)] >= v) p--;          // lower bound: first index with g[p] >= v
+    while (p < n && g[size_t(p)] < v) p++;
+  } else {
+    p = int64_t(std::lower_bound(g.begin(), g.end(), v) - g.begin());
+  }
   if (p == 0) return 0;
   if (p == int64_t(g.size())) return int64_t(g.size()) - 1;
   return (v - g[size_t(p - 1)] >= g[size_t(p)] - v) ? p : p - 1;
@@ -388,7 +399,8 @@ inline int32_t draw_chain(NpRandomState& rng, const scape_b200_params& P, const 
     picked[size_t(i)] += std::nearbyint(amp * (2 * uni - 1));
   }
   std::sort(picked, picked + K);
-  for (int i = 0; i < K; i++) c.a_idx[i] = int32_t(snap_to_grid(u.theta, picked[size_t(i)]));
+  const double grid_step = P.fixed_run_mode ? 0.0 : double(P.theta_step);   // fixed mode: irregular union of slices
+  for (int i = 0; i < K; i++) c.a_idx[i] = int32_t(snap_to_grid(u.theta, picked[size_t(i)], grid_step));
   for (int i = 0; i < K; i++) c.b_idx[i] = int32_t(rng.randint_below(u.B()));
   draw_weights(rng, K, P.max_unif_ws, c.ws);
   draw_component_order(rng, K, c.k_order);

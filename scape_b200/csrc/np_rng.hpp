@@ -92,16 +92,21 @@ struct NpRandomState {
   void shuffle(T* a, int64_t n) {
     int64_t i = n - 1;
     if (i < 1) return;
-    if (n <= 32 || uint64_t(i) > 0xffffffffull) {   // tiny arrays (gen_k_arr shuffles K entries) / 64-bit draws: the plain loop
+    if (uint64_t(i) > 0xffffffffull) {              // 64-bit draws: not on any path of the reference, kept exact
       for (; i >= 1; i--) std::swap(a[i], a[int64_t(interval(uint64_t(i)))]);
       return;
     }
     uint32_t mask = uint32_t(i);
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-    // phase 1: the accepted draws j_i for i = n-1 .. 1 (register-only loop-carried state)
-    static thread_local std::vector<uint32_t> js;
-    js.resize(size_t(n));
-    uint32_t* jp = js.data();
+    // phase 1: the accepted draws j_i for i = n-1 .. 1 (register-only loop-carried state); tiny arrays
+    // (gen_k_arr shuffles K entries ~11 times per chain) keep them on the stack
+    uint32_t small[64];
+    uint32_t* jp = small;
+    if (n > 64) {
+      static thread_local std::vector<uint32_t> js;
+      js.resize(size_t(n));
+      jp = js.data();
+    }
     while (i >= 1) {
       if (pos == N) refill();
       int p = pos;
@@ -159,7 +164,15 @@ struct NpRandomState {
       fresh.clear();
       for (int64_t i = 0; i < m; i++) {
         // searchsorted(side='right'): first index with cdf > x
-        int64_t idx = int64_t(std::upper_bound(cdf.begin(), cdf.end(), x[size_t(i)]) - cdf.begin());
+        int64_t idx;
+        if (pop <= 32) {                 // few peaks: count the entries <= x (same answer, no branches)
+          idx = 0;
+          const double xi = x[size_t(i)];
+          const double* cp = cdf.data();
+          for (int64_t q = 0; q < pop; q++) idx += (cp[q] <= xi);
+        } else {
+          idx = int64_t(std::upper_bound(cdf.begin(), cdf.end(), x[size_t(i)]) - cdf.begin());
+        }
         // keep first occurrences, in draw order (np.unique(return_index) + sort + take)
         if (std::find(fresh.begin(), fresh.end(), idx) == fresh.end()) fresh.push_back(idx);
       }

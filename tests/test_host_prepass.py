@@ -126,6 +126,26 @@ def test_chain_initialisation_draws(ui, reads):
         assert list(got[i].k_order[:50]) == list(order)
 
 
+def test_chain_initialisation_draws_many_utrs():
+    """A wider net for the arithmetic grid snap (start positions below the first / above the last theta,
+    exact ties), the branch-free shuffles and the weighted choice: 40 UTRs of mixed size, a K sweep each,
+    every alpha / beta index, weight and component order equal to the oracle's draw for draw."""
+    P = _lib.make_params()
+    ks = [5, 5, 5, 4, 4, 3, 3, 2, 1, 6, 8]
+    for ui in range(200, 240):
+        u = synth.make_utr(ui, [40, 150, 500, 3000][ui % 4], long_utr=(ui % 8 == 7))
+        m = _oracle_model(u)
+        got = _lib.draw_chains(P, u.x, u.l, u.r, u.pa, 1 + ui, ks)
+        rng = np.random.RandomState(1 + ui)
+        for i, k in enumerate(ks):
+            ch = so.draw_chain(m, k, rng)
+            order = so.draw_component_order(k, 50, rng)
+            assert list(got[i].a_idx[:k]) == list(ch.a_idx), (ui, k)
+            assert list(got[i].b_idx[:k]) == list(ch.b_idx)
+            assert list(got[i].ws[:k + 1]) == list(ch.ws)
+            assert list(got[i].k_order[:50]) == list(order)
+
+
 def test_reference_assertion_is_reported():
     """assert 0 <= x < utr_length (apa_core.py:388) -> negative status instead of a silent fit."""
     x = np.array([-5.0, 10.0, 30.0]); l = np.array([50.0, 50.0, 50.0]); nan = np.full(3, np.nan)
