@@ -104,7 +104,41 @@ inline int32_t bin_reads(const double* x, const double* l, const double* r, cons
     if (bx >= (1 << 20) || bl >= (1 << 12) || br >= (1 << 12) || bp >= (1 << 20)) return u.status = kErrBinRange;
     recs[size_t(i)] = {(uint64_t(bx) << 44) | (uint64_t(bl) << 32) | (uint64_t(br) << 20) | uint64_t(bp), int32_t(i)};
   }
-  std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.key < b.key; });
+  // Order by key.  The leading field is the x bin (a few hundred distinct values, one or two reads
+  // each), so a counting sort on it followed by insertion sorts inside the x bins does the job in
+  // O(n + range); a comparison sort is the fallback for absurd coordinate ranges.
+  {
+    uint64_t max_bx = 0;
+    for (const Rec& rc : recs) max_bx = std::max(max_bx, rc.key >> 44);
+    if (max_bx < uint64_t(4 * n + 4096)) {
+      static thread_local std::vector<int32_t> start;
+      static thread_local std::vector<Rec> sorted;
+      start.assign(size_t(max_bx) + 2, 0);
+      for (const Rec& rc : recs) start[size_t(rc.key >> 44) + 1]++;
+      for (size_t b = 1; b < start.size(); b++) start[b] += start[b - 1];
+      sorted.resize(recs.size());
+      for (const Rec& rc : recs) sorted[size_t(start[size_t(rc.key >> 44)]++)] = rc;   // start[b] becomes the END of bin b
+      size_t lo = 0;
+      for (size_t b = 0; b + 1 < start.size(); b++) {
+        const size_t hi = size_t(start[b]);
+        if (hi - lo > 24) {                             // crowded x bin (deep UTRs): comparison sort
+          std::sort(sorted.begin() + long(lo), sorted.begin() + long(hi), [](const Rec& a, const Rec& b) { return a.key < b.key; });
+          lo = hi;
+          continue;
+        }
+        for (size_t a = lo + 1; a < hi; a++) {          // insertion sort of one x bin by the full key
+          const Rec v = sorted[a];
+          size_t q = a;
+          while (q > lo && sorted[q - 1].key > v.key) { sorted[q] = sorted[q - 1]; q--; }
+          sorted[q] = v;
+        }
+        lo = hi;
+      }
+      recs.swap(sorted);
+    } else {
+      std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.key < b.key; });
+    }
+  }
   u.read_to_bin.assign(size_t(n), 0);
   u.x.clear(); u.l.clear(); u.r.clear(); u.pa.clear(); u.cnt.clear();
   size_t i = 0;
