@@ -422,11 +422,31 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   // instantiation of the E step (instruction-cache locality; 24 % 'no instruction' stalls otherwise);
   // within one K the chains with the longest fragment loop go first (a warp's time is ~ N / 32
   // fragment passes, the launch ends with the slowest warp)
-  std::stable_sort(index.begin(), index.end(), [&](int32_t a, int32_t b) {
-    const ChainDev &ca = chains[size_t(a)], &cb = chains[size_t(b)];
-    if (ca.K != cb.K) return ca.K > cb.K;
-    return utrs_host[size_t(ca.utr)].N > utrs_host[size_t(cb.utr)].N;
-  });
+  // (stable counting sort on (K descending, N descending): both keys are small integers, and this
+  // runs on the host's critical path between two waves)
+  if (warp_max_n <= 4096) {
+    const size_t stride = size_t(warp_max_n) + 1;
+    std::vector<int32_t> bucket_of(index.size());
+    std::vector<int32_t> start((SCAPE_B200_KCAP + 1) * stride + 1, 0);
+    for (size_t j = 0; j < index.size(); j++) {
+      const ChainDev& c = chains[size_t(index[j])];
+      const int N = utrs_host[size_t(c.utr)].N;
+      if (c.K < 0 || c.K > SCAPE_B200_KCAP || N < 0 || N > warp_max_n) return fail(-5, "internal: chain outside the E-step sort range");
+      const size_t b = size_t(SCAPE_B200_KCAP - c.K) * stride + size_t(warp_max_n - N);
+      bucket_of[j] = int32_t(b);
+      start[b + 1]++;
+    }
+    for (size_t b = 1; b < start.size(); b++) start[b] += start[b - 1];
+    std::vector<int32_t> sorted(index.size());
+    for (size_t j = 0; j < index.size(); j++) sorted[size_t(start[size_t(bucket_of[j])]++)] = index[j];
+    index.swap(sorted);
+  } else {
+    std::stable_sort(index.begin(), index.end(), [&](int32_t a, int32_t b) {
+      const ChainDev &ca = chains[size_t(a)], &cb = chains[size_t(b)];
+      if (ca.K != cb.K) return ca.K > cb.K;
+      return utrs_host[size_t(ca.utr)].N > utrs_host[size_t(cb.utr)].N;
+    });
+  }
   for (size_t i = 0; i < chains.size(); i++)
     if (utrs_host[size_t(chains[i].utr)].N > warp_max_n) index.push_back(int32_t(i));
   const int64_t n_big = int64_t(index.size()) - n_small;
