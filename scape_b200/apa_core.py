@@ -229,9 +229,15 @@ def infer(pickle_input_file, pickle_output_file, **kwargs):
             pickle.dump(res, fh)
 
 
-def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0, **kwargs) -> List[str]:
+def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0,
+                devices: Optional[Sequence[int]] = None, **kwargs) -> List[str]:
     """Multi-file entry point: same per-file seeding and output naming as
-    `_infer_pa`, but all files share one library call so their UTRs run concurrently."""
+    `_infer_pa`, but all files share one library call so their UTRs run concurrently.
+
+    `devices=[0, 1, ...]`: the files (RNG streams) are bin-packed over the GPUs by estimated cost
+    (`scape_b200.shard`) and fitted by one host thread per GPU (the C call releases the
+    GIL); there is nothing to exchange between GPUs.  Results do not depend on the partition: every
+    file is its own stream, seeded 1."""
     os.makedirs(os.path.join(output_dir, "pkl_output"), exist_ok=True)
     names, outs = [], []
     for f in pkl_input_files:
@@ -247,12 +253,50 @@ def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0
         if os.path.exists(o):
             os.remove(o)
     chunks = [read_chunk_file(f) for f in pkl_input_files]
-    results = fit_chunks(chunks, seeds=[1] * len(chunks), device=device, **kwargs)
+    devs = list(devices) if devices else [device]
+    if len(devs) <= 1:
+        results = fit_chunks(chunks, seeds=[1] * len(chunks), device=devs[0], **kwargs)
+    else:
+        results = _fit_chunks_multi_gpu(chunks, devs, **kwargs)
     for o, res_lst in zip(outs, results):
         with open(o, 'wb') as fh:
             for res in res_lst:
                 pickle.dump(res, fh)
     return outs
+
+
+def plan_multi_gpu(chunks: Sequence[Sequence[tuple]], n_gpus: int) -> List[List[int]]:
+    """Which chunk (stream) goes to which GPU: LPT packing of the a-priori stream costs."""
+    from . import shard
+    reads = [[len(df) for _, df in chunk] for chunk in chunks]
+    hints = [[int(np.max(np.asarray(df["x"])) + np.max(np.asarray(df["l"])) + 50) if len(df) else 2000
+              for _, df in chunk] for chunk in chunks]
+    return shard.lpt_partition(shard.stream_costs(reads, hints), n_gpus)
+
+
+def _fit_chunks_multi_gpu(chunks, devices, **kwargs):
+    import threading
+    parts = plan_multi_gpu(chunks, len(devices))
+    results: List[Optional[list]] = [None] * len(chunks)
+    errors: List[BaseException] = []
+
+    def work(dev, mine):
+        try:
+            if mine:
+                got = fit_chunks([chunks[i] for i in mine], seeds=[1] * len(mine), device=dev, **kwargs)
+                for i, r in zip(mine, got):
+                    results[i] = r
+        except BaseException as e:      # re-raised in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d, p)) for d, p in zip(devices, parts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
 
 
 def _infer_pa(pkl_input_file: str, output_dir: str, **kwargs):

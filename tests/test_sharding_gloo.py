@@ -62,3 +62,54 @@ def test_world_size_2_gloo_gather_keeps_input_order():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert out == [[f"stream{s}-utr{i}" for i in range(5)] for s in range(9)]
+
+
+def test_infer_files_multi_gpu_plan_and_output_order(tmp_path, monkeypatch):
+    """`infer_files(devices=[...])`: files are dealt to the GPUs by cost, every file is fitted exactly
+    once as its own stream (seed 1), and the result pickles land under the reference's names in input
+    order.  The GPU fit is replaced by a stand-in here (CPU test); the real thing is the same
+    `fit_chunks` call the single-GPU path makes."""
+    import pickle
+    import threading
+    from scape_b200 import apa_core, synth
+
+    sizes = [[60, 40], [4000, 30, 30], [200], [900, 800, 700], [25]]
+    utrs, k = [], 0
+    for f, ss in enumerate(sizes):
+        for n in ss:
+            utrs.append(synth.make_utr(600 + k, n))
+            k += 1
+    paths, pos = [], 0
+    for f, ss in enumerate(sizes):
+        paths += synth.write_chunk_files(utrs[pos:pos + len(ss)], str(tmp_path), per_file=len(ss), stem=f"f{f}")
+        pos += len(ss)
+
+    seen, lock = [], threading.Lock()
+
+    def fake_fit_chunks(chunks, seeds=None, device=0, **kw):
+        with lock:
+            seen.append((device, [c[0][0] for c in chunks], list(seeds)))
+        return [[("fit", gi, len(df), device) for gi, df in c] for c in chunks]
+
+    monkeypatch.setattr(apa_core, "fit_chunks", fake_fit_chunks)
+    outs = apa_core.infer_files(paths, str(tmp_path), devices=[0, 1, 2])
+    assert [os.path.basename(o) for o in outs] == [os.path.basename(p)[:-10] + ".res.pkl" for p in paths]
+    firsts = sorted(g for _, gs, _ in seen for g in gs)
+    assert firsts == sorted(apa_core.read_chunk_file(p)[0][0] for p in paths)          # every file once
+    assert all(set(sd) == {1} for _, _, sd in seen) and len({d for d, _, _ in seen}) == 3
+    pos = 0
+    for o, ss in zip(outs, sizes):
+        with open(o, "rb") as fh:
+            recs = []
+            while True:
+                try:
+                    recs.append(pickle.load(fh))
+                except EOFError:
+                    break
+        assert [r[1] for r in recs] == [u.gene_info_str for u in utrs[pos:pos + len(ss)]]
+        assert [r[2] for r in recs] == ss
+        pos += len(ss)
+    # the heaviest file sits alone on its GPU
+    plan = apa_core.plan_multi_gpu([apa_core.read_chunk_file(p) for p in paths], 3)
+    assert sorted(i for p in plan for i in p) == list(range(len(paths)))
+    assert [1] in plan
