@@ -1,6 +1,6 @@
 """Development check: kernel-seam parity + whole-UTR parity against the oracle on a few UTRs."""
 import os, sys, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import scape_oracle as so
 from scape_b200 import _lib, synth
