@@ -99,6 +99,18 @@ def pack(utrs):
     return off, cat("x"), cat("l"), cat("r"), cat("pa")
 
 
+def cfg3_plan(total, per_file, world):
+    """cfg-3: reads per UTR, the long-UTR cut, the chunk files (lists of UTR indices) and which files
+    every rank fits (LPT packing of the a-priori stream costs, scape_b200/shard.py)."""
+    from scape_b200 import shard, synth
+    counts = synth.heavy_tail_read_counts(total)
+    cut = np.quantile(synth.heavy_tail_read_counts(max(total, 1000)), 0.99)
+    files = [list(range(f, min(f + per_file, total))) for f in range(0, total, per_file)]
+    costs = shard.stream_costs([[counts[i] for i in f] for f in files],
+                               [[20000 if counts[i] >= cut else 2000 for i in f] for f in files])
+    return counts, cut, files, shard.lpt_partition(costs, world)
+
+
 def _cpu_fit_one(args):
     idx, reads = args[0], args[1]
     from oracle import scape_oracle as so
@@ -185,12 +197,8 @@ def main():
         # 20k heavy-tailed UTRs in TOTAL (strong scaling): chunk files are bin-packed over the ranks
         # by the a-priori cost model (scape_b200/shard.py), every rank generates and fits only its own
         total = args.utrs if args.utrs != N_UTR else 20000
-        counts = synth.heavy_tail_read_counts(total)
-        cut = np.quantile(synth.heavy_tail_read_counts(max(total, 1000)), 0.99)
-        files = [list(range(f, min(f + args.per_file, total))) for f in range(0, total, args.per_file)]
-        costs = shard.stream_costs([[counts[i] for i in f] for f in files],
-                                   [[20000 if counts[i] >= cut else 2000 for i in f] for f in files])
-        mine = shard.lpt_partition(costs, world)[rank]
+        counts, cut, files, parts = cfg3_plan(total, args.per_file, world)
+        mine = parts[rank]
         utrs = [synth.make_utr(i, int(counts[i]), long_utr=bool(counts[i] >= cut)) for f in mine for i in files[f]]
         scaling = "strong"
         label = (f"cfg-3: synthetic {total} UTRs in total, heavy-tailed reads per UTR (10..200k, median 600), "

@@ -113,3 +113,18 @@ def test_infer_files_multi_gpu_plan_and_output_order(tmp_path, monkeypatch):
     plan = apa_core.plan_multi_gpu([apa_core.read_chunk_file(p) for p in paths], 3)
     assert sorted(i for p in plan for i in p) == list(range(len(paths)))
     assert [1] in plan
+
+
+def test_bench_cfg3_plan_covers_every_utr_once():
+    """bench.py --workload cfg3 (strong scaling): whatever the number of ranks, every chunk file of the
+    20k-UTR heavy-tailed set is fitted by exactly one rank and the estimated loads are balanced."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    for world in (1, 2, 4, 8):
+        counts, cut, files, parts = bench.cfg3_plan(20000, 100, world)
+        assert len(files) == 200 and len(parts) == world
+        assert sorted(f for p in parts for f in p) == list(range(200))
+        utrs = sorted(i for p in parts for f in p for i in files[f])
+        assert utrs == list(range(20000))
+        loads = [sum(shard.utr_cost(int(counts[i]), 20000 if counts[i] >= cut else 2000) for f in p for i in files[f]) for p in parts]
+        assert max(loads) / (sum(loads) / world) < 1.10
