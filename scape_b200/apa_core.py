@@ -99,11 +99,52 @@ class ChunkBatch:
 
     def add(self, gene_info_str, df, stream: int):
         self.gene_info.append(gene_info_str)
-        for c, name in zip(self.cols, ("x", "l", "r", "pa")):
-            c.append(np.asarray(df[name], dtype=np.float64))
-        self.frames.append((np.array(df["cb_id"]), np.array(df["read_id"])))
-        self.n_reads.append(len(self.cols[0][-1]))
+        got = self._columns_fast(df)
+        if got is None:                       # non-numeric extra columns etc.: column by column
+            got = [np.asarray(df[name], dtype=np.float64) for name in ("x", "l", "r", "pa")] + \
+                  [np.array(df["cb_id"]), np.array(df["read_id"])]
+        for c, col in zip(self.cols, got[:4]):
+            c.append(col)
+        self.frames.append((got[4], got[5]))
+        self.n_reads.append(len(got[0]))
         self.stream.append(stream)
+
+    _layouts: dict = {}       # column names -> (positions of x, l, r, pa, cb_id, read_id; dtypes of the two ids)
+
+    @classmethod
+    def _columns_fast(cls, df):
+        """x, l, r, pa (float64) and cb_id, read_id (their own dtype) of a prepare_input frame through
+        ONE DataFrame -> ndarray conversion.  Per-column Series access, `get_loc` and `dtypes` cost
+        50-150 us each in pandas, which at ~10k UTR/s is more than the GPU spends on the UTR; the frames
+        of a run all share one layout, so positions and id dtypes are looked up once per layout.
+        Integer ids come back exactly (checked: integral and below 2**53), otherwise the caller falls
+        back to the column-by-column path."""
+        try:
+            key = tuple(df.columns.values)
+            lay = cls._layouts.get(key)
+            if lay is None:
+                loc = [df.columns.get_loc(n) for n in ("x", "l", "r", "pa", "cb_id", "read_id")]
+                if not all(isinstance(j, (int, np.integer)) for j in loc):
+                    return None
+                dts = df.dtypes
+                lay = (loc, [dts.iloc[loc[4]], dts.iloc[loc[5]]])
+                if any(d.kind not in "iuf" for d in lay[1]):
+                    return None
+                cls._layouts[key] = lay
+            loc, id_dtypes = lay
+            arr = df.to_numpy(dtype=np.float64)
+            out = [np.ascontiguousarray(arr[:, j]) for j in loc[:4]]
+            for j, dt in zip(loc[4:], id_dtypes):
+                col = arr[:, j]
+                if dt.kind in "iu":
+                    if len(col) and not (np.abs(col).max() < 2.0 ** 53 and np.array_equal(col, np.floor(col))):
+                        return None        # NaN, fractional or huge: this frame's ids are not that integer type
+                    out.append(col.astype(dt))
+                else:
+                    out.append(np.ascontiguousarray(col).astype(dt, copy=False))
+            return out
+        except (TypeError, ValueError, KeyError):
+            return None
 
     def __len__(self):
         return len(self.gene_info)

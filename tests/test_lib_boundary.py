@@ -109,3 +109,32 @@ def test_cli_contract(tmp_path):
     r = CliRunner().invoke(cli, ["infer_pa", "--help"])
     for flag in ("--pkl_input_file", "--output_dir", "--toml_para_file", "--pre_para_pkl_file"):
         assert flag in r.output
+
+
+def test_chunk_batch_packs_prepare_input_frames_exactly():
+    """ChunkBatch.add takes the four read columns and the two id columns out of a prepare_input frame
+    through one ndarray conversion; values and dtypes must equal the column-by-column access, and frames
+    it cannot treat that way (ids that are not integers) must take the slow path and stay exact."""
+    import numpy as np
+    from scape_b200 import apa_core, synth
+    batch = apa_core.ChunkBatch()
+    frames = [synth.to_dataframe(synth.make_utr(300 + i, 50 + 40 * i)) for i in range(6)]
+    frames[2] = frames[2][["read_id", "cb_id", "pa", "r", "l", "x", "junction", "seg1_en", "seg2_en"]]   # other column order
+    odd = frames[4].copy()
+    odd["cb_id"] = odd["cb_id"].astype(float)
+    odd.loc[3, "cb_id"] = np.nan
+    frames[4] = odd
+    for i, df in enumerate(frames):
+        batch.add(f"g{i}", df, i % 2)
+    off, x, l, r, pa, sid = batch.packed()
+    assert list(off) == list(np.cumsum([0] + [len(df) for df in frames]))
+    assert list(sid) == [0, 1, 0, 1, 0, 1]
+    for i, df in enumerate(frames):
+        sl = slice(off[i], off[i + 1])
+        assert np.array_equal(x[sl], np.asarray(df["x"], dtype=np.float64))
+        assert np.array_equal(l[sl], np.asarray(df["l"], dtype=np.float64))
+        assert np.array_equal(r[sl], np.asarray(df["r"], dtype=np.float64), equal_nan=True)
+        assert np.array_equal(pa[sl], np.asarray(df["pa"], dtype=np.float64), equal_nan=True)
+        cb, rid = batch.frames[i]
+        assert cb.dtype == df["cb_id"].dtype and np.array_equal(cb, np.array(df["cb_id"]), equal_nan=True)
+        assert rid.dtype == df["read_id"].dtype and np.array_equal(rid, np.array(df["read_id"]))
