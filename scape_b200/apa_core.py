@@ -109,6 +109,20 @@ class ChunkBatch:
         self.n_reads.append(len(got[0]))
         self.stream.append(stream)
 
+    def add_packed(self, stream: int, gene_infos, n_reads, x, l, r, pa, cb, rid):
+        """All UTRs of one chunk file at once, as produced by `_load_chunk_packed` (possibly in a worker
+        process): concatenated read columns plus the reads-per-UTR list."""
+        for c, col in zip(self.cols, (x, l, r, pa)):      # one piece per file: packed() only concatenates
+            c.append(col)
+        pos = 0
+        for gi, n in zip(gene_infos, n_reads):
+            sl = slice(pos, pos + n)
+            self.gene_info.append(gi)
+            self.frames.append((cb[sl], rid[sl]))
+            self.n_reads.append(int(n))
+            self.stream.append(stream)
+            pos += n
+
     _layouts: dict = {}       # column names -> (positions of x, l, r, pa, cb_id, read_id; dtypes of the two ids)
 
     @classmethod
@@ -165,6 +179,60 @@ def read_chunk_file(path) -> list:
                 out.append(pickle.load(fh))
             except EOFError:
                 return out
+
+
+def _load_chunk_packed(path):
+    """Unpickle one chunk file and pack it (runs in a worker process for many-file calls): the
+    DataFrames stay in the worker, a handful of flat arrays come back."""
+    b = ChunkBatch()
+    for gene_info_str, df in read_chunk_file(path):
+        b.add(gene_info_str, df, 0)
+    cat = lambda parts, dt=None: (np.concatenate(parts) if parts else np.zeros(0, dt or np.float64))
+    cols = [cat(c) for c in b.cols]
+    cb = cat([f[0] for f in b.frames], np.int64)
+    rid = cat([f[1] for f in b.frames], np.int64)
+    return b.gene_info, b.n_reads, cols[0], cols[1], cols[2], cols[3], cb, rid
+
+
+def _write_result_file(path, fixed_run_mode, gene_infos, n_reads, K, L, alpha, beta, ws, bic, n_lb, lb_arr, label, cb, rid):
+    """Build the Parameters objects of one chunk file from flat result arrays and pickle them
+    (apa_core.py:1134-1137); the mirror image of `_load_chunk_packed`, also worker-side."""
+    cls = _result_class()
+    pos = 0
+    with open(path, 'wb') as fh:
+        for u, gi in enumerate(gene_infos):
+            k, n = int(K[u]), int(n_reads[u])
+            para = cls(title='Final Result (subsample run)' if fixed_run_mode else 'Final Result',
+                       alpha_arr=alpha[u, :k].astype('int'), beta_arr=beta[u, :k].copy(), ws=ws[u, :k + 1].copy(),
+                       L=int(L[u]), cb_id_arr=cb[pos:pos + n], readID_arr=rid[pos:pos + n])
+            para.bic = np.float64(bic[u])
+            para.lb_arr = [np.float64(v) for v in lb_arr[u, :int(n_lb[u])]]
+            para.label_arr = label[pos:pos + n].copy()
+            para.gene_info_str = gi
+            pickle.dump(para, fh)
+            pos += n
+    return path
+
+
+_io_pool = None
+
+
+def _get_io_pool(workers: int):
+    """Persistent worker processes for unpickling / pickling chunk files.  forkserver, not fork: the
+    caller's process holds a CUDA context."""
+    global _io_pool
+    if _io_pool is None or _io_pool[0] != workers:
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        if _io_pool is not None:
+            _io_pool[1].shutdown(wait=False)
+        ctx = mp.get_context("forkserver")
+        try:
+            ctx.set_forkserver_preload(["numpy", "pandas", "scape_b200.apa_core"])
+        except Exception:  # pragma: no cover
+            pass
+        _io_pool = (workers, ProcessPoolExecutor(max_workers=workers, mp_context=ctx))
+    return _io_pool[1]
 
 
 def results_to_parameters(batch: ChunkBatch, out, fixed_run_mode: bool) -> list:
@@ -271,14 +339,19 @@ def infer(pickle_input_file, pickle_output_file, **kwargs):
 
 
 def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0,
-                devices: Optional[Sequence[int]] = None, **kwargs) -> List[str]:
+                devices: Optional[Sequence[int]] = None, io_workers: Optional[int] = None, **kwargs) -> List[str]:
     """Multi-file entry point: same per-file seeding and output naming as
     `_infer_pa`, but all files share one library call so their UTRs run concurrently.
 
     `devices=[0, 1, ...]`: the files (RNG streams) are bin-packed over the GPUs by estimated cost
     (`scape_b200.shard`) and fitted by one host thread per GPU (the C call releases the
     GIL); there is nothing to exchange between GPUs.  Results do not depend on the partition: every
-    file is its own stream, seeded 1."""
+    file is its own stream, seeded 1.
+
+    `io_workers` (default: one per core for calls with 64 or more files on one GPU, else 0): worker
+    processes that unpickle / pack the inputs and build / pickle the outputs; 0 keeps everything in
+    this process."""
+    global _io_pool
     os.makedirs(os.path.join(output_dir, "pkl_output"), exist_ok=True)
     names, outs = [], []
     for f in pkl_input_files:
@@ -293,8 +366,19 @@ def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0
     for o in outs:
         if os.path.exists(o):
             os.remove(o)
-    chunks = [read_chunk_file(f) for f in pkl_input_files]
     devs = list(devices) if devices else [device]
+    n_files = len(pkl_input_files)
+    if io_workers is None:
+        # starting the worker processes costs a few seconds once per process (forkserver + pandas import)
+        io_workers = min(os.cpu_count() or 1, n_files) if (n_files >= 64 or _io_pool is not None) else 0
+    if io_workers > 0 and len(devs) <= 1:
+        from concurrent.futures.process import BrokenProcessPool
+        try:
+            return _infer_files_pooled(pkl_input_files, outs, devs[0], io_workers, **kwargs)
+        except BrokenProcessPool as e:      # e.g. a __main__ that worker processes cannot re-import
+            _io_pool = None
+            print(f"infer_files: worker processes unavailable ({e}); continuing in this process")
+    chunks = [read_chunk_file(f) for f in pkl_input_files]
     if len(devs) <= 1:
         results = fit_chunks(chunks, seeds=[1] * len(chunks), device=devs[0], **kwargs)
     else:
@@ -303,6 +387,40 @@ def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0
         with open(o, 'wb') as fh:
             for res in res_lst:
                 pickle.dump(res, fh)
+    return outs
+
+
+def _infer_files_pooled(paths, outs, device, io_workers, **kwargs):
+    """`infer_files` for many files: the DataFrames are unpickled and packed, and the Parameters built
+    and pickled, in worker processes (one task per file); this process only sees flat arrays, packs
+    them into the one `fit_batch` call and slices its results per file.  Same streams, same seeds,
+    same result files as the in-process path."""
+    pool = _get_io_pool(io_workers)
+    fixed = bool(kwargs.get("fixed_run_mode", False))
+    pre_para = _load_pre_para(kwargs) if fixed else None
+    batch = ChunkBatch()
+    per_file = []
+    for s, packed in enumerate(pool.map(_load_chunk_packed, paths)):
+        batch.add_packed(s, *packed)
+        per_file.append((len(packed[0]), packed[0], packed[1], packed[6], packed[7]))
+    engine = _lib.Engine(_lib.make_params(pre_para=pre_para, **kwargs), device=device)
+    try:
+        off, x, l, r, pa, sid = batch.packed()
+        out = engine.fit(off, x, l, r, pa, sid, np.ones(len(paths), np.uint32))
+    finally:
+        engine.close()
+    bad = np.nonzero(out.status != 0)[0]
+    if len(bad):
+        results_to_parameters(batch, out, fixed)          # raises the reference's error for the first bad UTR
+    futures, u0 = [], 0
+    for o, (n_utr, gene_infos, n_reads, cb, rid) in zip(outs, per_file):
+        us = slice(u0, u0 + n_utr)
+        rs = slice(int(off[u0]), int(off[u0 + n_utr]))
+        futures.append(pool.submit(_write_result_file, o, fixed, gene_infos, n_reads, out.K[us], out.L[us], out.alpha[us],
+                                   out.beta[us], out.ws[us], out.bic[us], out.n_lb[us], out.lb_arr[us], out.label[rs], cb, rid))
+        u0 += n_utr
+    for f in futures:
+        f.result()
     return outs
 
 

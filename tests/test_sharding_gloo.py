@@ -128,3 +128,71 @@ def test_bench_cfg3_plan_covers_every_utr_once():
         assert utrs == list(range(20000))
         loads = [sum(shard.utr_cost(int(counts[i]), 20000 if counts[i] >= cut else 2000) for f in p for i in files[f]) for p in parts]
         assert max(loads) / (sum(loads) / world) < 1.10
+
+
+class _FakeEngine:
+    """Stand-in for the GPU fit: results are a deterministic function of the packed inputs."""
+
+    def __init__(self, params, device=0, tensor_dtype=None):
+        self.params = params
+
+    def close(self):
+        pass
+
+    def fit(self, off, x, l, r, pa, sid, seeds, stream_state=None):
+        from scape_b200 import _lib
+        n_utr = len(off) - 1
+        out = _lib.FitOutput(n_utr, int(off[-1]))
+        for u in range(n_utr):
+            n = int(off[u + 1] - off[u])
+            k = 1 + n % 3
+            out.K[u], out.L[u], out.bic[u], out.n_lb[u] = k, 2000 + u, -float(n) - 0.5 * sid[u], 3
+            out.alpha[u, :k] = 100.0 * (np.arange(k) + 1) + x[off[u]] % 7
+            out.beta[u, :k] = 10.0 + 5 * np.arange(k)
+            out.ws[u, :k + 1] = 1.0 / (k + 1)
+            out.lb_arr[u, :3] = [-3.0 * n, -2.5 * n, -2.4 * n]
+            out.label[off[u]:off[u + 1]] = (np.arange(n) + int(l[off[u]])) % (k + 1)
+        return out
+
+
+def test_infer_files_worker_processes_write_the_same_pickles(tmp_path, monkeypatch):
+    """Many-file calls unpickle / pack the inputs and build / pickle the outputs in worker processes;
+    the result files must hold exactly what the in-process path writes (GPU fit replaced by a stand-in)."""
+    import pickle
+    from scape_b200 import _lib, apa_core, synth
+    monkeypatch.setattr(_lib, "Engine", _FakeEngine)
+    utrs = [synth.make_utr(700 + i, 30 + 17 * (i % 9)) for i in range(36)]
+    a_dir, b_dir = tmp_path / "inproc", tmp_path / "pooled"
+    a_dir.mkdir(); b_dir.mkdir()
+    a_paths = synth.write_chunk_files(utrs, str(a_dir), per_file=4)
+    b_paths = synth.write_chunk_files(utrs, str(b_dir), per_file=4)
+    a_out = apa_core.infer_files(a_paths, str(a_dir), io_workers=0)
+    b_out = apa_core.infer_files(b_paths, str(b_dir), io_workers=3)
+    assert [os.path.basename(p) for p in a_out] == [os.path.basename(p) for p in b_out] and len(a_out) == 9
+
+    def load(path):
+        recs = []
+        with open(path, "rb") as fh:
+            while True:
+                try:
+                    recs.append(pickle.load(fh))
+                except EOFError:
+                    return recs
+
+    n = 0
+    for pa_, pb_ in zip(a_out, b_out):
+        ra, rb = load(pa_), load(pb_)
+        assert len(ra) == len(rb) == 4
+        for x, y in zip(ra, rb):
+            assert type(x) is type(y) and type(y).__module__ == "scape.apa_core"
+            assert sorted(vars(x)) == sorted(vars(y))
+            for key, vx in vars(x).items():
+                vy = getattr(y, key)
+                if isinstance(vx, np.ndarray):
+                    assert vx.dtype == vy.dtype and np.array_equal(vx, vy), key
+                elif isinstance(vx, list):
+                    assert vx == vy and all(type(p) is type(q) for p, q in zip(vx, vy)), key
+                else:
+                    assert vx == vy and type(vx) is type(vy), key
+            n += 1
+    assert n == 36
