@@ -371,10 +371,11 @@ def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0
     if io_workers is None:
         # starting the worker processes costs a few seconds once per process (forkserver + pandas import)
         io_workers = min(os.cpu_count() or 1, n_files) if (n_files >= 64 or _io_pool is not None) else 0
-    if io_workers > 0 and len(devs) <= 1:
+    io_workers = int(io_workers)
+    if io_workers > 0:
         from concurrent.futures.process import BrokenProcessPool
         try:
-            return _infer_files_pooled(pkl_input_files, outs, devs[0], io_workers, **kwargs)
+            return _infer_files_pooled(pkl_input_files, outs, devs, io_workers, **kwargs)
         except BrokenProcessPool as e:      # e.g. a __main__ that worker processes cannot re-import
             _io_pool = None
             print(f"infer_files: worker processes unavailable ({e}); continuing in this process")
@@ -390,35 +391,62 @@ def infer_files(pkl_input_files: Sequence[str], output_dir: str, device: int = 0
     return outs
 
 
-def _infer_files_pooled(paths, outs, device, io_workers, **kwargs):
+def _infer_files_pooled(paths, outs, devices, io_workers, **kwargs):
     """`infer_files` for many files: the DataFrames are unpickled and packed, and the Parameters built
     and pickled, in worker processes (one task per file); this process only sees flat arrays, packs
-    them into the one `fit_batch` call and slices its results per file.  Same streams, same seeds,
-    same result files as the in-process path."""
+    them into one `fit_batch` call per GPU (one host thread each; files dealt by estimated cost) and
+    slices the results per file.  Same streams, same seeds, same result files as the in-process path."""
+    import threading
+    from . import shard
     pool = _get_io_pool(io_workers)
     fixed = bool(kwargs.get("fixed_run_mode", False))
     pre_para = _load_pre_para(kwargs) if fixed else None
-    batch = ChunkBatch()
-    per_file = []
-    for s, packed in enumerate(pool.map(_load_chunk_packed, paths)):
-        batch.add_packed(s, *packed)
-        per_file.append((len(packed[0]), packed[0], packed[1], packed[6], packed[7]))
-    engine = _lib.Engine(_lib.make_params(pre_para=pre_para, **kwargs), device=device)
-    try:
-        off, x, l, r, pa, sid = batch.packed()
-        out = engine.fit(off, x, l, r, pa, sid, np.ones(len(paths), np.uint32))
-    finally:
-        engine.close()
-    bad = np.nonzero(out.status != 0)[0]
-    if len(bad):
-        results_to_parameters(batch, out, fixed)          # raises the reference's error for the first bad UTR
-    futures, u0 = [], 0
-    for o, (n_utr, gene_infos, n_reads, cb, rid) in zip(outs, per_file):
-        us = slice(u0, u0 + n_utr)
-        rs = slice(int(off[u0]), int(off[u0 + n_utr]))
-        futures.append(pool.submit(_write_result_file, o, fixed, gene_infos, n_reads, out.K[us], out.L[us], out.alpha[us],
-                                   out.beta[us], out.ws[us], out.bic[us], out.n_lb[us], out.lb_arr[us], out.label[rs], cb, rid))
-        u0 += n_utr
+    packed = list(pool.map(_load_chunk_packed, paths))
+    if len(devices) > 1:
+        hints = [int(np.max(p[2]) + np.max(p[3]) + 50) if len(p[2]) else 2000 for p in packed]   # max x + max l of the file
+        costs = shard.stream_costs([p[1] for p in packed], [[h] * len(p[1]) for h, p in zip(hints, packed)])
+        parts = shard.lpt_partition(costs, len(devices))
+    else:
+        parts = [list(range(len(paths)))]
+    errors: List[BaseException] = []
+    futures, flock = [], threading.Lock()
+
+    def work(dev, mine):
+        try:
+            if not mine:
+                return
+            batch = ChunkBatch()
+            for s, f in enumerate(mine):
+                batch.add_packed(s, *packed[f])
+            engine = _lib.Engine(_lib.make_params(pre_para=pre_para, **kwargs), device=dev)
+            try:
+                off, x, l, r, pa, sid = batch.packed()
+                out = engine.fit(off, x, l, r, pa, sid, np.ones(len(mine), np.uint32))
+            finally:
+                engine.close()
+            if np.any(out.status != 0):
+                results_to_parameters(batch, out, fixed)      # raises the reference's error for the first bad UTR
+            u0 = 0
+            for f in mine:
+                gene_infos, n_reads, cb, rid = packed[f][0], packed[f][1], packed[f][6], packed[f][7]
+                n_utr = len(gene_infos)
+                us = slice(u0, u0 + n_utr)
+                rs = slice(int(off[u0]), int(off[u0 + n_utr]))
+                fut = pool.submit(_write_result_file, outs[f], fixed, gene_infos, n_reads, out.K[us], out.L[us], out.alpha[us],
+                                  out.beta[us], out.ws[us], out.bic[us], out.n_lb[us], out.lb_arr[us], out.label[rs], cb, rid)
+                with flock:
+                    futures.append(fut)
+                u0 += n_utr
+        except BaseException as e:          # re-raised in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d, p)) for d, p in zip(devices, parts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
     for f in futures:
         f.result()
     return outs

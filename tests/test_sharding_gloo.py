@@ -131,7 +131,8 @@ def test_bench_cfg3_plan_covers_every_utr_once():
 
 
 class _FakeEngine:
-    """Stand-in for the GPU fit: results are a deterministic function of the packed inputs."""
+    """Stand-in for the GPU fit: a UTR's results are a deterministic function of its own reads only (like
+    the real fit with one seeded stream per file, they must not depend on what else is in the call)."""
 
     def __init__(self, params, device=0, tensor_dtype=None):
         self.params = params
@@ -146,7 +147,7 @@ class _FakeEngine:
         for u in range(n_utr):
             n = int(off[u + 1] - off[u])
             k = 1 + n % 3
-            out.K[u], out.L[u], out.bic[u], out.n_lb[u] = k, 2000 + u, -float(n) - 0.5 * sid[u], 3
+            out.K[u], out.L[u], out.bic[u], out.n_lb[u] = k, 2000 + n % 11, -float(n) - 0.5 * float(x[off[u]] % 3), 3
             out.alpha[u, :k] = 100.0 * (np.arange(k) + 1) + x[off[u]] % 7
             out.beta[u, :k] = 10.0 + 5 * np.arange(k)
             out.ws[u, :k + 1] = 1.0 / (k + 1)
@@ -169,6 +170,11 @@ def test_infer_files_worker_processes_write_the_same_pickles(tmp_path, monkeypat
     a_out = apa_core.infer_files(a_paths, str(a_dir), io_workers=0)
     b_out = apa_core.infer_files(b_paths, str(b_dir), io_workers=3)
     assert [os.path.basename(p) for p in a_out] == [os.path.basename(p) for p in b_out] and len(a_out) == 9
+    # ... and with the files dealt over three (stand-in) GPUs on top of the worker processes
+    c_dir = tmp_path / "pooled3"
+    c_dir.mkdir()
+    c_paths = synth.write_chunk_files(utrs, str(c_dir), per_file=4)
+    c_out = apa_core.infer_files(c_paths, str(c_dir), io_workers=3, devices=[0, 1, 2])
 
     def load(path):
         recs = []
@@ -180,7 +186,7 @@ def test_infer_files_worker_processes_write_the_same_pickles(tmp_path, monkeypat
                     return recs
 
     n = 0
-    for pa_, pb_ in zip(a_out, b_out):
+    for pa_, pb_ in list(zip(a_out, b_out)) + list(zip(a_out, c_out)):
         ra, rb = load(pa_), load(pb_)
         assert len(ra) == len(rb) == 4
         for x, y in zip(ra, rb):
@@ -195,4 +201,4 @@ def test_infer_files_worker_processes_write_the_same_pickles(tmp_path, monkeypat
                 else:
                     assert vx == vy and type(vx) is type(vy), key
             n += 1
-    assert n == 36
+    assert n == 72
