@@ -173,6 +173,7 @@ struct scape_b200_handle {
   int host_threads = 0;     // 0 = CPUs of this process / ranks sharing the host
   std::unique_ptr<WorkPool> prep_pool;
   bool overlap = true;      // likelihood phase of wave w+1 runs under the EM of wave w
+  bool poison = false;      // SCAPE_B200_POISON=1 (tests): fill the tensor arena with NaN bits before every wave
 };
 
 static double now_ms() {
@@ -291,6 +292,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   if (const char* s = getenv("SCAPE_B200_THREADS")) h->host_threads = atoi(s);
   if (const char* s = getenv("SCAPE_B200_TENSOR")) h->tensor_f32 = (strcmp(s, "f64") != 0);
   if (const char* s = getenv("SCAPE_B200_OVERLAP")) h->overlap = atoi(s) != 0;
+  if (const char* s = getenv("SCAPE_B200_POISON")) h->poison = atoi(s) != 0;
   if (const char* s = getenv("SCAPE_B200_LANES")) h->n_lanes = std::max(1, std::min(kMaxLanes, atoi(s)));
   *out = h;
   return 0;
@@ -411,7 +413,12 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     chain_off[size_t(c.utr) + 1]++;
     if (!c.weights_only) { scans[size_t(c.utr)] = 1; any_scan = true; }
   }
-  for (size_t i = 0; i < W; i++) chain_off[i + 1] += chain_off[i];
+  for (size_t i = 0; i < W; i++) {
+    if (scans[i] && chain_off[i + 1] > kScanMaxChains)
+      return fail(-5, "internal: " + std::to_string(chain_off[i + 1]) + " chains of one UTR in one run; the scan lists at most " +
+                          std::to_string(kScanMaxChains));
+    chain_off[i + 1] += chain_off[i];
+  }
   std::vector<int32_t> index;
   index.reserve(chains.size());
   static const int warp_max_n = getenv("SCAPE_B200_WARP_MAXN") ? atoi(getenv("SCAPE_B200_WARP_MAXN")) : kWarpEstepMaxN;
@@ -558,6 +565,8 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   L.tm.scan_ms += s_ms;
   L.tm.scan_launches += L.em_events.scan_launches;
   L.tm.launches += nl;
+  for (auto& c : chains)
+    if (c.error) return fail(-7, "non-finite grid-search scores (a NaN reached max_alpha_beta)");
   for (auto& c : chains) {
     const UtrDev& u = utrs_host[size_t(c.utr)];
     L.tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;     // FP64 tensor, one chain at a time
@@ -705,6 +714,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     for (size_t i = 0; i < W; i++) max_ldr = std::max<int64_t>(max_ldr, ud[i].ldR);
     const int64_t slack = int64_t(kTensorSlackRows) * max_ldr;     // elements; see scan_subbatch's register ring
     CU(S.d_table.ensure(size_t(ntab))); CU(S.d_tensor.ensure(size_t(nten + slack)));
+    if (h->poison) CU(cudaMemsetAsync(S.d_tensor.p, 0xFF, S.d_tensor.cap * sizeof(double), sq));   // every byte the kernels do not write is NaN
     CU(cudaMemsetAsync((char*)S.d_tensor.p + size_t(nten) * esz, 0, size_t(slack) * esz, sq));
     CU(S.d_utrs.ensure(W)); CU(S.d_rows.ensure(size_t(n_rows)));
     CU(S.d_trows.ensure(size_t(n_trows) + 1)); CU(S.d_tiles.ensure(size_t(n_tiles) + 1));

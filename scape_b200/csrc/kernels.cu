@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(256) tensor_kernel(const UtrDev* __restrict__ 
   const double* tab = table + u.table_off + n;
   // tensor layout [n][R], R = T*B candidate rows (alpha-major, beta-minor) contiguous per fragment
   TT* out = tensor + u.tensor_off + (int64_t)n * u.ldR + (int64_t)rr.t * B;
+  // The pitch ldR rounds T*B up to 4: the pad columns must hold finite values, because the scan's
+  // k-loop runs a few fragments past a UTR's last one (multiplied by V = 0) and those reads can land
+  // on the pad columns of the next UTR's region.  The last alpha row always takes this kernel.
+  if (rr.t == u.T - 1)
+    for (int64_t c = (int64_t)u.T * B; c < u.ldR; c++) tensor[u.tensor_off + (int64_t)n * u.ldR + c] = TT(0);
   const int64_t ld = u.Npad;
   const double* col_all = tab + (int64_t)lo_all * ld;
   // One exp per theta of the union window, shared by all betas:
@@ -385,6 +390,7 @@ constexpr int GW = GT / 32;                // warps
 constexpr int SCAN_ROWS = GT;              // candidate rows per block (1 per thread)
 constexpr int SCAN_GB = 32;                // chains per register sub-batch (32 FP64 accumulators per thread)
 constexpr int SCAN_MAXCH = 160;            // running chains of one UTR a scan CTA can list
+static_assert(SCAN_MAXCH == kScanMaxChains, "api.cu checks the chain count of a UTR against kScanMaxChains");
 constexpr int SCAN_VCHUNK = 256;           // fragments of V staged per chunk
 constexpr int SCAN_VPITCH = SCAN_VCHUNK + 4;  // pitch = 4 mod 16 doubles: the 8x4 B-fragment loads are bank-conflict free
 
@@ -471,8 +477,17 @@ __device__ __forceinline__ int apply_pending(ChainDev& ch, ScanDesc& sd, const U
       if (ob > best || (ob == best && orow < row)) { best = ob; row = orow; }
     }
     if (lane == 0) {
-      ch.a_idx[ch.cur_k] = row / u.B;
-      ch.b_idx[ch.cur_k] = row % u.B;
+      if (row < ch.row0 || row >= ch.row1) {
+        // no candidate of the window won a `>` comparison: every score was NaN.  Fail the chain (the
+        // host turns this into an error) instead of indexing the tensor with a row that is not one.
+        ch.error = 1;
+        ch.state = 0;
+        ch.bic = CUDART_NAN;
+        go = 0;
+      } else {
+        ch.a_idx[ch.cur_k] = row / u.B;
+        ch.b_idx[ch.cur_k] = row % u.B;
+      }
       ch.pending = 0;
       sd.pending = 0;
       if (ch.trace_off >= 0) ch.trace_pending = ch.n_iter;
@@ -487,7 +502,7 @@ __device__ __forceinline__ int apply_pending(ChainDev& ch, ScanDesc& sd, const U
       ch.trace_pending = 0;
     }
     if (ch.state == 2) { finalize_chain(ch, u.N); go = 0; }
-    if (ch.n_iter >= SCAPE_B200_NROUND) go = 0;
+    if (ch.n_iter >= SCAPE_B200_NROUND || ch.error) go = 0;
   }
   __syncwarp();
   return __shfl_sync(0xffffffffu, go, 0);

@@ -74,6 +74,7 @@ struct ChainDev {
   int32_t state;                  // 0 finished, 1 running, 2 converged (finishes once its last arg-max is applied)
   int32_t pending;                // the scan of this step must cover this chain
   int32_t cur_k, row0, row1, hlo, hhi, trace_pending;
+  int32_t error, pad_;            // out: 1 = the grid search saw only non-finite scores (the chain is abandoned)
 };
 
 // What the scan needs to know about a chain, compact (the E step writes it, scan CTAs read 50 of them)
@@ -128,6 +129,7 @@ void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev
 cudaError_t upload_model_const(const ModelConst& mc);
 constexpr int kTensorSlackRows = 64;   // zeroed fragment rows after the last UTR's tensor: the scan's register ring prefetches past the hull
 constexpr int kScanRows = 256;    // candidate rows per scan CTA (must equal SCAN_ROWS in kernels.cu)
+constexpr int kScanMaxChains = 160;  // running chains of one UTR a scan CTA can list (must equal SCAN_MAXCH)
 constexpr int kPartialBytes = 16; // sizeof(ScanPartial)
 // returns the number of kernel launches made
 // CUDA events bracketing every launch group of one EM run (kept per lane, reused)

@@ -23,3 +23,19 @@ def golden():
     labels = np.load(os.path.join(GOLD, "reference_labels.npz"))
     inputs = np.load(os.path.join(GOLD, "example_inputs.npz"))
     return dict(cases=res, labels=labels, inputs=inputs)
+
+
+_REPORT = []
+
+
+@pytest.fixture
+def report_line():
+    """Lines a test wants in the terminal summary (they survive `-q` and land in the driver's log)."""
+    return _REPORT.append
+
+
+def pytest_terminal_summary(terminalreporter):
+    if _REPORT:
+        terminalreporter.write_sep("=", "parity / measurement summary")
+        for line in _REPORT:
+            terminalreporter.write_line(line)
