@@ -106,6 +106,9 @@ typedef struct scape_b200_timing {
   double em_scan_bytes;                           /* tensor bytes the grid search actually loads (fragment hull only) */
   double estep_ms, scan_ms;                       /* em_ms split: E-step kernels / arg-max scan kernels */
   int64_t scan_launches;
+  double cluster_ms;                              /* em_ms spent in the cluster-resident EM kernel (E passes + grid search of a whole run) */
+  double cluster_grid_flops;                      /* algorithmic grid-search flops (2 W_k B N per chain iteration) done by that kernel */
+  int64_t cluster_launches;
 } scape_b200_timing;
 
 typedef struct scape_b200_handle scape_b200_handle;

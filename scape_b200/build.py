@@ -6,8 +6,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "host_prep.hpp", "np_rng.hpp", "work_pool.hpp")] + \
+SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cu", "em_cluster.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "em_device.cuh", "host_prep.hpp", "np_rng.hpp", "work_pool.hpp")] + \
     [os.path.join(os.path.dirname(HERE), "include", "scape_b200.h")]
 LIB = os.path.join(HERE, "libscape_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -122,6 +122,8 @@ struct Lane {
   DevBuf<ChainDev> d_chains;
   DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
   DevBuf<ScanRef> d_refs;
+  DevBuf<ClusterJob> d_cjobs;
+  cudaEvent_t ev_cl[2] = {nullptr, nullptr};   // around the cluster-resident EM launch
   DevBuf<ScanDesc> d_descs;
   DevBuf<int32_t> d_chain_off, d_chain_idx, d_lists, d_counts;
   DevBuf<double> d_partials, d_counter;
@@ -137,7 +139,7 @@ struct Lane {
     d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
     d_table.release(); d_tensor.release(); d_lz.release(); d_v.release(); d_trace_ws.release(); d_utrs.release();
     d_rows.release(); d_trows.release(); d_tiles.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
-    d_refs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
+    d_refs.release(); d_cjobs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_lists.release(); d_counts.release();
     d_counter.release(); d_jobs.release();
     h_chains.release(); h_refits.release();
@@ -279,6 +281,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
     CU(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio_hi));
     CU(cudaStreamCreateWithPriority(&L.st_lik, cudaStreamNonBlocking, prio_lo));
     for (auto& e : L.ev) CU(cudaEventCreate(&e));
+    for (auto& e : L.ev_cl) CU(cudaEventCreate(&e));
     for (auto& e : L.staged.ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&L.ev_mid, cudaEventDisableTiming));
     if (const char* s = getenv("SCAPE_B200_STAGE_STEP")) L.stage_step = atoi(s);
@@ -306,6 +309,7 @@ int scape_b200_destroy(scape_b200_handle* h) {
     cudaStreamSynchronize(L.st_lik);
     L.release();
     for (auto& e : L.ev) cudaEventDestroy(e);
+    for (auto& e : L.ev_cl) cudaEventDestroy(e);
     for (auto& e : L.staged.ev) cudaEventDestroy(e);
     cudaEventDestroy(L.ev_mid);
     cudaStreamDestroy(L.st);
@@ -390,11 +394,29 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   std::vector<int32_t> chain_off(W + 1, 0);
   std::vector<char> scans(W, 0);
   bool any_scan = false;
+  // Which EM kernel a UTR's chains take: the cluster-resident kernel (one cluster per UTR, all
+  // iterations in one launch) when a pass of its V rows fits the kernel's shared memory and its
+  // per-iteration grid search is small enough for one cluster, else the bulk-synchronous step kernels
+  // (whole GPU per step: giant UTRs).  SCAPE_B200_EM=bsp forces the latter for everything.
+  static const bool cluster_on = !(getenv("SCAPE_B200_EM") && strcmp(getenv("SCAPE_B200_EM"), "bsp") == 0);
+  static const double cluster_max_cost = getenv("SCAPE_B200_CLUSTER_COST") ? atof(getenv("SCAPE_B200_CLUSTER_COST")) : 4e8;
+  std::vector<char> in_cluster(W, 0);
+  {
+    std::vector<int32_t> n_scan(W, 0);
+    for (size_t i = 0; i < chains.size(); i++)
+      if (!chains[i].weights_only) n_scan[size_t(chains[i].utr)]++;
+    for (size_t i = 0; i < W && cluster_on; i++) {
+      const UtrDev& u = utrs_host[i];
+      const double cost = double(u.N) * double(u.T) * u.B * n_scan[i];     // fragment x candidate row x chain products per iteration
+      in_cluster[i] = n_scan[i] > 0 && cluster_chains_per_pass(u.N) >= 8 && cost <= cluster_max_cost;
+    }
+  }
   for (size_t i = 0; i < chains.size(); i++) {
     ChainDev& c = chains[i];
     if (i > 0 && c.utr < chains[i - 1].utr) return fail(-5, "internal: chains not ordered by UTR");
     const UtrDev& u = utrs_host[size_t(c.utr)];
-    const int64_t n_blk = (int64_t(u.T) * u.B + kScanRows - 1) / kScanRows;
+    const int rows_per_partial = in_cluster[size_t(c.utr)] ? kClusterTileRows : kScanRows;
+    const int64_t n_blk = (int64_t(u.T) * u.B + rows_per_partial - 1) / rows_per_partial;
     c.lz_off = lz;
     lz += int64_t(c.K + 1) * u.Npad;
     c.v_off = vsz;
@@ -422,8 +444,9 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   std::vector<int32_t> index;
   index.reserve(chains.size());
   static const int warp_max_n = getenv("SCAPE_B200_WARP_MAXN") ? atoi(getenv("SCAPE_B200_WARP_MAXN")) : kWarpEstepMaxN;
+  auto bsp_chain = [&](size_t i) { return !in_cluster[size_t(chains[i].utr)]; };
   for (size_t i = 0; i < chains.size(); i++)
-    if (utrs_host[size_t(chains[i].utr)].N <= warp_max_n) index.push_back(int32_t(i));
+    if (bsp_chain(i) && utrs_host[size_t(chains[i].utr)].N <= warp_max_n) index.push_back(int32_t(i));
   const int64_t n_small = int64_t(index.size());
   // same-K chains next to each other: the warps resident on an SM then run the same template
   // instantiation of the E step (instruction-cache locality; 24 % 'no instruction' stalls otherwise);
@@ -455,7 +478,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     });
   }
   for (size_t i = 0; i < chains.size(); i++)
-    if (utrs_host[size_t(chains[i].utr)].N > warp_max_n) index.push_back(int32_t(i));
+    if (bsp_chain(i) && utrs_host[size_t(chains[i].utr)].N > warp_max_n) index.push_back(int32_t(i));
   const int64_t n_big = int64_t(index.size()) - n_small;
   // Scan work items.  A CTA's cost is (fragments of the UTR) x (chains it multiplies); the step ends
   // with the slowest CTA.  UTRs whose single-CTA cost is above half of an even share of the wave's
@@ -468,7 +491,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     const double slots = 2.0 * h->n_sm;
     double total = 0;
     for (size_t i = 0; i < W; i++)
-      if (scans[i]) {
+      if (scans[i] && !in_cluster[i]) {
         const UtrDev& u = utrs_host[i];
         const double n_blk = double((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
         total += n_blk * u.N * double(chain_off[i + 1] - chain_off[i]);
@@ -476,7 +499,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     const double limit = std::max(0.5 * total / slots, 2048.0);
     std::vector<double> cost;
     for (size_t i = 0; i < W; i++)
-      if (scans[i]) {
+      if (scans[i] && !in_cluster[i]) {
         const UtrDev& u = utrs_host[i];
         const int32_t n_blk = int32_t((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
         const int C = chain_off[i + 1] - chain_off[i];
@@ -500,6 +523,27 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
       refs.swap(sorted);
     }
   }
+  // Cluster jobs, most expensive first (the hardware dispatches clusters in launch order as SMs free up)
+  std::vector<ClusterJob> cjobs;
+  {
+    std::vector<double> ccost;
+    for (size_t i = 0; i < W; i++)
+      if (in_cluster[i]) {
+        const UtrDev& u = utrs_host[i];
+        // all chains of the UTR (weights-only ones included: the kernel iterates them to convergence in place)
+        cjobs.push_back(ClusterJob{int32_t(i), chain_off[i], chain_off[i + 1] - chain_off[i], cluster_chains_per_pass(u.N)});
+        ccost.push_back(double(u.N) * u.T * double(chain_off[i + 1] - chain_off[i]));
+      }
+    std::vector<size_t> ord(cjobs.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return ccost[a] > ccost[b]; });
+    std::vector<ClusterJob> sorted(cjobs.size());
+    for (size_t i = 0; i < ord.size(); i++) sorted[i] = cjobs[ord[i]];
+    cjobs.swap(sorted);
+  }
+  CU(L.d_cjobs.ensure(cjobs.size() + 1));
+  if (!cjobs.empty())
+    CU(cudaMemcpyAsync(L.d_cjobs.p, cjobs.data(), sizeof(ClusterJob) * cjobs.size(), cudaMemcpyHostToDevice, L.st));
   CU(L.d_lz.ensure(size_t(lz)));
   CU(L.d_v.ensure(size_t(vsz + 8)));
   CU(L.d_chains.ensure(chains.size()));
@@ -543,10 +587,31 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     // depend on the composition of its wave
     plan.g_small = (g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) ? g_env : 4;
   }
-  int nl = launch_em_steps(L.d_chains.p, L.d_descs.p, L.d_chain_idx.p, n_small, n_big, any_scan, big_k, L.d_refs.p, int64_t(refs.size()),
-                           L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_lz.p,
-                           L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
-                           L.d_trace_ws.p, L.st, L.em_events, plan);
+  int nl = 0;
+  if (!cjobs.empty()) {
+    // cluster size: as many CTAs per UTR as keep all the wave's clusters resident at once (2 CTAs per SM)
+    static const int c_env = getenv("SCAPE_B200_CLUSTER") ? atoi(getenv("SCAPE_B200_CLUSTER")) : 0;
+    int csize = 1;
+    while (csize < 8 && size_t(csize) * 2 * cjobs.size() <= size_t(2 * h->n_sm)) csize *= 2;
+    if (c_env == 1 || c_env == 2 || c_env == 4 || c_env == 8) csize = c_env;
+    // the wave scheduler's hook (next wave's likelihood phase on the low-priority stream) fires at a
+    // step of the bulk-synchronous loop; a wave without one releases it before the cluster launch, so
+    // the staged wave's table / tensor kernels fill the SMs as this wave's clusters retire
+    if (n_small + n_big == 0 && L.em_events.hook) L.em_events.hook();
+    CU(cudaEventRecord(L.ev_cl[0], L.st));
+    CU(launch_em_cluster(L.d_cjobs.p, int(cjobs.size()), csize, L.d_chains.p, L.d_descs.p, L.d_utrs.p, L.d_tensor.p,
+                         h->tensor_f32, L.d_cnt.p, L.d_lz.p, L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p,
+                         L.d_trace_b.p, L.d_trace_ws.p, L.st));
+    CU(cudaEventRecord(L.ev_cl[1], L.st));
+    nl += 1;
+  }
+  if (n_small + n_big > 0)
+    nl += launch_em_steps(L.d_chains.p, L.d_descs.p, L.d_chain_idx.p, n_small, n_big, any_scan && !refs.empty(), big_k, L.d_refs.p, int64_t(refs.size()),
+                          L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_lz.p,
+                          L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
+                          L.d_trace_ws.p, L.st, L.em_events, plan);
+  else
+    L.em_events.kinds.clear();
   CU(cudaGetLastError());
   CU(cudaEventRecord(L.ev[5], L.st));
   double scan_elems = 0;
@@ -561,6 +626,14 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   L.busy.emplace_back(t0, t0 + ms);
   double e_ms = 0, s_ms = 0;
   em_steps_elapsed(L.em_events, &e_ms, &s_ms);
+  if (!cjobs.empty()) {
+    float cms = 0;
+    CU(cudaEventElapsedTime(&cms, L.ev_cl[0], L.ev_cl[1]));
+    L.tm.cluster_ms += cms;
+    L.tm.cluster_launches += 1;
+    for (auto& c : chains)
+      if (in_cluster[size_t(c.utr)]) L.tm.cluster_grid_flops += c.grid_rows * double(utrs_host[size_t(c.utr)].N) * 2.0;
+  }
   L.tm.estep_ms += e_ms;
   L.tm.scan_ms += s_ms;
   L.tm.scan_launches += L.em_events.scan_launches;
@@ -1193,6 +1266,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
     h->tm.em_grid_bytes += t.em_grid_bytes; h->tm.em_grid_flops += t.em_grid_flops; h->tm.tensor_exp += t.tensor_exp;
     h->tm.h2d_bytes += t.h2d_bytes; h->tm.d2h_bytes += t.d2h_bytes; h->tm.em_scan_bytes += t.em_scan_bytes;
     h->tm.estep_ms += t.estep_ms; h->tm.scan_ms += t.scan_ms; h->tm.scan_launches += t.scan_launches;
+    h->tm.cluster_ms += t.cluster_ms; h->tm.cluster_launches += t.cluster_launches; h->tm.cluster_grid_flops += t.cluster_grid_flops;
     iv.insert(iv.end(), h->lanes[l].busy.begin(), h->lanes[l].busy.end());
   }
   std::sort(iv.begin(), iv.end());

@@ -1,0 +1,393 @@
+// Device code shared by the EM kernels (kernels.cu: bulk-synchronous step kernels; em_cluster.cu:
+// the cluster-resident EM kernel): the E pass of one chain (cal_z_k, norm_z, maximize_ws, elbo --
+// apa_core.py:473-573), the application of a grid arg-max found by a scan (max_alpha_beta :507-523)
+// and the FP64 tensor-core MMA wrapper.  Every translation unit that includes this header owns a
+// copy of the model constants (`c_mc`) and must upload it (upload_model_const_tu).
+#pragma once
+#include "kernels.cuh"
+
+namespace scape {
+
+static __constant__ ModelConst c_mc;
+static inline cudaError_t upload_model_const_tu(const ModelConst& mc) { return cudaMemcpyToSymbol(c_mc, &mc, sizeof(ModelConst)); }
+
+constexpr int GT = 256;                    // threads per CTA
+constexpr int GW = GT / 32;                // warps
+constexpr int SCAN_ROWS = GT;              // candidate rows per block (1 per thread)
+constexpr int SCAN_GB = 32;                // chains per register sub-batch (32 FP64 accumulators per thread)
+constexpr int SCAN_MAXCH = 160;            // running chains of one UTR a scan CTA can list
+static_assert(SCAN_MAXCH == kScanMaxChains, "api.cu checks the chain count of a UTR against kScanMaxChains");
+constexpr int SCAN_VCHUNK = 256;           // fragments of V staged per chunk
+constexpr int SCAN_VPITCH = SCAN_VCHUNK + 4;  // pitch = 4 mod 16 doubles: the 8x4 B-fragment loads are bank-conflict free
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+template <typename TT> __device__ __forceinline__ double lds_elem(uint32_t addr);
+template <> __device__ __forceinline__ double lds_elem<float>(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return (double)v;
+}
+template <> __device__ __forceinline__ double lds_elem<double>(uint32_t addr) { return lds_f64(addr); }
+
+// ------------------------------------------------------------------------------------------------
+// E step
+// ------------------------------------------------------------------------------------------------
+struct ScanPartial {
+  double score;
+  int row;
+  int pad;
+};
+struct EShared {
+  double red[GW][SCAPE_B200_KCAP + 4];
+  double tot[SCAPE_B200_KCAP + 4];
+  double lwk;
+  long long rk;
+  int k, go, hull[2];
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_sum(double (&val)[NV], EShared& sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    double x = val[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh.red[warp][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < GW; w++) acc += sh.red[w][threadIdx.x];
+    sh.tot[threadIdx.x] = acc;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void finalize_chain(ChainDev& ch, int N) {
+  const int K = ch.K;
+  ch.bic = -2.0 * ch.last_a + (3 * K + 1) * log((double)N);   // cal_bic (:702-706)
+  ch.state = 0;
+}
+
+// (0) of a step, executed by one full warp: apply the arg-max the previous scan found for this chain
+// (first maximum in row order over the per-block partials), write the trace, finalise converged
+// chains.  Returns 1 (in every lane) if the chain still has an E step to do.
+template <int PROWS = SCAN_ROWS>
+__device__ __forceinline__ int apply_pending(ChainDev& ch, ScanDesc& sd, const UtrDev& u,
+                                             const ScanPartial* __restrict__ partials, int32_t* trace_a,
+                                             int32_t* trace_b, double* trace_ws) {
+  const int lane = threadIdx.x & 31;
+  int go = 1;
+  if (ch.pending) {
+    const int b0 = ch.row0 / PROWS, b1 = (ch.row1 - 1) / PROWS;     // PROWS = candidate rows per partial
+    double best = -CUDART_INF;
+    int row = 0x7fffffff;
+    for (int b = b0 + lane; b <= b1; b += 32) {
+      // L2 load: in the cluster kernel the partials were written by other SMs a cluster barrier ago
+      const double2 raw = __ldcg(reinterpret_cast<const double2*>(partials + ch.pb_off + b));
+      ScanPartial p;
+      p.score = raw.x;
+      p.row = (int)(__double_as_longlong(raw.y) & 0xffffffffll);
+      if (p.score > best || (p.score == best && p.row < row)) { best = p.score; row = p.row; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int orow = __shfl_xor_sync(0xffffffffu, row, o);
+      if (ob > best || (ob == best && orow < row)) { best = ob; row = orow; }
+    }
+    if (lane == 0) {
+      if (row < ch.row0 || row >= ch.row1) {
+        // no candidate of the window won a `>` comparison: every score was NaN.  Fail the chain (the
+        // host turns this into an error) instead of indexing the tensor with a row that is not one.
+        ch.error = 1;
+        ch.state = 0;
+        ch.bic = CUDART_NAN;
+        go = 0;
+      } else {
+        ch.a_idx[ch.cur_k] = row / u.B;
+        ch.b_idx[ch.cur_k] = row % u.B;
+      }
+      ch.pending = 0;
+      sd.pending = 0;
+      if (ch.trace_off >= 0) ch.trace_pending = ch.n_iter;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (ch.trace_off >= 0 && ch.trace_pending > 0) {
+      const int64_t o = ch.trace_off + (int64_t)(ch.trace_pending - 1) * (SCAPE_B200_KCAP + 1);
+      for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
+      for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
+      ch.trace_pending = 0;
+    }
+    if (ch.state == 2) { finalize_chain(ch, u.N); go = 0; }
+    if (ch.n_iter >= SCAPE_B200_NROUND || ch.error) go = 0;
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, go, 0);
+}
+
+// After the E pass: weights (maximize_ws :498-505), ELBO (:559-561), convergence (:743), and the
+// candidate window / fragment hull the scan needs.  `tot` = [cnt@Z (NK), sum Z[:,k], A term, H term].
+template <int NK>
+__device__ __forceinline__ void estep_epilogue(ChainDev& ch, ScanDesc& sd, const UtrDev& u, const double* tot, int k,
+                                               int it, int hull_lo, int hull_hi) {
+  constexpr int K = NK - 1;
+  const double cap = c_mc.max_unif_ws;
+  const int N = u.N, B = u.B;
+  double w[NK];
+  double sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < NK; j++) sum += tot[j];
+#pragma unroll
+  for (int j = 0; j < NK; j++) w[j] = tot[j] / sum;
+  if (w[K] > cap) {
+    double rest = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) rest += w[j];
+#pragma unroll
+    for (int j = 0; j < K; j++) w[j] = (1 - cap) * w[j] / rest;
+    w[K] = cap;
+  }
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    ch.ws[j] = w[j];
+    ch.lw[j] = (w[j] <= 0.0) ? SCAPE_SENTINEL : log(w[j]);
+  }
+  const double lb_new = tot[NK + 1] + tot[NK + 2];
+  ch.last_a = tot[NK + 1];
+  ch.lb_arr[it] = lb_new;
+  ch.n_iter = it + 1;
+  const double lb = ch.lb_prev;
+  const bool conv = fabs(lb_new - lb) < fabs(1e-6 * lb);
+  if (!conv) ch.lb_prev = lb_new;
+  const bool last = conv || it == SCAPE_B200_NROUND - 1;
+  ch.cur_k = k;
+  if (ch.weights_only) {                                        // mstep_fixed (:552-557): no grid search
+    if (last) finalize_chain(ch, N); else ch.state = 1;
+  } else {
+    // max_alpha_beta (:507-523): candidate window of component k
+    const int lo = (k == 0) ? 0 : ch.a_idx[k - 1];
+    const int hi = (k == K - 1) ? u.T - 1 : ch.a_idx[k + 1];
+    ch.row0 = lo * B;
+    ch.row1 = (hi + 1) * B;
+    ch.hlo = hull_lo;
+    ch.hhi = hull_hi;
+    ch.grid_rows += (double)(ch.row1 - ch.row0);
+    ch.pending = 1;
+    ch.state = last ? 2 : 1;
+    sd.row0 = ch.row0; sd.row1 = ch.row1; sd.hlo = hull_lo; sd.hhi = hull_hi;
+    sd.v_off = ch.v_off; sd.pb_off = ch.pb_off;
+    sd.pending = 1;
+  }
+}
+
+// One fragment of the E pass (shared by the warp- and the block-per-chain kernels).
+// What one fragment of the E pass reads from HBM / L2: its count, its tensor entry for the refreshed
+// component (a strided gather: DRAM latency) and the stale log_zmat columns.  Kept apart from the
+// arithmetic so that a caller can fetch the next fragment while it computes the current one.
+template <int NK, typename TT>
+struct FragIn {
+  double c;
+  TT a;
+  double lz[NK];
+};
+template <int NK, typename TT>
+__device__ __forceinline__ void estep_load(FragIn<NK, TT>& f, int n, int k, int64_t rk, int npad, int64_t R,
+                                           const TT* __restrict__ A, const double* __restrict__ cnt,
+                                           const double* __restrict__ lz) {
+  f.c = cnt[n];
+  f.a = A[(int64_t)n * R + rk];
+#pragma unroll
+  for (int j = 0; j < NK; j++) f.lz[j] = (j == k) ? 0.0 : lz[(int64_t)j * npad + n];
+}
+
+template <int NK, typename TT>
+__device__ __forceinline__ void estep_compute(const FragIn<NK, TT>& f, int n, int k, double lwk, bool guard, int npad,
+                                              double* __restrict__ lz, double* __restrict__ V, double (&red)[NK + 3],
+                                              int& h_lo, int& h_hi);
+
+template <int NK, typename TT>
+__device__ __forceinline__ void estep_fragment(int n, int k, double lwk, int64_t rk, bool guard, int npad, int64_t R,
+                                               const TT* __restrict__ A, const double* __restrict__ cnt,
+                                               double* __restrict__ lz, double* __restrict__ V, double (&red)[NK + 3],
+                                               int& h_lo, int& h_hi) {
+  FragIn<NK, TT> f;
+  estep_load<NK, TT>(f, n, k, rk, npad, R, A, cnt, lz);
+  estep_compute<NK, TT>(f, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
+}
+
+template <int NK, typename TT>
+__device__ __forceinline__ void estep_compute(const FragIn<NK, TT>& f, int n, int k, double lwk, bool guard, int npad,
+                                              double* __restrict__ lz, double* __restrict__ V, double (&red)[NK + 3],
+                                              int& h_lo, int& h_hi) {
+  const double c = f.c;
+  const double fresh = lwk + (double)f.a;
+  double z[NK], lzv[NK];
+  double m = -CUDART_INF;
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    lzv[j] = (j == k) ? fresh : f.lz[j];
+    m = fmax(m, lzv[j]);
+  }
+  lz[(int64_t)k * npad + n] = fresh;
+  double s = 0.0, ex[NK];
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    ex[j] = (lzv[j] - m) * c;                // exponent of the count-tempered softmax (norm_z :491-493)
+    z[j] = exp(ex[j]);
+    s += z[j];
+  }
+  const double inv_s = 1.0 / s;              // one reciprocal instead of NK divisions (<= 1 ulp per entry)
+  double zk = 0.0;
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    z[j] = z[j] * inv_s;
+    if (j == k) zk = z[j];
+  }
+  red[NK] += zk;                             // np.sum(Z[:, k]) before the guard
+  if (guard) {
+    zk += 1e-8;
+#pragma unroll
+    for (int j = 0; j < NK; j++)
+      if (j == k) z[j] = zk;
+  }
+  double ps = 0.0, Aterm = 0.0;
+#pragma unroll
+  for (int j = 0; j < NK; j++) {
+    red[j] = fma(c, z[j], red[j]);           // cnt @ Z
+    if (z[j] != 0.0) Aterm += (z[j] * c) * lzv[j];
+    ps += z[j];
+  }
+  // scipy.stats.entropy(Z[n, :]) = -sum p log p with p = Z / sum(Z).  Without the guard,
+  // log p_j = ex_j - log(s) - log(ps) exactly in real arithmetic: two logs instead of NK.
+  double h = 0.0;
+  const double inv_ps = 1.0 / ps;
+  if (!guard) {
+    const double lnorm = log(s) + log(ps);
+#pragma unroll
+    for (int j = 0; j < NK; j++) {
+      const double p = z[j] * inv_ps;
+      if (p > 0.0) h -= p * (ex[j] - lnorm);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NK; j++) {
+      const double p = z[j] * inv_ps;
+      if (p > 0.0) h -= p * log(p);
+    }
+  }
+  red[NK + 1] += Aterm;
+  red[NK + 2] = fma(c, h, red[NK + 2]);
+  const double vn = zk * c;
+  V[n] = vn;
+  if (vn != 0.0) { h_lo = min(h_lo, n); h_hi = n; }
+}
+
+// Warp-per-chain E step (small fragment counts): no block barriers, reductions by shuffles.
+template <int NK, typename TT, bool PF>
+__device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, const TT* __restrict__ A,
+                               const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ V) {
+  constexpr int K = NK - 1;
+  const int lane = threadIdx.x & 31;
+  const int N = u.N, npad = u.Npad, B = u.B;
+  const int64_t R = u.ldR;
+  const int it = ch.n_iter;
+  if (it == 0) {
+    for (int j = 0; j < NK; j++) {
+      const double w = ch.ws[j];
+      const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
+      if (lane == 0) ch.lw[j] = lw;
+      if (j < K) {
+        const int64_t rj = (int64_t)ch.a_idx[j] * B + ch.b_idx[j];
+        for (int n = lane; n < N; n += 32) lz[(int64_t)j * npad + n] = lw + (double)A[(int64_t)n * R + rj];
+      } else {
+        const double val = lw + u.unif_loglik;
+        for (int n = lane; n < N; n += 32) lz[(int64_t)j * npad + n] = val;
+      }
+    }
+    __syncwarp();
+  }
+  const int k = ch.k_order[it];
+  const double lwk = ch.lw[k];
+  const int64_t rk = (int64_t)ch.a_idx[k] * B + ch.b_idx[k];
+  bool guard = false;
+  double red[NK + 3];
+  int h_lo, h_hi;
+  while (true) {
+#pragma unroll
+    for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
+    h_lo = N;
+    h_hi = -1;
+    if (PF) {
+      // software pipeline: the next fragment's loads (a strided tensor gather and the stale columns,
+      // DRAM / L2 latency) are in flight while this one is computed -- ncu: 54 % of the stall
+      // samples of the unpipelined loop sit on the first use of those loads
+      FragIn<NK, TT> cur, nxt;
+      int n = lane;
+      if (n < N) estep_load<NK, TT>(cur, n, k, rk, npad, R, A, cnt, lz);
+      while (n < N) {
+        const int nn = n + 32;
+        if (nn < N) estep_load<NK, TT>(nxt, nn, k, rk, npad, R, A, cnt, lz);
+        estep_compute<NK, TT>(cur, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
+        cur = nxt;
+        n = nn;
+      }
+    } else {
+      for (int n = lane; n < N; n += 32) estep_fragment<NK, TT>(n, k, lwk, rk, guard, npad, R, A, cnt, lz, V, red, h_lo, h_hi);
+    }
+#pragma unroll
+    for (int j = 0; j < NK + 3; j++) {
+      double x = red[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      red[j] = x;
+    }
+    if (!guard && red[NK] < 1e-8) {          // mstep guard (:526-529), uniform across the warp
+      guard = true;
+      continue;
+    }
+    break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    h_lo = min(h_lo, __shfl_xor_sync(0xffffffffu, h_lo, o));
+    h_hi = max(h_hi, __shfl_xor_sync(0xffffffffu, h_hi, o));
+  }
+  __syncwarp();
+  if (lane == 0) estep_epilogue<NK>(ch, sd, u, red, k, it, h_lo, h_hi);
+}
+
+// A chain's record (944 bytes over 8 cache lines) is read field by field through several dependent
+// steps of an E pass (state -> window -> k_order -> log w, alpha, beta ...): staged once into shared
+// memory by a coalesced copy, worked on there and copied back, the pass pays one global round trip
+// for it instead of one per step.
+static_assert(sizeof(ChainDev) % 8 == 0, "ChainDev is copied in 8-byte words");
+__device__ __forceinline__ void copy_chain(ChainDev* dst, const ChainDev* src, int t, int nt) {
+  const double* s = reinterpret_cast<const double*>(src);
+  double* d = reinterpret_cast<double*>(dst);
+  for (int i = t; i < (int)(sizeof(ChainDev) / 8); i += nt) d[i] = s[i];
+}
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor-core MMA.  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
+//   A: a0 = A[lane>>2][lane&3]     B: b0 = B[lane&3][lane>>2]     D: d{0,1} = D[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+
+}  // namespace scape

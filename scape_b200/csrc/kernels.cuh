@@ -160,6 +160,35 @@ struct EstepPlan {
   bool warp_prefetch = true;
   int stage_chain = 1;          // E-step kernels work on a shared-memory copy of the chain record
 };
+// ---- cluster-resident EM (em_cluster.cu) -----------------------------------------------------------
+// One thread-block cluster per UTR runs every chain of the UTR through all its EM iterations inside
+// ONE launch: E pass (warp per chain) -> cluster barrier -> grid arg-max on the FP64 tensor cores
+// (32-row tiles x the chains whose window covers the tile) -> cluster barrier -> next iteration.
+// A UTR never waits for another UTR; its tensor, log_zmat and V stay in L2 for the whole run.
+struct ClusterJob {
+  int32_t utr;           // index into the wave's UtrDev array
+  int32_t chain_begin;   // first chain of the UTR in the run's chain array (chains are ordered by UTR)
+  int32_t n_chains;      // <= kScanMaxChains
+  int32_t cpp;           // chains whose V rows fit the kernel's shared-memory budget per pass (1..32)
+};
+constexpr int kClusterTileRows = 32;            // candidate rows per scan task = rows per partial
+constexpr int kClusterVBytes = 96 * 1024;       // dynamic shared memory per CTA: staged V rows (2 CTAs per SM)
+constexpr int kClusterPassMax = 32;             // chains per pass (one ballot)
+// pitch (in doubles) of a staged V row that holds `len` fragments: multiple of 4, = 4 mod 16
+inline __host__ __device__ int cluster_v_pitch(int len) {
+  const int len4 = (len + 3) & ~3;
+  return len4 + ((20 - (len4 & 15)) & 15);
+}
+// chains per pass for a UTR with N fragments, 0 = does not fit (use the bulk-synchronous kernels)
+inline int cluster_chains_per_pass(int N) {
+  const int rows = int(kClusterVBytes / sizeof(double)) / cluster_v_pitch(N + 8) - 1;   // one row of zeros
+  return rows < 1 ? 0 : (rows > kClusterPassMax ? kClusterPassMax : rows);
+}
+cudaError_t launch_em_cluster(const ClusterJob* jobs_dev, int n_jobs, int cluster_size, ChainDev* chains_dev,
+                              ScanDesc* descs_dev, const UtrDev* utrs_dev, const void* tensor, bool f32,
+                              const double* cnt, double* lz, double* vbuf, void* partials, double* scan_elems,
+                              int32_t* trace_a, int32_t* trace_b, double* trace_ws, cudaStream_t st);
+
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
                     bool big_k,
                     const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,

@@ -263,7 +263,9 @@ def test_scheduling_knobs_do_not_change_a_bit():
     # do not write themselves (pitch padding, slack rows the scan's prefetch ring touches) would then
     # poison the grid search -- the digest must not change either.
     for knob in ("", "SCAPE_B200_PREDRAW=0", "SCAPE_B200_OVERLAP=0", "SCAPE_B200_SCAN_SPLIT=0", "SCAPE_B200_WARP_PF=0",
-                 "SCAPE_B200_STAGE_CHAIN=0", "SCAPE_B200_POISON=1"):
+                 "SCAPE_B200_STAGE_CHAIN=0", "SCAPE_B200_POISON=1",
+                 # the EM kernel choice (cluster-resident vs bulk-synchronous step kernels) and the cluster size
+                 "SCAPE_B200_EM=bsp", "SCAPE_B200_CLUSTER=1", "SCAPE_B200_CLUSTER=4", "SCAPE_B200_CLUSTER=8"):
         env = dict(os.environ)
         if knob:
             k, v = knob.split("=")
