@@ -47,10 +47,10 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def scan_traffic():
-    """DRAM bytes per em_scan_kernel launch from the committed ncu capture (profiles/), or None."""
+def scan_traffic(cluster=False):
+    """DRAM bytes per launch of the dominant EM kernel from the committed ncu capture (profiles/), or None."""
     import glob
-    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_scan_traffic.json")))
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_cluster_traffic.json" if cluster else "r*_scan_traffic.json")))
     if not found:
         return None, "no ncu capture committed"
     p = found[-1]                      # the latest capture (names sort by round)
@@ -111,115 +111,131 @@ def cfg3_plan(total, per_file, world):
     return counts, cut, files, shard.lpt_partition(costs, world)
 
 
-def _cpu_fit_one(args):
-    idx, reads = args[0], args[1]
+def workload_label(args, world):
+    """`config.workload` of the benchmark line: the same string for both arms (--impl b200 / reference)."""
+    if args.workload == "cfg2":
+        return (f"cfg-2: synthetic {args.utrs} UTRs x {args.reads} reads per GPU, Kmax={args.kmax}, "
+                f"{(args.utrs + args.per_file - 1) // args.per_file} chunk files = RNG streams (seed 1 each)")
+    if args.workload in ("cfg3", "cfg4"):
+        total = args.utrs if args.utrs != N_UTR else 20000
+        label = (f"cfg-3: synthetic {total} UTRs in total, heavy-tailed reads per UTR (10..200k, median 600), "
+                 f"{(total + args.per_file - 1) // args.per_file} chunk files cost-balanced (LPT) over {world} GPU(s), Kmax={args.kmax}")
+        if args.workload == "cfg4":
+            label = label.replace("cfg-3", "cfg-4 (pre_para fixed mode, K=3, restricted theta grid)")
+        return label
+    return f"cfg-5 point: {min(args.utrs, 256)} UTRs x {args.reads} reads, n_max_apa={args.kmax}, one stream per UTR"
+
+
+# ---- CPU arm: the oracle port on whole chunk-file prefixes under the reference's seed policy ----------
+def _cpu_fit_file(job):
+    """First `m` UTRs of chunk file `f` of the cfg-2 set, np.random.seed(1) once per file, UTRs serial on
+    that stream (apa_core.py:125, 1104-1137).  Returns per-UTR (index, K, alpha, ws, lb_last, n_frag)."""
+    f, m, per_file, reads, kmax = job
     from oracle import scape_oracle as so
     from scape_b200 import synth
-    u = synth.make_utr(idx, reads, long_utr=bool(args[2]) if len(args) > 2 else False)
-    t = time.perf_counter()
-    res = so.fit_utr(u.x, u.l, u.r, u.pa, np.random.RandomState(1))
-    return time.perf_counter() - t, res.n_frag, res.K
+    rng = np.random.RandomState(1)
+    rows = []
+    for j in range(m):
+        u = synth.make_utr(f * per_file + j, reads)
+        res = so.fit_utr(u.x, u.l, u.r, u.pa, rng, n_max_apa=kmax)
+        rows.append((f * per_file + j, int(res.K), [int(a) for a in res.alpha_arr], [float(b) for b in res.beta_arr],
+                     [float(w) for w in res.ws], float(res.lb_arr[-1]), int(res.n_frag)))
+    return rows
 
 
-def cpu_sample(first, count, reads, cores, jobs=None):
-    """Oracle port on `cores` processes over UTRs [first, first+count) of the workload (or the explicit
-    (index, reads, long_utr) job list); wall clock."""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        rows = pool.map(_cpu_fit_one, jobs or [(first + i, reads) for i in range(count)], chunksize=1)
-    wall = time.perf_counter() - t0
-    return count / wall, wall, rows
+class CpuArm:
+    """One persistent process pool (fork, before any CUDA context exists in this process) fitting
+    `m` leading UTRs of `cores` chunk files per step."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        import warnings
+        warnings.simplefilter("ignore")
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores)
+
+    def step(self, first_file, m, args):
+        n_files = (args.utrs + args.per_file - 1) // args.per_file
+        jobs = [((first_file + i) % n_files, m, args.per_file, args.reads, args.kmax) for i in range(self.cores)]
+        t0 = time.perf_counter()
+        rows = self.pool.map(_cpu_fit_file, jobs, chunksize=1)
+        return time.perf_counter() - t0, [r for file_rows in rows for r in file_rows]
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the Python /
+    Taichi reference cannot travel to the GPU box) on all host cores, same workload string."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = cores * 2
+    m = args.ref_utrs_per_file
+    arm = CpuArm(cores)
     for w in range(args.warmup):
-        cpu_sample(N_UTR - per_step, min(per_step, cores), READS, cores)
-    t0 = time.perf_counter()
+        arm.step(w * cores, 1, args)
+    wall = 0.0
     for s in range(args.steps):
-        cpu_sample(s * per_step, per_step, READS, cores)
-    wall = time.perf_counter() - t0
-    v = args.steps * per_step / wall
-    sample = f"{per_step} UTRs/step (UTR indices s*{per_step}..) of the 10000 x 500-read workload, fresh RandomState(1) per UTR"
+        dt, _ = arm.step((args.warmup + s) * cores, m, args)
+        wall += dt
+    arm.close()
+    v = args.steps * cores * m / wall
+    sample = (f"per step: the first {m} UTRs of {cores} chunk files of the workload (distinct files per step), each file on its "
+              f"own process with np.random.seed(1) per file and its UTRs serial on that stream; persistent pool of {cores} processes")
     print(json.dumps({
         "impl": "reference", "metric": "infer_pa_utrs_per_s", "value": v, "unit": "UTR/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg-2: synthetic 10k UTRs x 500 reads, Kmax=5 (bounded sample per step)"},
+        "config": {"workload": workload_label(args, world), "seed_policy": "file"},
         "cpu_baseline": {"value": v, "unit": "UTR/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "UTR/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle/scape_oracle.py (vectorised numpy restatement, bit-identical to the reference's results and "
-                "~6x faster than the reference's own Python loops) because the Python/Taichi reference cannot travel",
+                "~6x faster than the reference's own Python loops) because the Python/Taichi reference cannot travel; "
+                "the CPU arm does not use the GPUs, so its value does not change with --gpus",
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--utrs", type=int, default=N_UTR, help="UTRs per GPU per step (default: the named config)")
-    ap.add_argument("--reads", type=int, default=READS)
-    ap.add_argument("--per-file", type=int, default=PER_FILE)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
-                    help="BASELINE.json configs[1..4]; cfg2 is the benchmark line, the others are reported beside it")
-    ap.add_argument("--kmax", type=int, default=5, help="n_max_apa (cfg5 sweeps it)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    from scape_b200 import _lib, shard, synth
-    scaling = "weak"
-    pre_para = None
-    if args.workload == "cfg2":
-        utrs = synth.make_batch(args.utrs, args.reads, first=rank * args.utrs)
-        label = (f"cfg-2: synthetic {args.utrs} UTRs x {args.reads} reads per GPU, Kmax={args.kmax}, "
-                 f"{(args.utrs + args.per_file - 1) // args.per_file} chunk files = RNG streams (seed 1 each)")
-    elif args.workload in ("cfg3", "cfg4"):
+def make_workload(name, args, rank, world):
+    from scape_b200 import synth
+    a = argparse.Namespace(**vars(args))
+    a.workload = name
+    wl = dict(name=name, scaling="weak", pre_para=None, per_file=args.per_file, kmax=args.kmax)
+    if name == "cfg2":
+        wl["utrs"] = synth.make_batch(args.utrs, args.reads, first=rank * args.utrs)
+    elif name in ("cfg3", "cfg4"):
         # 20k heavy-tailed UTRs in TOTAL (strong scaling): chunk files are bin-packed over the ranks
         # by the a-priori cost model (scape_b200/shard.py), every rank generates and fits only its own
         total = args.utrs if args.utrs != N_UTR else 20000
         counts, cut, files, parts = cfg3_plan(total, args.per_file, world)
-        mine = parts[rank]
-        utrs = [synth.make_utr(i, int(counts[i]), long_utr=bool(counts[i] >= cut)) for f in mine for i in files[f]]
-        scaling = "strong"
-        label = (f"cfg-3: synthetic {total} UTRs in total, heavy-tailed reads per UTR (10..200k, median 600), "
-                 f"{len(files)} chunk files cost-balanced (LPT) over {world} GPU(s), Kmax={args.kmax}")
-        if args.workload == "cfg4":
+        wl["utrs"] = [synth.make_utr(i, int(counts[i]), long_utr=bool(counts[i] >= cut)) for f in parts[rank] for i in files[f]]
+        wl["scaling"] = "strong"
+        if name == "cfg4":
             class _Pre:           # what --pre_para_pkl_file supplies: first Parameters object of the file
                 alpha_arr = np.array([500, 900, 1400]); beta_arr = np.array([20.0, 35.0, 30.0]); K = 3; L = 21000
-            pre_para = _Pre
-            label = label.replace("cfg-3", "cfg-4 (pre_para fixed mode, K=3, restricted theta grid)")
-        args.utrs = len(utrs)
+            wl["pre_para"] = _Pre
     else:
         # cfg-5 point: 256 independent UTRs (one stream each, so all of them are one wave)
-        args.utrs = min(args.utrs, 256)
-        args.per_file = 1
-        utrs = synth.make_batch(args.utrs, args.reads, first=rank * args.utrs)
-        label = f"cfg-5 point: {args.utrs} UTRs x {args.reads} reads, n_max_apa={args.kmax}, one stream per UTR"
+        wl["per_file"] = 1
+        wl["utrs"] = synth.make_batch(min(args.utrs, 256), args.reads, first=rank * min(args.utrs, 256))
+    wl["label"] = workload_label(a, world)
+    return wl
+
+
+def run_workload(wl, args, steps, warmup, rank, local, world, dist, cpu_arm=None):
+    """W warm-up passes, K timed passes (barrier + synchronize on both sides), one extra un-pipelined
+    pass for the per-kernel roofline.  Returns the result dict on rank 0, None elsewhere."""
+    from scape_b200 import _lib
+    utrs = wl["utrs"]
+    n_utr = len(utrs)
     off, x, l, r, pa = pack(utrs)
-    n_files = (args.utrs + args.per_file - 1) // args.per_file
-    sid = (np.arange(args.utrs) // args.per_file).astype(np.int32)
+    n_files = (n_utr + wl["per_file"] - 1) // wl["per_file"]
+    sid = (np.arange(n_utr) // wl["per_file"]).astype(np.int32)
     seeds = np.ones(n_files, np.uint32)
-    eng = _lib.Engine(_lib.make_params(pre_para=pre_para, n_max_apa=args.kmax), device=local)
+    eng = _lib.Engine(_lib.make_params(pre_para=wl["pre_para"], n_max_apa=wl["kmax"]), device=local)
 
     def barrier():
         if dist is not None:
@@ -227,19 +243,17 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         eng.fit(off, x, l, r, pa, sid, seeds)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, em_ms, tim = 0.0, 0.0, None
     acc = {}
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = eng.fit(off, x, l, r, pa, sid, seeds)
-        tim = out.timing
-        for k, v in tim.items():
+        for k, v in out.timing.items():
             acc[k] = acc.get(k, 0.0) + v
     barrier()
     wall = time.perf_counter() - t0
@@ -257,93 +271,153 @@ def main():
     iters = float(out.em_work[:, 1].sum())
     if dist is not None:
         import torch
-        t = torch.tensor([wall, dev_ms, acc["em_ms"]], dtype=torch.float64, device="cuda")
+        t = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall, dev_ms, em_max = t.tolist()
-        s = torch.tensor([work, float(args.utrs)], dtype=torch.float64, device="cuda")
+        wall, dev_ms = t.tolist()
+        s = torch.tensor([work, float(n_utr), acc["launches"], acc["h2d_bytes"], acc["d2h_bytes"], acc["waves"]],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        work_all, utr_all = s.tolist()
+        work_all, utr_all, launches, h2d, d2h, waves = s.tolist()
     else:
-        work_all, utr_all = work, float(args.utrs)
+        work_all, utr_all, launches, h2d, d2h, waves = work, float(n_utr), acc["launches"], acc["h2d_bytes"], acc["d2h_bytes"], acc["waves"]
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        eng.close()
+        return None
 
-    K = args.steps
+    K = steps
     hbm_peak, hbm_src = measured_peaks()
     fp64 = eng.fp64_peaks()                     # measured on this GPU, this run (no FP64 entry in MEASURED_PEAKS.json)
-    cluster = alone.get("cluster_ms", 0.0) > alone["scan_ms"]     # which EM kernel dominates this workload
+    cluster = alone.get("resident_ms", 0.0) > alone["scan_ms"]     # which EM kernel dominates this workload
     if cluster:
-        scan_s = alone["cluster_ms"] / 1e3
-        ach_tflops = alone["cluster_grid_flops"] / scan_s / 1e12
-        dom_launches = max(int(alone["cluster_launches"]), 1)
-        dom_flops = alone["cluster_grid_flops"]
+        dom_s = alone["resident_ms"] / 1e3
+        dom_flops = alone["resident_grid_flops"]
+        dom_launches = max(int(alone["resident_launches"]), 1)
+        kernel = ("em_cluster_kernel (cluster-resident EM: every E pass and every max_alpha_beta grid arg-max -- FP64 MMA "
+                  "tiles -- of a UTR's chains in one launch; only the grid search's algorithmic flops are counted, the E passes' "
+                  "time is inside the denominator)")
     else:
-        scan_s = alone["scan_ms"] / 1e3
-        ach_tflops = alone["em_grid_flops"] / scan_s / 1e12
-        dom_launches = max(int(alone["scan_launches"]), 1)
+        dom_s = alone["scan_ms"] / 1e3
         dom_flops = alone["em_grid_flops"]
-    traffic, traffic_src = scan_traffic()
+        dom_launches = max(int(alone["scan_launches"]), 1)
+        kernel = "em_scan_kernel (max_alpha_beta grid arg-max as a blocked FP64 MMA product)"
+    ach_tflops = dom_flops / dom_s / 1e12
+    traffic, traffic_src = scan_traffic(cluster)
     res = {
         "metric": "infer_pa_utrs_per_s", "value": utr_all * K / (dev_ms / 1e3), "unit": "UTR/s",
-        "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
-        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": label,
+        "n_gpus": world, "steps": K, "warmup": warmup, "ms_per_step": dev_ms / K,
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"],
                    "seed_policy": "file", "tensor_storage": "f32 (FP64 arithmetic)",
-                   "l2": "per-wave tensor working set (~0.26 GB) exceeds the 126 MB L2; nothing is flushed between steps, "
-                         "every step streams 100 waves x 0.26 GB",
+                   "l2": "inputs larger than L2: a wave's marginal tensors (~0.26 GB for 100 cfg-2 UTRs) exceed the 126 MB L2 and every "
+                         "step streams all waves again; nothing is flushed between steps",
                    "value_time": "GPU busy time = union of the CUDA-event kernel intervals (EM stream and the "
-                                 "likelihood stream that works one wave ahead)",
-                   "e2e_time": "wall clock of Engine.fit (C ABI scape_b200_fit_batch) on host buffers"},
+                                 "likelihood stream that works one wave ahead), max over ranks",
+                   "e2e_time": "wall clock of Engine.fit (C ABI scape_b200_fit_batch) on host buffers, max over ranks"},
         "read_comp_em_iter_per_s": work_all * K / (dev_ms / 1e3),
         "read_comp_em_iter_per_s_e2e": work_all * K / wall,
         "em_iterations_per_step": iters,
-        "e2e": {"value": utr_all * K / wall, "unit": "UTR/s", "h2d_bytes_per_step": acc["h2d_bytes"] / K,
-                "d2h_bytes_per_step": acc["d2h_bytes"] / K, "ms_per_step": 1e3 * wall / K},
-        "gpu_launches": int(acc["launches"]),
-        "roofline": {"kernel": ("em_cluster_kernel (cluster-resident EM: E passes + max_alpha_beta grid arg-max as FP64 MMA tiles, "
-                                "all iterations of a UTR in one launch; only the grid search's flops are counted)") if cluster else
-                               "em_scan_kernel (max_alpha_beta grid arg-max as a blocked FP64 MMA product)",
+        "e2e": {"value": utr_all * K / wall, "unit": "UTR/s", "h2d_bytes_per_step": h2d / K,
+                "d2h_bytes_per_step": d2h / K, "ms_per_step": 1e3 * wall / K},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": kernel,
                      "bound": "tensor", "achieved": ach_tflops, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
                      "frac": ach_tflops / fp64["dmma_tflops"], "traffic": traffic, "traffic_source": traffic_src,
-                     "timing": "CUDA events around every scan launch of one extra pass with wave pipelining off "
-                               "(kernel alone on the GPU)",
+                     "timing": "CUDA events around every launch of that kernel in one extra pass with wave pipelining off "
+                               "(kernel alone on the GPU), rank 0",
                      "peak_source": "FP64 mma.m8n8k4 stream measured in this run (scape_b200_fp64_peaks); "
                                     f"CUDA-core DFMA stream {fp64['dfma_tflops']:.1f} TFLOP/s",
                      "algorithmic_flops_per_launch": dom_flops / dom_launches,
-                     "avg_launch_ms": 1e3 * scan_s / dom_launches,
+                     "avg_launch_ms": 1e3 * dom_s / dom_launches,
                      "launches": dom_launches,
-                     "share_of_gpu_time": 1e3 * scan_s / alone["device_busy_ms"],
-                     "hbm_view": {"algorithmic_GBps": alone["em_grid_bytes"] / scan_s / 1e9, "peak_GBps": hbm_peak,
-                                  "peak_source": hbm_src, "loaded_GBps": alone["em_scan_bytes"] / scan_s / 1e9,
-                                  "note": "SURVEY 8d algorithmic bytes = 8*W_k*B*N per chain iteration; the blocked scan "
-                                          "loads each tensor block once per step for all chains of the UTR"}},
-        "phases_ms_per_step": {k: acc[k] / K for k in ("table_ms", "tensor_ms", "em_ms", "cluster_ms", "estep_ms", "scan_ms", "label_ms",
+                     "share_of_gpu_time": 1e3 * dom_s / alone["device_busy_ms"],
+                     "hbm_view": {"algorithmic_GBps": alone["em_grid_bytes"] / max(alone["em_ms"], 1e-9) / 1e6, "peak_GBps": hbm_peak,
+                                  "peak_source": hbm_src, "loaded_GBps": alone["em_scan_bytes"] / max(alone["em_ms"], 1e-9) / 1e6,
+                                  "note": "SURVEY 8d algorithmic bytes = 8*W_k*B*N per chain iteration over the EM time; the kernels "
+                                          "load a tensor tile once for all chains that need it, from L2 where the UTR stays resident"}},
+        "phases_ms_per_step": {k: acc[k] / K for k in ("table_ms", "tensor_ms", "em_ms", "resident_ms", "estep_ms", "scan_ms", "label_ms",
                                                         "host_prep_ms", "host_rng_ms", "device_busy_ms", "total_ms")},
-        "phases_alone_ms": {k: alone[k] for k in ("table_ms", "tensor_ms", "em_ms", "cluster_ms", "estep_ms", "scan_ms", "label_ms",
+        "phases_alone_ms": {k: alone[k] for k in ("table_ms", "tensor_ms", "em_ms", "resident_ms", "estep_ms", "scan_ms", "label_ms",
                                                   "device_busy_ms", "total_ms")},
         "tensor_exp_per_s": alone["tensor_exp"] / (alone["tensor_ms"] / 1e3),
-        "waves_per_step": acc["waves"] / K,
+        "waves_per_step": waves / K,
         "clocks": clocks,
     }
-    if not args.no_cpu:
-        cores = os.cpu_count() or 1
-        n = cores * 2
-        if args.workload == "cfg3":
-            # bounded sample: the first 2*cores UTRs of the set with at most 5000 reads (a 100k-read UTR
-            # alone takes the oracle minutes); it therefore flatters the CPU arm on this workload
-            jobs = [(i, int(c), bool(c >= cut)) for i, c in enumerate(counts) if c <= 5000][:n]
-            v, wall_cpu, rows = cpu_sample(0, n, args.reads, cores, jobs=jobs)
-            sample = f"first {len(jobs)} UTRs with <= 5000 reads of the heavy-tailed set, oracle port, {wall_cpu:.1f} s wall"
-        elif args.workload == "cfg2":
-            v, wall_cpu, rows = cpu_sample(0, n, args.reads, cores)
-            sample = f"first {n} UTRs of the workload, oracle port, {wall_cpu:.1f} s wall"
-        else:
-            v = None
-        if v is not None:
-            res["cpu_baseline"] = {"value": v, "unit": "UTR/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(res))
+    if cpu_arm is not None and wl["name"] == "cfg2":
+        # cpu_baseline leg (rank 0, N = 1): bounded sample = the first m UTRs of `cores` chunk files under
+        # the file seed policy -- the same UTRs, same streams the GPU arm just fitted, so the results are
+        # compared UTR by UTR (the oracle as the checker).
+        m = args.ref_utrs_per_file
+        a = argparse.Namespace(**vars(args)); a.utrs = n_utr; a.per_file = wl["per_file"]; a.kmax = wl["kmax"]
+        wall_cpu, rows = cpu_arm.step(0, m, a)
+        v = len(rows) / wall_cpu
+        same_k = ok = 0
+        for idx, Kc, alpha, beta, ws, lb, nf in rows:
+            if int(out.K[idx]) != Kc:
+                continue
+            same_k += 1
+            lbg = out.lb_arr[idx, out.n_lb[idx] - 1]
+            ok += bool(np.max(np.abs(out.alpha[idx, :Kc] - alpha), initial=0) <= 1 and
+                       np.max(np.abs(out.beta[idx, :Kc] - beta), initial=0) <= 1e-3 and
+                       np.max(np.abs(out.ws[idx, :Kc + 1] - ws)) <= 1e-3 and abs(lbg - lb) <= 1e-6 * abs(lb))
+        res["cpu_baseline"] = {"value": v, "unit": "UTR/s", "cores": cpu_arm.cores, "kind": "port",
+                               "sample": f"first {m} UTRs of {cpu_arm.cores} chunk files of the workload (np.random.seed(1) per "
+                                         f"file, UTRs serial on the stream), oracle port, {wall_cpu:.1f} s wall"}
+        res["parity_check"] = {"utrs": len(rows), "K_identical": same_k, "within_north_star_tolerance": ok,
+                               "against": "cpu_baseline leg (oracle port), same UTRs and RNG streams as the GPU arm"}
+    eng.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--utrs", type=int, default=N_UTR, help="UTRs per GPU per step (default: the named config)")
+    ap.add_argument("--reads", type=int, default=READS)
+    ap.add_argument("--per-file", type=int, default=PER_FILE)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg-3 block reported beside the cfg-2 line")
+    ap.add_argument("--ref-utrs-per-file", type=int, default=3,
+                    help="CPU arm / cpu_baseline leg: leading UTRs of each chunk file fitted per step (bounded sample)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[1..4]; cfg2 is the benchmark line (with a cfg3 block beside it)")
+    ap.add_argument("--kmax", type=int, default=5, help="n_max_apa (cfg5 sweeps it)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the CPU pool is forked before this process touches CUDA
+    cpu_arm = CpuArm(os.cpu_count() or 1) if (rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2") else None
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    res = run_workload(make_workload(args.workload, args, rank, world), args, args.steps, args.warmup, rank, local, world,
+                       dist, cpu_arm)
+    if cpu_arm is not None:
+        cpu_arm.close()
+    if args.workload == "cfg2" and not args.no_cfg3 and args.utrs == N_UTR:
+        # BASELINE.json configs[2] beside the headline: the 20k-UTR heavy-tailed set, strong scaling
+        # (chunk files LPT-packed over the ranks), same timing rules
+        blk = run_workload(make_workload("cfg3", args, rank, world), args, max(args.steps, 3), max(args.warmup, 3), rank,
+                           local, world, dist)
+        if rank == 0:
+            res["cfg3"] = {k: blk[k] for k in ("value", "unit", "ms_per_step", "scaling", "steps", "warmup", "e2e", "gpu_launches",
+                                               "waves_per_step", "read_comp_em_iter_per_s", "phases_ms_per_step",
+                                               "phases_alone_ms", "clocks")}
+            res["cfg3"]["workload"] = blk["config"]["workload"]
+            res["cfg3"]["roofline"] = {k: blk["roofline"][k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac",
+                                                                       "share_of_gpu_time")}
+    if rank == 0:
+        print(json.dumps(res))
     if dist is not None:
         dist.destroy_process_group()
 

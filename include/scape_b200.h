@@ -106,9 +106,9 @@ typedef struct scape_b200_timing {
   double em_scan_bytes;                           /* tensor bytes the grid search actually loads (fragment hull only) */
   double estep_ms, scan_ms;                       /* em_ms split: E-step kernels / arg-max scan kernels */
   int64_t scan_launches;
-  double cluster_ms;                              /* em_ms spent in the cluster-resident EM kernel (E passes + grid search of a whole run) */
-  double cluster_grid_flops;                      /* algorithmic grid-search flops (2 W_k B N per chain iteration) done by that kernel */
-  int64_t cluster_launches;
+  double resident_ms;                             /* em_ms spent in the resident EM kernels (chain-resident tail / cluster-resident): E passes + grid search, many iterations per launch */
+  double resident_grid_flops;                     /* algorithmic grid-search flops (2 W_k B N per chain iteration) done inside those kernels */
+  int64_t resident_launches;
 } scape_b200_timing;
 
 typedef struct scape_b200_handle scape_b200_handle;

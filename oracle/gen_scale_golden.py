@@ -11,7 +11,7 @@ deterministic, the fixture keeps (index, reads, long_utr) per UTR.
 Suites (BASELINE.json configs):
   cfg2     10 chunk files x 100 UTRs x 500 reads, UTR indices 0..999 (the first 10 files of bench.py's
            cfg-2 set), n_max_apa 5
-  cfg3     stratified sample of the 20k heavy-tailed set: 29 UTRs per reads-per-UTR decile + 6 UTRs
+  cfg3     stratified sample of the 20k heavy-tailed set: 30 UTRs per reads-per-UTR decile + 6 UTRs
            with >= 100k reads + 6 more of the long-UTR class (top 1 % by reads), dealt to 12 files
   cfg4     `--pre_para_pkl_file` mode (fixed_run, apa_core.py:883-928): the first 200 UTRs of the
            heavy-tailed set in 4 files; files 0-1 use a fixed 3-site pre_para, files 2-3 the
@@ -60,7 +60,7 @@ def suites():
     pick = []
     for d in range(10):
         dec = np.sort(order[d * 2000:(d + 1) * 2000])
-        pick += [int(i) for i in dec[:29]]
+        pick += [int(i) for i in dec[:30]]
     giants = [int(i) for i in np.sort(np.nonzero(counts >= 100000)[0])[:6]]
     longs = [int(i) for i in np.sort(np.nonzero((counts >= cut) & (counts < 100000))[0])[:6]]
     pick = sorted(set(pick) - set(giants) - set(longs))

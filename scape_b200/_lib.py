@@ -71,7 +71,7 @@ class Timing(C.Structure):
         ("em_grid_bytes", C.c_double), ("em_grid_flops", C.c_double), ("tensor_exp", C.c_double),
         ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("em_scan_bytes", C.c_double),
         ("estep_ms", C.c_double), ("scan_ms", C.c_double), ("scan_launches", C.c_int64),
-        ("cluster_ms", C.c_double), ("cluster_grid_flops", C.c_double), ("cluster_launches", C.c_int64),
+        ("resident_ms", C.c_double), ("resident_grid_flops", C.c_double), ("resident_launches", C.c_int64),
     ]
 
     def as_dict(self):

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cu", "em_cluster.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cu", "em_cluster.cu", "em_tail.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "em_device.cuh", "host_prep.hpp", "np_rng.hpp", "work_pool.hpp")] + \
     [os.path.join(os.path.dirname(HERE), "include", "scape_b200.h")]
 LIB = os.path.join(HERE, "libscape_b200.so")

@@ -123,6 +123,7 @@ struct Lane {
   DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
   DevBuf<ScanRef> d_refs;
   DevBuf<ClusterJob> d_cjobs;
+  DevBuf<long long> d_clstats;
   cudaEvent_t ev_cl[2] = {nullptr, nullptr};   // around the cluster-resident EM launch
   DevBuf<ScanDesc> d_descs;
   DevBuf<int32_t> d_chain_off, d_chain_idx, d_lists, d_counts;
@@ -130,7 +131,8 @@ struct Lane {
   DevBuf<LabelDev> d_jobs;
   PinnedBuf<ChainDev> h_chains, h_refits;
   cudaEvent_t ev[8];
-  EmStepEvents em_events;
+  EmStepEvents em_events, em_events2;   // bulk-synchronous runs: all steps / the head of the tail route
+  PinnedBuf<char> h_runmeta;            // per-run index lists, scan items, cluster jobs (pinned upload staging)
   scape_b200_timing tm;
   std::vector<std::pair<float, float>> busy;   // kernel intervals (ms since the fit's base event)
   std::string err;
@@ -139,10 +141,10 @@ struct Lane {
     d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
     d_table.release(); d_tensor.release(); d_lz.release(); d_v.release(); d_trace_ws.release(); d_utrs.release();
     d_rows.release(); d_trows.release(); d_tiles.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
-    d_refs.release(); d_cjobs.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
+    d_refs.release(); d_cjobs.release(); d_clstats.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_lists.release(); d_counts.release();
     d_counter.release(); d_jobs.release();
-    h_chains.release(); h_refits.release();
+    h_chains.release(); h_refits.release(); h_runmeta.release();
     h_stage[0].release(); h_stage[1].release();
     staged.release();
   }
@@ -376,78 +378,41 @@ int np_argmin(const std::vector<double>& v) {
   return best;
 }
 
-// Upload chains, run them (NROUND bulk-synchronous steps), bring them back.  `utrs_host` is the
-// wave's UtrDev array; chains must be ordered by UTR (they are generated that way).
-int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chains, const std::vector<UtrDev>& utrs_host,
-               bool want_trace = false) {
-  if (n_chains == 0) return 0;
-  struct Span {
-    ChainDev* p; size_t n;
-    size_t size() const { return n; }
-    ChainDev* data() const { return p; }
-    ChainDev& operator[](size_t i) const { return p[i]; }
-    ChainDev* begin() const { return p; }
-    ChainDev* end() const { return p + n; }
-  } chains{chains_p, n_chains};
-  const size_t W = utrs_host.size();
-  int64_t lz = 0, vsz = 0, tr = 0, pb = 0;
-  std::vector<int32_t> chain_off(W + 1, 0);
-  std::vector<char> scans(W, 0);
-  bool any_scan = false;
-  // Which EM kernel a UTR's chains take: the cluster-resident kernel (one cluster per UTR, all
-  // iterations in one launch) when a pass of its V rows fits the kernel's shared memory and its
-  // per-iteration grid search is small enough for one cluster, else the bulk-synchronous step kernels
-  // (whole GPU per step: giant UTRs).  SCAPE_B200_EM=bsp forces the latter for everything.
-  static const bool cluster_on = !(getenv("SCAPE_B200_EM") && strcmp(getenv("SCAPE_B200_EM"), "bsp") == 0);
-  static const double cluster_max_cost = getenv("SCAPE_B200_CLUSTER_COST") ? atof(getenv("SCAPE_B200_CLUSTER_COST")) : 4e8;
-  std::vector<char> in_cluster(W, 0);
-  {
-    std::vector<int32_t> n_scan(W, 0);
-    for (size_t i = 0; i < chains.size(); i++)
-      if (!chains[i].weights_only) n_scan[size_t(chains[i].utr)]++;
-    for (size_t i = 0; i < W && cluster_on; i++) {
-      const UtrDev& u = utrs_host[i];
-      const double cost = double(u.N) * double(u.T) * u.B * n_scan[i];     // fragment x candidate row x chain products per iteration
-      in_cluster[i] = n_scan[i] > 0 && cluster_chains_per_pass(u.N) >= 8 && cost <= cluster_max_cost;
-    }
-  }
-  for (size_t i = 0; i < chains.size(); i++) {
-    ChainDev& c = chains[i];
-    if (i > 0 && c.utr < chains[i - 1].utr) return fail(-5, "internal: chains not ordered by UTR");
-    const UtrDev& u = utrs_host[size_t(c.utr)];
-    const int rows_per_partial = in_cluster[size_t(c.utr)] ? kClusterTileRows : kScanRows;
-    const int64_t n_blk = (int64_t(u.T) * u.B + rows_per_partial - 1) / rows_per_partial;
-    c.lz_off = lz;
-    lz += int64_t(c.K + 1) * u.Npad;
-    c.v_off = vsz;
-    vsz += (int64_t(u.N) + 7) / 8 * 8;
-    c.pb_off = pb;
-    pb += n_blk;
-    c.trace_off = want_trace ? tr : -1;
-    tr += int64_t(SCAPE_B200_NROUND) * (SCAPE_B200_KCAP + 1);
-    c.n_iter = 0;
-    c.grid_rows = 0;
-    c.lb_prev = kSentinel;
-    c.last_a = 0;
-    c.state = 1;
-    c.pending = 0;
-    c.trace_pending = 0;
-    chain_off[size_t(c.utr) + 1]++;
-    if (!c.weights_only) { scans[size_t(c.utr)] = 1; any_scan = true; }
-  }
-  for (size_t i = 0; i < W; i++) {
-    if (scans[i] && chain_off[i + 1] > kScanMaxChains)
-      return fail(-5, "internal: " + std::to_string(chain_off[i + 1]) + " chains of one UTR in one run; the scan lists at most " +
-                          std::to_string(kScanMaxChains));
-    chain_off[i + 1] += chain_off[i];
-  }
+// How the EM chains of a run are executed (SCAPE_B200_EM; measurements in DESIGN.md section 5):
+//   bsp      all 51 steps as bulk-synchronous {E step, scan} launch pairs over all chains of the wave
+//            (batched FP64 MMA scan).  Fastest whenever a wave holds enough chains to fill the GPU
+//            (cfg-2: 100 UTRs = 5,000 chains per wave), and what giant UTRs always take.
+//   tail     the first SCAPE_B200_TAIL_STEP (8) iterations bulk-synchronous, then ONE launch of the
+//            chain-resident kernel (em_tail.cu): every chain still running gets a CTA and iterates to
+//            convergence on its own.  2 launches + 16 instead of 101 per wave: wins on small waves
+//            (few RNG streams per GPU), where the step kernels are latency floors.
+//   cluster  one thread-block cluster per UTR, all iterations in one launch (em_cluster.cu).  Measured
+//            slower than both everywhere (idle warps at the cluster barriers); kept as an experiment.
+//   auto (default)  tail for runs of fewer than SCAPE_B200_TAIL_CHAINS (1500) chains, else bsp
+enum EmRoute : char { kRouteBsp = 0, kRouteCluster = 1, kRouteTail = 2 };
+
+// The chains of a set of UTRs prepared for the bulk-synchronous step kernels: the E-step launch
+// order (few-fragment chains first, sorted by K and N) and the scan's work items.
+struct StepSet {
   std::vector<int32_t> index;
+  int64_t n_small = 0, n_big = 0;
+  std::vector<ScanRef> refs;        // chunked-path items first (n_refs_chunk of them), then tile-path items
+  int64_t n_refs_chunk = 0;
+  bool big_k = false;
+};
+
+template <class Chains>
+int build_step_set(scape_b200_handle* h, const Chains& chains, const std::vector<UtrDev>& utrs_host,
+                   const std::vector<int32_t>& chain_off, const std::vector<char>& scans, const std::vector<char>& route,
+                   char want, StepSet& out) {
+  const size_t W = utrs_host.size();
+  std::vector<int32_t>& index = out.index;
   index.reserve(chains.size());
   static const int warp_max_n = getenv("SCAPE_B200_WARP_MAXN") ? atoi(getenv("SCAPE_B200_WARP_MAXN")) : kWarpEstepMaxN;
-  auto bsp_chain = [&](size_t i) { return !in_cluster[size_t(chains[i].utr)]; };
+  auto mine = [&](size_t i) { return route[size_t(chains[i].utr)] == want; };
   for (size_t i = 0; i < chains.size(); i++)
-    if (bsp_chain(i) && utrs_host[size_t(chains[i].utr)].N <= warp_max_n) index.push_back(int32_t(i));
-  const int64_t n_small = int64_t(index.size());
+    if (mine(i) && utrs_host[size_t(chains[i].utr)].N <= warp_max_n) index.push_back(int32_t(i));
+  out.n_small = int64_t(index.size());
   // same-K chains next to each other: the warps resident on an SM then run the same template
   // instantiation of the E step (instruction-cache locality; 24 % 'no instruction' stalls otherwise);
   // within one K the chains with the longest fragment loop go first (a warp's time is ~ N / 32
@@ -478,57 +443,150 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     });
   }
   for (size_t i = 0; i < chains.size(); i++)
-    if (bsp_chain(i) && utrs_host[size_t(chains[i].utr)].N > warp_max_n) index.push_back(int32_t(i));
-  const int64_t n_big = int64_t(index.size()) - n_small;
+    if (mine(i) && utrs_host[size_t(chains[i].utr)].N > warp_max_n) index.push_back(int32_t(i));
+  out.n_big = int64_t(index.size()) - out.n_small;
+  for (int32_t ci : index) out.big_k = out.big_k || chains[size_t(ci)].K > 7;
   // Scan work items.  A CTA's cost is (fragments of the UTR) x (chains it multiplies); the step ends
   // with the slowest CTA.  UTRs whose single-CTA cost is above half of an even share of the wave's
   // work over the resident CTA slots get their chain sub-batches narrowed (32 -> 16 -> 8 chains) and
   // dealt to separate CTAs (the tensor block is then re-read from L2, which a big UTR can afford).
   // Items are issued most expensive first.
-  std::vector<ScanRef> refs;
-  {
-    static const int split_mode = getenv("SCAPE_B200_SCAN_SPLIT") ? atoi(getenv("SCAPE_B200_SCAN_SPLIT")) : 1;
-    const double slots = 2.0 * h->n_sm;
-    double total = 0;
-    for (size_t i = 0; i < W; i++)
-      if (scans[i] && !in_cluster[i]) {
-        const UtrDev& u = utrs_host[i];
-        const double n_blk = double((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
-        total += n_blk * u.N * double(chain_off[i + 1] - chain_off[i]);
+  std::vector<ScanRef>& refs = out.refs;
+  static const int split_mode = getenv("SCAPE_B200_SCAN_SPLIT") ? atoi(getenv("SCAPE_B200_SCAN_SPLIT")) : 1;
+  const double slots = 2.0 * h->n_sm;
+  double total = 0;
+  for (size_t i = 0; i < W; i++)
+    if (scans[i] && route[i] == want) {
+      const UtrDev& u = utrs_host[i];
+      const double n_blk = double((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
+      total += n_blk * u.N * double(chain_off[i + 1] - chain_off[i]);
+    }
+  const double limit = std::max(0.5 * total / slots, 2048.0);
+  std::vector<double> cost;
+  for (size_t i = 0; i < W; i++)
+    if (scans[i] && route[i] == want) {
+      const UtrDev& u = utrs_host[i];
+      const int32_t n_blk = int32_t((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
+      const int C = chain_off[i + 1] - chain_off[i];
+      int gb = 32, nsb = 1;
+      // tile path when whole V rows of >= 8 chains fit the scan CTA's shared memory (N <= ~1280)
+      static const bool tiles_on = getenv("SCAPE_B200_SCAN_TILES") ? atoi(getenv("SCAPE_B200_SCAN_TILES")) != 0 : false;   // opt-in: measured 16 % slower
+      const int tile_gb = tiles_on ? scan_tile_chains(u.N) : 0;
+      if (tile_gb) gb = tile_gb;
+      if (split_mode && double(u.N) * C > limit) {
+        while (gb > 8 && double(u.N) * std::min(gb, C) > limit) gb /= 2;
+        nsb = (C + gb - 1) / gb;
       }
-    const double limit = std::max(0.5 * total / slots, 2048.0);
-    std::vector<double> cost;
-    for (size_t i = 0; i < W; i++)
-      if (scans[i] && !in_cluster[i]) {
-        const UtrDev& u = utrs_host[i];
-        const int32_t n_blk = int32_t((int64_t(u.T) * u.B + kScanRows - 1) / kScanRows);
-        const int C = chain_off[i + 1] - chain_off[i];
-        int gb = 32, nsb = 1;
-        if (split_mode && double(u.N) * C > limit) {
-          while (gb > 8 && double(u.N) * std::min(gb, C) > limit) gb /= 2;
-          nsb = (C + gb - 1) / gb;
+      for (int32_t b = 0; b < n_blk; b++)
+        for (int sb = 0; sb < nsb; sb++) {
+          refs.push_back(ScanRef{int32_t(i), b, int16_t(sb), int16_t(nsb), int16_t(gb), int16_t(tile_gb ? 1 : 0)});
+          cost.push_back(double(u.N) * std::min(nsb == 1 ? C : gb, C));
         }
-        for (int32_t b = 0; b < n_blk; b++)
-          for (int s = 0; s < nsb; s++) {
-            refs.push_back(ScanRef{int32_t(i), b, int16_t(s), int16_t(nsb), int16_t(gb), 0});
-            cost.push_back(double(u.N) * std::min(nsb == 1 ? C : gb, C));
-          }
-      }
-    if (split_mode) {
-      std::vector<size_t> ord(refs.size());
-      for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
-      std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
-      std::vector<ScanRef> sorted(refs.size());
-      for (size_t i = 0; i < ord.size(); i++) sorted[i] = refs[ord[i]];
-      refs.swap(sorted);
+    }
+  // work items of the chunked path first, then those of the tile path (two kernels), each most expensive first
+  {
+    std::vector<size_t> ord(refs.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+      if (refs[a].pad != refs[b].pad) return refs[a].pad < refs[b].pad;
+      return split_mode ? cost[a] > cost[b] : false;
+    });
+    std::vector<ScanRef> sorted(refs.size());
+    for (size_t i = 0; i < ord.size(); i++) sorted[i] = refs[ord[i]];
+    refs.swap(sorted);
+    out.n_refs_chunk = 0;
+    for (const ScanRef& r : refs) out.n_refs_chunk += r.pad == 0;
+  }
+  return 0;
+}
+
+// Upload chains, run them to convergence, bring them back.  `utrs_host` is the wave's UtrDev array;
+// chains must be ordered by UTR (they are generated that way).
+int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chains, const std::vector<UtrDev>& utrs_host,
+               bool want_trace = false) {
+  if (n_chains == 0) return 0;
+  struct Span {
+    ChainDev* p; size_t n;
+    size_t size() const { return n; }
+    ChainDev* data() const { return p; }
+    ChainDev& operator[](size_t i) const { return p[i]; }
+    ChainDev* begin() const { return p; }
+    ChainDev* end() const { return p + n; }
+  } chains{chains_p, n_chains};
+  const size_t W = utrs_host.size();
+  int64_t lz = 0, vsz = 0, tr = 0, pb = 0;
+  std::vector<int32_t> chain_off(W + 1, 0);
+  std::vector<char> scans(W, 0);
+  bool any_scan = false;
+  static const char* em_env = getenv("SCAPE_B200_EM");
+  static const size_t tail_chains = getenv("SCAPE_B200_TAIL_CHAINS") ? size_t(atol(getenv("SCAPE_B200_TAIL_CHAINS"))) : 1500;
+  const char mode = (!em_env || !strcmp(em_env, "auto")) ? (chains.size() < tail_chains ? kRouteTail : kRouteBsp)
+                    : !strcmp(em_env, "bsp") ? kRouteBsp : !strcmp(em_env, "cluster") ? kRouteCluster : kRouteTail;
+  static const int tail_step = std::max(0, std::min(SCAPE_B200_NROUND, getenv("SCAPE_B200_TAIL_STEP") ? atoi(getenv("SCAPE_B200_TAIL_STEP")) : 8));
+  // per-iteration cost (fragment x candidate row x chain products) above which a UTR stays on the
+  // bulk-synchronous kernels for the whole run: the resident kernels give a UTR / a chain a few SMs,
+  // a giant UTR's grid search needs all of them
+  static const double resident_max_cost = getenv("SCAPE_B200_CLUSTER_COST") ? atof(getenv("SCAPE_B200_CLUSTER_COST")) : 4e8;
+  std::vector<char> route(W, kRouteBsp);
+  {
+    std::vector<int32_t> n_scan(W, 0);
+    for (size_t i = 0; i < chains.size(); i++)
+      if (!chains[i].weights_only) n_scan[size_t(chains[i].utr)]++;
+    for (size_t i = 0; i < W && mode != kRouteBsp; i++) {
+      const UtrDev& u = utrs_host[i];
+      const double cost = double(u.N) * double(u.T) * u.B * n_scan[i];
+      if (n_scan[i] == 0 || cost > resident_max_cost) continue;
+      if (mode == kRouteCluster && cluster_chains_per_pass(u.N) >= 8) route[i] = kRouteCluster;
+      if (mode == kRouteTail && u.N <= 4096) route[i] = kRouteTail;
     }
   }
+  for (size_t i = 0; i < chains.size(); i++) {
+    ChainDev& c = chains[i];
+    if (i > 0 && c.utr < chains[i - 1].utr) return fail(-5, "internal: chains not ordered by UTR");
+    const UtrDev& u = utrs_host[size_t(c.utr)];
+    const int rows_per_partial = route[size_t(c.utr)] == kRouteCluster ? kClusterTileRows : kScanRows;
+    const int64_t n_blk = (int64_t(u.T) * u.B + rows_per_partial - 1) / rows_per_partial;
+    c.lz_off = lz;
+    lz += int64_t(c.K + 1) * u.Npad;
+    c.v_off = vsz;
+    vsz += (int64_t(u.N) + 7) / 8 * 8;
+    c.pb_off = pb;
+    pb += n_blk;
+    c.trace_off = want_trace ? tr : -1;
+    tr += int64_t(SCAPE_B200_NROUND) * (SCAPE_B200_KCAP + 1);
+    c.n_iter = 0;
+    c.grid_rows = 0;
+    c.lb_prev = kSentinel;
+    c.last_a = 0;
+    c.state = 1;
+    c.pending = 0;
+    c.trace_pending = 0;
+    chain_off[size_t(c.utr) + 1]++;
+    if (!c.weights_only) { scans[size_t(c.utr)] = 1; any_scan = true; }
+  }
+  for (size_t i = 0; i < W; i++) {
+    if (scans[i] && chain_off[i + 1] > kScanMaxChains)
+      return fail(-5, "internal: " + std::to_string(chain_off[i + 1]) + " chains of one UTR in one run; the scan lists at most " +
+                          std::to_string(kScanMaxChains));
+    chain_off[i + 1] += chain_off[i];
+  }
+  StepSet full, head;                 // all 51 steps / the first tail_step steps before the chain-resident kernel
+  if (int rc = build_step_set(h, chains, utrs_host, chain_off, scans, route, kRouteBsp, full)) return rc;
+  if (int rc = build_step_set(h, chains, utrs_host, chain_off, scans, route, kRouteTail, head)) return rc;
+  // chains of the tail route in UTR order: neighbours in the launch share a tensor (L2)
+  std::vector<int32_t> tail_list;
+  int tail_max_n = 0;
+  for (size_t i = 0; i < chains.size(); i++)
+    if (route[size_t(chains[i].utr)] == kRouteTail) {
+      tail_list.push_back(int32_t(i));
+      tail_max_n = std::max(tail_max_n, utrs_host[size_t(chains[i].utr)].N);
+    }
   // Cluster jobs, most expensive first (the hardware dispatches clusters in launch order as SMs free up)
   std::vector<ClusterJob> cjobs;
   {
     std::vector<double> ccost;
     for (size_t i = 0; i < W; i++)
-      if (in_cluster[i]) {
+      if (route[i] == kRouteCluster) {
         const UtrDev& u = utrs_host[i];
         // all chains of the UTR (weights-only ones included: the kernel iterates them to convergence in place)
         cjobs.push_back(ClusterJob{int32_t(i), chain_off[i], chain_off[i + 1] - chain_off[i], cluster_chains_per_pass(u.N)});
@@ -541,17 +599,18 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     for (size_t i = 0; i < ord.size(); i++) sorted[i] = cjobs[ord[i]];
     cjobs.swap(sorted);
   }
+  // ---- device buffers + uploads ------------------------------------------------------------------
+  const size_t n_index = full.index.size() + head.index.size() + tail_list.size();
+  const size_t n_refs = full.refs.size() + head.refs.size();
   CU(L.d_cjobs.ensure(cjobs.size() + 1));
-  if (!cjobs.empty())
-    CU(cudaMemcpyAsync(L.d_cjobs.p, cjobs.data(), sizeof(ClusterJob) * cjobs.size(), cudaMemcpyHostToDevice, L.st));
   CU(L.d_lz.ensure(size_t(lz)));
   CU(L.d_v.ensure(size_t(vsz + 8)));
   CU(L.d_chains.ensure(chains.size()));
   CU(L.d_chain_off.ensure(W + 1));
   CU(L.d_descs.ensure(chains.size()));
   CU(cudaMemsetAsync(L.d_descs.p, 0, sizeof(ScanDesc) * chains.size(), L.st));
-  CU(L.d_chain_idx.ensure(index.size()));
-  CU(L.d_refs.ensure(refs.size() + 1));
+  CU(L.d_chain_idx.ensure(n_index + 1));
+  CU(L.d_refs.ensure(n_refs + 1));
   CU(L.d_partials.ensure(size_t(pb) * 2 + 2));
   CU(L.d_counter.ensure(1));
   if (want_trace) {
@@ -559,16 +618,35 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     CU(L.d_trace_b.ensure(size_t(tr)));
     CU(L.d_trace_ws.ensure(size_t(tr)));
   }
-  CU(cudaMemcpyAsync(L.d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, L.st));
-  CU(cudaMemcpyAsync(L.d_chain_off.p, chain_off.data(), sizeof(int32_t) * (W + 1), cudaMemcpyHostToDevice, L.st));
-  CU(cudaMemcpyAsync(L.d_chain_idx.p, index.data(), sizeof(int32_t) * index.size(), cudaMemcpyHostToDevice, L.st));
-  if (!refs.empty())
-    CU(cudaMemcpyAsync(L.d_refs.p, refs.data(), sizeof(ScanRef) * refs.size(), cudaMemcpyHostToDevice, L.st));
+  // the small host arrays go through one pinned blob (pageable sources would make the copies synchronous)
+  int32_t *d_idx_full = L.d_chain_idx.p, *d_idx_head = d_idx_full + full.index.size(),
+          *d_tail = d_idx_head + head.index.size();
+  ScanRef *d_refs_full = L.d_refs.p, *d_refs_head = d_refs_full + full.refs.size();
+  {
+    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t o_idx = 0, o_refs = o_idx + up16(4 * n_index), o_off = o_refs + up16(sizeof(ScanRef) * n_refs),
+                 o_jobs = o_off + up16(4 * (W + 1)), o_end = o_jobs + up16(sizeof(ClusterJob) * cjobs.size());
+    CU(L.h_runmeta.resize(o_end + 16));
+    char* b = L.h_runmeta.p;
+    int32_t* hi = (int32_t*)(b + o_idx);
+    std::copy(full.index.begin(), full.index.end(), hi);
+    std::copy(head.index.begin(), head.index.end(), hi + full.index.size());
+    std::copy(tail_list.begin(), tail_list.end(), hi + full.index.size() + head.index.size());
+    ScanRef* hr = (ScanRef*)(b + o_refs);
+    std::copy(full.refs.begin(), full.refs.end(), hr);
+    std::copy(head.refs.begin(), head.refs.end(), hr + full.refs.size());
+    std::copy(chain_off.begin(), chain_off.end(), (int32_t*)(b + o_off));
+    std::copy(cjobs.begin(), cjobs.end(), (ClusterJob*)(b + o_jobs));
+    CU(cudaMemcpyAsync(L.d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, L.st));
+    CU(cudaMemcpyAsync(L.d_chain_off.p, b + o_off, sizeof(int32_t) * (W + 1), cudaMemcpyHostToDevice, L.st));
+    if (n_index) CU(cudaMemcpyAsync(L.d_chain_idx.p, hi, sizeof(int32_t) * n_index, cudaMemcpyHostToDevice, L.st));
+    if (n_refs) CU(cudaMemcpyAsync(L.d_refs.p, hr, sizeof(ScanRef) * n_refs, cudaMemcpyHostToDevice, L.st));
+    if (!cjobs.empty())
+      CU(cudaMemcpyAsync(L.d_cjobs.p, b + o_jobs, sizeof(ClusterJob) * cjobs.size(), cudaMemcpyHostToDevice, L.st));
+  }
   CU(cudaMemsetAsync(L.d_counter.p, 0, sizeof(double), L.st));
-  L.tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * refs.size() + 4 * (W + 1));
+  L.tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * n_refs + 4 * (W + 1) + 4 * n_index);
   CU(cudaEventRecord(L.ev[4], L.st));
-  bool big_k = false;
-  for (auto& c : chains) big_k = big_k || c.K > 7;
   EstepPlan plan;
   {
     static const bool group_steps = getenv("SCAPE_B200_ESTEP") && atoi(getenv("SCAPE_B200_ESTEP")) != 0;
@@ -587,29 +665,91 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     // depend on the composition of its wave
     plan.g_small = (g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) ? g_env : 4;
   }
+  // The wave scheduler's hook (staging the next wave's likelihood phase on the low-priority stream)
+  // fires at a step of the bulk-synchronous loop of `full`; a run without one releases it before its
+  // resident kernel, so the staged wave's table / tensor kernels fill the SMs as this wave's CTAs retire.
+  const bool have_full = !full.index.empty();
+  bool hook_pending = bool(L.em_events.hook) && !have_full;
+  auto fire_mark = [&]() { if (hook_pending && L.em_events.mark) L.em_events.mark(); };
+  auto fire_hook = [&]() { if (hook_pending) { hook_pending = false; L.em_events.hook(); } };
   int nl = 0;
+  bool resident_timed = false;
+  static const bool cl_dbg = getenv("SCAPE_B200_DBG") != nullptr;
   if (!cjobs.empty()) {
-    // cluster size: as many CTAs per UTR as keep all the wave's clusters resident at once (2 CTAs per SM)
     static const int c_env = getenv("SCAPE_B200_CLUSTER") ? atoi(getenv("SCAPE_B200_CLUSTER")) : 0;
-    int csize = 1;
-    while (csize < 8 && size_t(csize) * 2 * cjobs.size() <= size_t(2 * h->n_sm)) csize *= 2;
+    int csize = 8;
     if (c_env == 1 || c_env == 2 || c_env == 4 || c_env == 8) csize = c_env;
-    // the wave scheduler's hook (next wave's likelihood phase on the low-priority stream) fires at a
-    // step of the bulk-synchronous loop; a wave without one releases it before the cluster launch, so
-    // the staged wave's table / tensor kernels fill the SMs as this wave's clusters retire
-    if (n_small + n_big == 0 && L.em_events.hook) L.em_events.hook();
+    static const int solo_max = getenv("SCAPE_B200_SOLO") ? atoi(getenv("SCAPE_B200_SOLO")) : 8;   // chains left when a cluster splits up
+    fire_mark();
+    if (cl_dbg) CU(L.d_clstats.ensure(cjobs.size() * 10));
     CU(cudaEventRecord(L.ev_cl[0], L.st));
     CU(launch_em_cluster(L.d_cjobs.p, int(cjobs.size()), csize, L.d_chains.p, L.d_descs.p, L.d_utrs.p, L.d_tensor.p,
                          h->tensor_f32, L.d_cnt.p, L.d_lz.p, L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p,
-                         L.d_trace_b.p, L.d_trace_ws.p, L.st));
+                         L.d_trace_b.p, L.d_trace_ws.p, cl_dbg ? L.d_clstats.p : nullptr, solo_max, L.st));
     CU(cudaEventRecord(L.ev_cl[1], L.st));
+    resident_timed = true;
+    if (cl_dbg) {
+      constexpr int NS = 10;
+      std::vector<long long> st(cjobs.size() * NS);
+      CU(cudaMemcpyAsync(st.data(), L.d_clstats.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, L.st));
+      CU(cudaStreamSynchronize(L.st));
+      float cms = 0;
+      CU(cudaEventElapsedTime(&cms, L.ev_cl[0], L.ev_cl[1]));
+      double sum[NS] = {0}, mx[NS] = {0};
+      for (size_t j = 0; j < cjobs.size(); j++)
+        for (int k = 0; k < NS; k++) { sum[k] += double(st[j * NS + k]); mx[k] = std::max(mx[k], double(st[j * NS + k])); }
+      const double n = double(cjobs.size()), us = 1.0 / 1965.0;     // cycles -> us at the B200's 1965 MHz
+      fprintf(stderr, "cluster EM: %zu jobs x %d CTAs, kernel %.0f us | per job mean (max): rounds %.1f (%.0f) total %.0f (%.0f) us; "
+                      "rounds < 12: E %.0f scan %.0f; later: E %.0f (%.0f) scan %.0f (%.0f); wait1 %.0f (%.0f) wait2 %.0f (%.0f) | "
+                      "solo from round %.1f, %.0f us\n",
+              cjobs.size(), csize, cms * 1e3, sum[0] / n, mx[0], sum[1] / n * us, mx[1] * us, sum[8] / n * us, sum[9] / n * us,
+              sum[2] / n * us, mx[2] * us, sum[4] / n * us, mx[4] * us, sum[3] / n * us, mx[3] * us, sum[5] / n * us, mx[5] * us,
+              sum[6] / n, sum[7] / n * us);
+    }
     nl += 1;
+    fire_hook();
   }
-  if (n_small + n_big > 0)
-    nl += launch_em_steps(L.d_chains.p, L.d_descs.p, L.d_chain_idx.p, n_small, n_big, any_scan && !refs.empty(), big_k, L.d_refs.p, int64_t(refs.size()),
-                          L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_lz.p,
-                          L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
-                          L.d_trace_ws.p, L.st, L.em_events, plan);
+  L.em_events2.kinds.clear();
+  if (!tail_list.empty()) {
+    // first tail_step iterations bulk-synchronous (E step + batched scan per iteration, no closing E step) ...
+    if (tail_step > 0 && !head.index.empty()) {
+      L.em_events2.hook = nullptr;
+      nl += launch_em_steps(L.d_chains.p, L.d_descs.p, d_idx_head, head.n_small, head.n_big, any_scan, head.big_k, d_refs_head,
+                            head.n_refs_chunk, int64_t(head.refs.size()) - head.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p,
+                            L.d_lz.p, L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p, L.d_trace_ws.p,
+                            L.st, L.em_events2, plan, tail_step);
+    }
+    // ... then every chain that still runs iterates to convergence in a CTA of its own
+    fire_mark();
+    if (cl_dbg) {
+      CU(L.d_clstats.ensure(16));
+      CU(cudaMemsetAsync(L.d_clstats.p, 0, 8 * 16, L.st));
+    }
+    CU(cudaEventRecord(L.ev_cl[0], L.st));
+    CU(launch_em_tail(L.d_chains.p, L.d_descs.p, d_tail, 0, int(tail_list.size()), tail_max_n, kScanRows, L.d_utrs.p,
+                      L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_lz.p, L.d_partials.p, L.d_trace_a.p, L.d_trace_b.p,
+                      L.d_trace_ws.p, cl_dbg ? (unsigned long long*)L.d_clstats.p : nullptr, L.st));
+    CU(cudaEventRecord(L.ev_cl[1], L.st));
+    if (cl_dbg) {
+      unsigned long long st[6];
+      CU(cudaMemcpyAsync(st, L.d_clstats.p, sizeof(st), cudaMemcpyDeviceToHost, L.st));
+      CU(cudaStreamSynchronize(L.st));
+      float cms = 0;
+      CU(cudaEventElapsedTime(&cms, L.ev_cl[0], L.ev_cl[1]));
+      const double it = std::max(1.0, double(st[0])), us = 1.0 / 1965.0;
+      fprintf(stderr, "tail EM: %zu chains listed, %llu ran %llu iterations, kernel %.0f us | per iteration: total %.1f us = E %.1f + scan %.1f "
+                      "+ apply %.1f (CTA time)\n", tail_list.size(), st[5], st[0], cms * 1e3, double(st[1]) / it * us,
+              double(st[2]) / it * us, double(st[3]) / it * us, double(st[4]) / it * us);
+    }
+    resident_timed = true;
+    nl += 1;
+    fire_hook();
+  }
+  if (have_full)
+    nl += launch_em_steps(L.d_chains.p, L.d_descs.p, d_idx_full, full.n_small, full.n_big, any_scan, full.big_k, d_refs_full,
+                          full.n_refs_chunk, int64_t(full.refs.size()) - full.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p,
+                          L.d_lz.p, L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p, L.d_trace_ws.p, L.st,
+                          L.em_events, plan, SCAPE_B200_NROUND + 1);
   else
     L.em_events.kinds.clear();
   CU(cudaGetLastError());
@@ -624,19 +764,19 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   CU(cudaEventElapsedTime(&t0, h->base_ev, L.ev[4]));
   L.tm.em_ms += ms;
   L.busy.emplace_back(t0, t0 + ms);
-  double e_ms = 0, s_ms = 0;
-  em_steps_elapsed(L.em_events, &e_ms, &s_ms);
-  if (!cjobs.empty()) {
+  for (const EmStepEvents* ee : {&L.em_events, &L.em_events2}) {
+    double e_ms = 0, s_ms = 0;
+    em_steps_elapsed(*ee, &e_ms, &s_ms);
+    L.tm.estep_ms += e_ms;
+    L.tm.scan_ms += s_ms;
+    L.tm.scan_launches += ee->kinds.empty() ? 0 : ee->scan_launches;
+  }
+  if (resident_timed) {
     float cms = 0;
     CU(cudaEventElapsedTime(&cms, L.ev_cl[0], L.ev_cl[1]));
-    L.tm.cluster_ms += cms;
-    L.tm.cluster_launches += 1;
-    for (auto& c : chains)
-      if (in_cluster[size_t(c.utr)]) L.tm.cluster_grid_flops += c.grid_rows * double(utrs_host[size_t(c.utr)].N) * 2.0;
+    L.tm.resident_ms += cms;
+    L.tm.resident_launches += 1;
   }
-  L.tm.estep_ms += e_ms;
-  L.tm.scan_ms += s_ms;
-  L.tm.scan_launches += L.em_events.scan_launches;
   L.tm.launches += nl;
   for (auto& c : chains)
     if (c.error) return fail(-7, "non-finite grid-search scores (a NaN reached max_alpha_beta)");
@@ -644,8 +784,9 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     const UtrDev& u = utrs_host[size_t(c.utr)];
     L.tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;     // FP64 tensor, one chain at a time
     L.tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
+    if (route[size_t(c.utr)] != kRouteBsp) L.tm.resident_grid_flops += (c.grid_rows - c.grid_rows_head) * double(u.N) * 2.0;
   }
-  L.tm.em_scan_bytes += scan_elems * (h->tensor_f32 ? 4.0 : 8.0);   // what the blocked scan really loads
+  L.tm.em_scan_bytes += scan_elems * (h->tensor_f32 ? 4.0 : 8.0);   // what the batched scans really load
   return 0;
 }
 
@@ -935,9 +1076,11 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       if (n_chains == 0) break;
       if (overlap && !next_staged) {
         L.em_events.hook_step = std::min(L.stage_step, SCAPE_B200_NROUND - 1);
-        L.em_events.hook = [&]() {
+        L.em_events.mark = [&]() {
           cudaEventRecord(L.ev_mid, L.st);
           cudaStreamWaitEvent(L.st_lik, L.ev_mid, 0);
+        };
+        L.em_events.hook = [&]() {
           stage_rc = stage();
           next_staged = true;
         };
@@ -945,6 +1088,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       {
         const int rc = run_chains(h, L, chains, n_chains, ud);
         L.em_events.hook = nullptr;
+        L.em_events.mark = nullptr;
         if (rc) return rc;
         if (stage_rc) return stage_rc;
       }
@@ -1266,7 +1410,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
     h->tm.em_grid_bytes += t.em_grid_bytes; h->tm.em_grid_flops += t.em_grid_flops; h->tm.tensor_exp += t.tensor_exp;
     h->tm.h2d_bytes += t.h2d_bytes; h->tm.d2h_bytes += t.d2h_bytes; h->tm.em_scan_bytes += t.em_scan_bytes;
     h->tm.estep_ms += t.estep_ms; h->tm.scan_ms += t.scan_ms; h->tm.scan_launches += t.scan_launches;
-    h->tm.cluster_ms += t.cluster_ms; h->tm.cluster_launches += t.cluster_launches; h->tm.cluster_grid_flops += t.cluster_grid_flops;
+    h->tm.resident_ms += t.resident_ms; h->tm.resident_launches += t.resident_launches; h->tm.resident_grid_flops += t.resident_grid_flops;
     iv.insert(iv.end(), h->lanes[l].busy.begin(), h->lanes[l].busy.end());
   }
   std::sort(iv.begin(), iv.end());

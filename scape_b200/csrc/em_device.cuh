@@ -80,6 +80,38 @@ __device__ __forceinline__ void finalize_chain(ChainDev& ch, int N) {
   ch.state = 0;
 }
 
+// Executed by ONE thread: take over the arg-max (`row`, when the chain was waiting for one), write the
+// trace, finalise a converged chain.  Returns 1 if the chain still has an E pass to do.
+__device__ __forceinline__ int apply_row(ChainDev& ch, ScanDesc& sd, const UtrDev& u, bool have_row, int row,
+                                         int32_t* trace_a, int32_t* trace_b, double* trace_ws) {
+  int go = 1;
+  if (have_row) {
+    if (row < ch.row0 || row >= ch.row1) {
+      // no candidate of the window won a `>` comparison: every score was NaN.  Fail the chain (the
+      // host turns this into an error) instead of indexing the tensor with a row that is not one.
+      ch.error = 1;
+      ch.state = 0;
+      ch.bic = CUDART_NAN;
+      go = 0;
+    } else {
+      ch.a_idx[ch.cur_k] = row / u.B;
+      ch.b_idx[ch.cur_k] = row % u.B;
+    }
+    ch.pending = 0;
+    sd.pending = 0;
+    if (ch.trace_off >= 0) ch.trace_pending = ch.n_iter;
+  }
+  if (ch.trace_off >= 0 && ch.trace_pending > 0) {
+    const int64_t o = ch.trace_off + (int64_t)(ch.trace_pending - 1) * (SCAPE_B200_KCAP + 1);
+    for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
+    for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
+    ch.trace_pending = 0;
+  }
+  if (ch.state == 2) { finalize_chain(ch, u.N); go = 0; }
+  if (ch.n_iter >= SCAPE_B200_NROUND || ch.error) go = 0;
+  return go;
+}
+
 // (0) of a step, executed by one full warp: apply the arg-max the previous scan found for this chain
 // (first maximum in row order over the per-block partials), write the trace, finalise converged
 // chains.  Returns 1 (in every lane) if the chain still has an E step to do.
@@ -88,11 +120,11 @@ __device__ __forceinline__ int apply_pending(ChainDev& ch, ScanDesc& sd, const U
                                              const ScanPartial* __restrict__ partials, int32_t* trace_a,
                                              int32_t* trace_b, double* trace_ws) {
   const int lane = threadIdx.x & 31;
-  int go = 1;
-  if (ch.pending) {
+  int row = 0x7fffffff;
+  const bool pending = ch.pending != 0;                  // read before lane 0 clears it
+  if (pending) {
     const int b0 = ch.row0 / PROWS, b1 = (ch.row1 - 1) / PROWS;     // PROWS = candidate rows per partial
     double best = -CUDART_INF;
-    int row = 0x7fffffff;
     for (int b = b0 + lane; b <= b1; b += 32) {
       // L2 load: in the cluster kernel the partials were written by other SMs a cluster barrier ago
       const double2 raw = __ldcg(reinterpret_cast<const double2*>(partials + ch.pb_off + b));
@@ -107,34 +139,10 @@ __device__ __forceinline__ int apply_pending(ChainDev& ch, ScanDesc& sd, const U
       const int orow = __shfl_xor_sync(0xffffffffu, row, o);
       if (ob > best || (ob == best && orow < row)) { best = ob; row = orow; }
     }
-    if (lane == 0) {
-      if (row < ch.row0 || row >= ch.row1) {
-        // no candidate of the window won a `>` comparison: every score was NaN.  Fail the chain (the
-        // host turns this into an error) instead of indexing the tensor with a row that is not one.
-        ch.error = 1;
-        ch.state = 0;
-        ch.bic = CUDART_NAN;
-        go = 0;
-      } else {
-        ch.a_idx[ch.cur_k] = row / u.B;
-        ch.b_idx[ch.cur_k] = row % u.B;
-      }
-      ch.pending = 0;
-      sd.pending = 0;
-      if (ch.trace_off >= 0) ch.trace_pending = ch.n_iter;
-    }
   }
   __syncwarp();
-  if (lane == 0) {
-    if (ch.trace_off >= 0 && ch.trace_pending > 0) {
-      const int64_t o = ch.trace_off + (int64_t)(ch.trace_pending - 1) * (SCAPE_B200_KCAP + 1);
-      for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
-      for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
-      ch.trace_pending = 0;
-    }
-    if (ch.state == 2) { finalize_chain(ch, u.N); go = 0; }
-    if (ch.n_iter >= SCAPE_B200_NROUND || ch.error) go = 0;
-  }
+  int go = 1;
+  if (lane == 0) go = apply_row(ch, sd, u, pending, row, trace_a, trace_b, trace_ws);
   __syncwarp();
   return __shfl_sync(0xffffffffu, go, 0);
 }
@@ -370,6 +378,105 @@ __device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, cons
   if (lane == 0) estep_epilogue<NK>(ch, sd, u, red, k, it, h_lo, h_hi);
 }
 
+// ---- G warps per chain: named-barrier groups (used by em_estep_group_kernel and the cluster kernel) ----
+struct EGroupShared {
+  double red[GW][SCAPE_B200_KCAP + 4];
+  double tot[SCAPE_B200_KCAP + 4];
+  double lwk;
+  long long rk;
+  int k, go, hull[2];
+};
+
+__device__ __forceinline__ void group_sync(int gid, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(nthreads) : "memory");
+}
+
+template <int NV>
+__device__ __forceinline__ void group_reduce_sum(double (&val)[NV], EGroupShared& sh, int G, int gid, int tig) {
+  const int lane = tig & 31, wig = tig >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    double x = val[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh.red[wig][i] = x;
+  }
+  group_sync(gid, 32 * G);
+  if (tig < NV) {
+    double acc = 0.0;
+    for (int w = 0; w < G; w++) acc += sh.red[w][tig];
+    sh.tot[tig] = acc;
+  }
+  group_sync(gid, 32 * G);
+}
+
+template <int NK, typename TT>
+__device__ __noinline__ void estep_group_run(EGroupShared& sh, int G, int gid, int tig, ChainDev& ch, ScanDesc& sd, const UtrDev& u,
+                                const TT* __restrict__ A, const double* __restrict__ cnt, double* __restrict__ lz,
+                                double* __restrict__ V) {
+  constexpr int K = NK - 1;
+  const int gthreads = 32 * G;
+  const int N = u.N, npad = u.Npad, B = u.B;
+  const int64_t R = u.ldR;
+  const int it = ch.n_iter;
+  if (it == 0) {
+    // initial log_zmat: all K+1 columns (em_algo :722-724)
+    for (int j = 0; j < NK; j++) {
+      const double w = ch.ws[j];
+      const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
+      if (tig == 0) ch.lw[j] = lw;
+      if (j < K) {
+        const int64_t rj = (int64_t)ch.a_idx[j] * B + ch.b_idx[j];
+        for (int n = tig; n < N; n += gthreads) lz[(int64_t)j * npad + n] = lw + (double)A[(int64_t)n * R + rj];
+      } else {
+        const double val = lw + u.unif_loglik;
+        for (int n = tig; n < N; n += gthreads) lz[(int64_t)j * npad + n] = val;
+      }
+    }
+  }
+  if (tig == 0) {
+    const int k = ch.k_order[it];
+    sh.k = k;
+    sh.lwk = ch.lw[k];
+    sh.rk = (long long)ch.a_idx[k] * B + ch.b_idx[k];
+  }
+  group_sync(gid, gthreads);
+  const int k = sh.k;
+  const double lwk = sh.lwk;
+  const int64_t rk = sh.rk;
+  bool guard = false;
+  double red[NK + 3];
+  while (true) {
+#pragma unroll
+    for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
+    int h_lo = N, h_hi = -1;
+    if (tig == 0) { sh.hull[0] = N; sh.hull[1] = -1; }
+    {
+      // software pipeline: the next fragment's loads are in flight while this one is computed
+      FragIn<NK, TT> cur, nxt;
+      int n = tig;
+      if (n < N) estep_load<NK, TT>(cur, n, k, rk, npad, R, A, cnt, lz);
+      while (n < N) {
+        const int nn = n + gthreads;
+        if (nn < N) estep_load<NK, TT>(nxt, nn, k, rk, npad, R, A, cnt, lz);
+        estep_compute<NK, TT>(cur, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
+        cur = nxt;
+        n = nn;
+      }
+    }
+    group_sync(gid, gthreads);
+    if (h_hi >= 0) { atomicMin(&sh.hull[0], h_lo); atomicMax(&sh.hull[1], h_hi); }
+    group_reduce_sum<NK + 3>(red, sh, G, gid, tig);
+    if (!guard && sh.tot[NK] < 1e-8) {       // mstep guard (:526-529); uniform across the group
+      guard = true;
+      group_sync(gid, gthreads);
+      continue;
+    }
+    break;
+  }
+  if (tig == 0) estep_epilogue<NK>(ch, sd, u, sh.tot, k, it, sh.hull[0], sh.hull[1]);
+}
+
 // A chain's record (944 bytes over 8 cache lines) is read field by field through several dependent
 // steps of an E pass (state -> window -> k_order -> log w, alpha, beta ...): staged once into shared
 // memory by a coalesced copy, worked on there and copied back, the pass pays one global round trip
@@ -387,6 +494,179 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
+}
+
+
+// ---- grid arg-max as 32-row FP64 MMA tiles (used by em_scan_kernel's tile path and the cluster kernel) ----
+// The chains of a pass: <= 32 chains of one UTR whose V rows (fragments [NA, NB), pitch P doubles, plus
+// one row of zeros at index `cnt`) sit in shared memory.
+struct PassCtx {
+  int row0[kClusterPassMax], row1[kClusterPassMax], hlo[kClusterPassMax], hhi[kClusterPassMax];
+  long long voff[kClusterPassMax], pboff[kClusterPassMax];
+  int NA, NB, P;
+};
+
+// scores of one 32-row tile against the nt <= 8 NG chains of the pass that cover it (bit `s` of `mask`:
+// chain slot s of the pass), fragments [h0, h1), h0 % 4 == 0.
+// 4 consecutive candidate rows of one fragment as one 128-bit load (float storage) or two (double):
+// row groups start at multiples of 4 and the tensor pitch is a multiple of 4 elements.
+template <typename TT> struct ARow4;
+template <> struct ARow4<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ double get(int i) const { return (double)(i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w); }
+};
+template <> struct ARow4<double> {
+  double2 a, b;
+  __device__ __forceinline__ void load(const double* p) {
+    a = __ldg(reinterpret_cast<const double2*>(p));
+    b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  }
+  __device__ __forceinline__ double get(int i) const { return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? b.x : b.y; }
+};
+
+// scores of one 32-row tile against the nt <= 8 NG chains of the pass that cover it (bit `s` of `mask`:
+// chain slot s of the pass), fragments [h0, h1), h0 % 4 == 0.
+//
+// MMA rows are dealt to candidate rows as row(mi, g) = base + 4 g + mi: the four A operands a lane needs
+// for one k-step (mi = 0..3, fragment k0 + q) are then 16 contiguous bytes of the [fragment][row]
+// tensor -- ONE 128-bit load per lane and k-step instead of four 32-bit ones, and the 8 lanes of a
+// quad column read one whole 128-byte line.  The loads are the scan's bottleneck (the tensor streams
+// from HBM / L2 with no reuse inside a warp): fewer, wider loads leave room for a deeper ring.
+template <int NG, typename TT, bool TO_SMEM>
+__device__ __forceinline__ void scan_tile_mma(const PassCtx& sh, const UtrDev& u, const TT* __restrict__ A,
+                                              const double* Vs, ScanPartial* partials, int t, int cntp,
+                                              unsigned mask, int nt, int h0, int h1, double* wbest, int* wrow) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;          // MMA group id / thread-in-group
+  const int64_t R = u.ldR;
+  const int Rv = u.T * u.B;
+  const int base = t * kClusterTileRows;
+  const int tile_end = min(base + kClusterTileRows, Rv);
+  const int NA = sh.NA, P = sh.P;
+  // B operand of this lane: V[chain slot of column 8 ni + g][fragment k0 + q]; columns past nt read the zero row
+  const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+  uint32_t vb[NG];
+#pragma unroll
+  for (int ni = 0; ni < NG; ni++) {
+    const int idx = 8 * ni + g;
+    const int slot = idx < nt ? (int)__fns(mask, 0, idx + 1) : cntp;
+    vb[ni] = vs_base + (uint32_t)(slot * P + (h0 - NA) + q) * 8u;
+  }
+  double acc[4][NG][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NG; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  const int len4 = (h1 - h0 + 3) & ~3;
+  // Register ring, refilled unconditionally with pointer increments (see scan_subbatch in kernels.cu):
+  // reads run up to 4 PFD + 3 fragments past h1, into the next UTR's tensor or the zeroed slack rows
+  // (all finite), against V = 0.  Row groups past the grid end are clamped to the last group of the
+  // pitch (masked below).
+  constexpr int PFD = (NG == 1 ? 14 : NG == 2 ? 12 : NG == 3 ? 8 : 6) / (sizeof(TT) == 8 ? 2 : 1);
+  static_assert(4 * PFD + 3 < kTensorSlackRows, "the ring may read at most kTensorSlackRows fragments past a UTR");
+  const int64_t kstep = 4 * R;
+  const TT* pp = A + min((int64_t)base + 4 * g, R - 4) + (int64_t)(h0 + q) * R;
+  ARow4<TT> pre[PFD];
+#pragma unroll
+  for (int p = 0; p < PFD; p++) {
+    pre[p].load(pp);
+    pp += kstep;
+  }
+  int kk = 0;
+  for (; kk + 4 * PFD <= len4; kk += 4 * PFD) {
+#pragma unroll
+    for (int p = 0; p < PFD; p++) {
+      double a[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) a[mi] = pre[p].get(mi);
+      pre[p].load(pp);
+      pp += kstep;
+      double b[NG];
+#pragma unroll
+      for (int ni = 0; ni < NG; ni++) b[ni] = lds_f64(vb[ni] + (uint32_t)(kk + 4 * p) * 8u);
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PFD; p++) {                          // remainder: the ring already holds it
+    if (kk + 4 * p < len4) {
+      double b[NG];
+#pragma unroll
+      for (int ni = 0; ni < NG; ni++) b[ni] = lds_f64(vb[ni] + (uint32_t)(kk + 4 * p) * 8u);
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], pre[p].get(mi), b[ni]);
+    }
+  }
+  // first maximum of the tile per chain: larger score wins, ties go to the smaller row.
+  // acc[mi][ni][i] = score[row = base + 4 g + mi][column 8 ni + 2 q + i]
+#pragma unroll
+  for (int ni = 0; ni < NG; ni++) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int c = 8 * ni + 2 * q + i;
+      const bool live = c < nt;
+      const int slot = live ? (int)__fns(mask, 0, c + 1) : 0;
+      const int w0 = live ? sh.row0[slot] : 0, w1 = live ? min(sh.row1[slot], tile_end) : 0;
+      double b = -CUDART_INF;
+      int r = 0x7fffffff;
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) {
+        const int row = base + 4 * g + mi;
+        if (row >= w0 && row < w1 && acc[mi][ni][i] > b) { b = acc[mi][ni][i]; r = row; }   // rows ascend with mi
+      }
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {         // lanes with the same q hold the same column
+        const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+        const int orow = __shfl_xor_sync(0xffffffffu, r, o);
+        if (ob > b || (ob == b && orow < r)) { b = ob; r = orow; }
+      }
+      if (live && g == 0) {
+        if (TO_SMEM) {                                   // the caller combines the tiles of its row block
+          wbest[slot] = b;
+          wrow[slot] = r;
+        } else {
+          ScanPartial p;
+          p.score = b; p.row = r; p.pad = 0;
+          partials[sh.pboff[slot] + t] = p;
+        }
+      }
+    }
+  }
+}
+
+template <typename TT, bool TO_SMEM>
+__device__ __forceinline__ void scan_tile(const PassCtx& sh, const UtrDev& u, const TT* __restrict__ A,
+                                          const double* Vs, ScanPartial* partials, int t, int cntp,
+                                          double* scan_elems, double* wbest, int* wrow) {
+  const int lane = threadIdx.x & 31;
+  const int base = t * kClusterTileRows;
+  const int tile_end = min(base + kClusterTileRows, u.T * u.B);
+  const bool cover = lane < cntp && sh.row0[lane] < tile_end && sh.row1[lane] > base;
+  const unsigned mask = __ballot_sync(0xffffffffu, cover);
+  const int nt = __popc(mask);
+  if (nt == 0) return;
+  int h0 = 1 << 30, h1 = 0;
+  if (cover && sh.hhi[lane] >= 0) { h0 = sh.hlo[lane]; h1 = sh.hhi[lane] + 1; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    h0 = min(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+    h1 = max(h1, __shfl_xor_sync(0xffffffffu, h1, o));
+  }
+  if (h1 <= h0) { h0 = 0; h1 = 0; }              // every v is zero: all scores 0, the first row of each window wins
+  h0 &= ~3;
+  if (scan_elems && lane == 0) atomicAdd(scan_elems, (double)(tile_end - base) * (double)(h1 - h0));
+  const int NG = (nt + 7) >> 3;
+  if (NG == 1) scan_tile_mma<1, TT, TO_SMEM>(sh, u, A, Vs, partials, t, cntp, mask, nt, h0, h1, wbest, wrow);
+  else if (NG == 2) scan_tile_mma<2, TT, TO_SMEM>(sh, u, A, Vs, partials, t, cntp, mask, nt, h0, h1, wbest, wrow);
+  else if (NG == 3) scan_tile_mma<3, TT, TO_SMEM>(sh, u, A, Vs, partials, t, cntp, mask, nt, h0, h1, wbest, wrow);
+  else scan_tile_mma<4, TT, TO_SMEM>(sh, u, A, Vs, partials, t, cntp, mask, nt, h0, h1, wbest, wrow);
 }
 
 

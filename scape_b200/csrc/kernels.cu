@@ -11,9 +11,11 @@
 namespace scape {
 
 cudaError_t upload_model_const_cluster(const ModelConst& mc);   // em_cluster.cu's copy
+cudaError_t upload_model_const_tail(const ModelConst& mc);      // em_tail.cu's copy
 cudaError_t upload_model_const(const ModelConst& mc) {
   cudaError_t e = upload_model_const_tu(mc);
-  return e == cudaSuccess ? upload_model_const_cluster(mc) : e;
+  if (e == cudaSuccess) e = upload_model_const_cluster(mc);
+  return e == cudaSuccess ? upload_model_const_tail(mc) : e;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -582,104 +584,7 @@ em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restric
 //     launch work for the few running chains only (an all-chains grid costs ~18 us of empty CTAs).
 // Groups synchronise with named barriers (bar.sync id, 32 G); __syncthreads() is never used here.
 // ------------------------------------------------------------------------------------------------
-struct EGroupShared {
-  double red[GW][SCAPE_B200_KCAP + 4];
-  double tot[SCAPE_B200_KCAP + 4];
-  double lwk;
-  long long rk;
-  int k, go, hull[2];
-};
-
-__device__ __forceinline__ void group_sync(int gid, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(nthreads) : "memory");
-}
-
-template <int NV>
-__device__ __forceinline__ void group_reduce_sum(double (&val)[NV], EGroupShared& sh, int G, int gid, int tig) {
-  const int lane = tig & 31, wig = tig >> 5;
-#pragma unroll
-  for (int i = 0; i < NV; i++) {
-    double x = val[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) sh.red[wig][i] = x;
-  }
-  group_sync(gid, 32 * G);
-  if (tig < NV) {
-    double acc = 0.0;
-    for (int w = 0; w < G; w++) acc += sh.red[w][tig];
-    sh.tot[tig] = acc;
-  }
-  group_sync(gid, 32 * G);
-}
-
-template <int NK, typename TT>
-__device__ __noinline__ void estep_group_run(EGroupShared& sh, int G, int gid, int tig, ChainDev& ch, ScanDesc& sd, const UtrDev& u,
-                                const TT* __restrict__ A, const double* __restrict__ cnt, double* __restrict__ lz,
-                                double* __restrict__ V) {
-  constexpr int K = NK - 1;
-  const int gthreads = 32 * G;
-  const int N = u.N, npad = u.Npad, B = u.B;
-  const int64_t R = u.ldR;
-  const int it = ch.n_iter;
-  if (it == 0) {
-    // initial log_zmat: all K+1 columns (em_algo :722-724)
-    for (int j = 0; j < NK; j++) {
-      const double w = ch.ws[j];
-      const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
-      if (tig == 0) ch.lw[j] = lw;
-      if (j < K) {
-        const int64_t rj = (int64_t)ch.a_idx[j] * B + ch.b_idx[j];
-        for (int n = tig; n < N; n += gthreads) lz[(int64_t)j * npad + n] = lw + (double)A[(int64_t)n * R + rj];
-      } else {
-        const double val = lw + u.unif_loglik;
-        for (int n = tig; n < N; n += gthreads) lz[(int64_t)j * npad + n] = val;
-      }
-    }
-  }
-  if (tig == 0) {
-    const int k = ch.k_order[it];
-    sh.k = k;
-    sh.lwk = ch.lw[k];
-    sh.rk = (long long)ch.a_idx[k] * B + ch.b_idx[k];
-  }
-  group_sync(gid, gthreads);
-  const int k = sh.k;
-  const double lwk = sh.lwk;
-  const int64_t rk = sh.rk;
-  bool guard = false;
-  double red[NK + 3];
-  while (true) {
-#pragma unroll
-    for (int j = 0; j < NK + 3; j++) red[j] = 0.0;
-    int h_lo = N, h_hi = -1;
-    if (tig == 0) { sh.hull[0] = N; sh.hull[1] = -1; }
-    {
-      // software pipeline: the next fragment's loads are in flight while this one is computed
-      FragIn<NK, TT> cur, nxt;
-      int n = tig;
-      if (n < N) estep_load<NK, TT>(cur, n, k, rk, npad, R, A, cnt, lz);
-      while (n < N) {
-        const int nn = n + gthreads;
-        if (nn < N) estep_load<NK, TT>(nxt, nn, k, rk, npad, R, A, cnt, lz);
-        estep_compute<NK, TT>(cur, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
-        cur = nxt;
-        n = nn;
-      }
-    }
-    group_sync(gid, gthreads);
-    if (h_hi >= 0) { atomicMin(&sh.hull[0], h_lo); atomicMax(&sh.hull[1], h_hi); }
-    group_reduce_sum<NK + 3>(red, sh, G, gid, tig);
-    if (!guard && sh.tot[NK] < 1e-8) {       // mstep guard (:526-529); uniform across the group
-      guard = true;
-      group_sync(gid, gthreads);
-      continue;
-    }
-    break;
-  }
-  if (tig == 0) estep_epilogue<NK>(ch, sd, u, sh.tot, k, it, sh.hull[0], sh.hull[1]);
-}
-
+// (EGroupShared, group_sync, group_reduce_sum and estep_group_run live in em_device.cuh)
 // list_in / n_in: the chains to step (n_host >= 0: the host knows the count, else *n_in);
 // list_out / n_out: the chains that still run after this step, appended here.
 template <typename TT>
@@ -757,6 +662,7 @@ struct ScanShared {
   int wrow[GW][SCAN_GB];
   int w0[SCAN_GB], w1[SCAN_GB];  // candidate windows of the sub-batch's chains
   long long voff[SCAN_GB], pboff[SCAN_GB];
+  PassCtx px;                    // tile path: the sub-batch's chains (windows, hulls, staged V rows)
 };
 
 // One sub-batch of up to 8*NG chains against this CTA's 256 candidate rows:
@@ -920,8 +826,70 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __
   }
 }
 
-// one CTA per (UTR, block of SCAN_ROWS candidate rows)
+// Tile path of a sub-batch (UTRs whose whole V rows fit the CTA's shared memory): the 8 warps take the
+// 8 32-row tiles of the block, and every warp multiplies only the chains of the sub-batch whose window
+// covers ITS tile, over the hull of THOSE chains (scan_tile, em_device.cuh).  scan_subbatch above
+// multiplies all 256 rows by all chains of the sub-batch over the union of all their hulls: measured
+// 1.9x the algorithmic MMAs (3x what windows and hulls strictly need).  Per-chain sums are
+// bit-identical in both paths (4-fragment MMA steps aligned to multiples of 4, ascending).
 template <typename TT>
+__device__ __forceinline__ void scan_subbatch_tiles(ScanShared& sh, const ScanDesc* __restrict__ descs, const UtrDev& u,
+                                                    const TT* __restrict__ A, const double* __restrict__ v_all,
+                                                    ScanPartial* partials, int first, int cnt, int blk, double* Vs,
+                                                    double* scan_elems) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PassCtx& px = sh.px;
+  if (warp == 0) {
+    int h0 = 1 << 30, h1 = 0;
+    if (lane < cnt) {
+      const ScanDesc d = descs[sh.list[first + lane]];
+      px.row0[lane] = d.row0; px.row1[lane] = d.row1; px.hlo[lane] = d.hlo; px.hhi[lane] = d.hhi;
+      px.voff[lane] = d.v_off;
+      px.pboff[lane] = d.pb_off;
+      if (d.hhi >= 0) { h0 = d.hlo; h1 = d.hhi + 1; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      h0 = min(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+      h1 = max(h1, __shfl_xor_sync(0xffffffffu, h1, o));
+    }
+    if (lane == 0) {
+      if (h1 <= h0) { h0 = 0; h1 = 0; }
+      px.NA = h0 & ~7;
+      px.NB = h1;
+      px.P = cluster_v_pitch(h1 - (h0 & ~7));
+    }
+  }
+  sh.wbest[warp][lane] = -CUDART_INF;                    // chains that do not cover this warp's tile
+  sh.wrow[warp][lane] = 0x7fffffff;
+  __syncthreads();
+  const int NA = px.NA, NB = px.NB, P = px.P;
+  for (int j = warp; j <= cnt; j += GW) {                // row cnt = zeros (MMA columns without a chain)
+    double* dst = Vs + j * P;
+    const double* src = v_all + (j < cnt ? px.voff[j] : 0) + NA;
+    for (int o = lane; o < P; o += 32) dst[o] = (j < cnt && NA + o < NB) ? src[o] : 0.0;
+  }
+  __syncthreads();
+  scan_tile<TT, true>(px, u, A, Vs, partials, blk * (SCAN_ROWS / kClusterTileRows) + warp, cnt, scan_elems, sh.wbest[warp],
+                      sh.wrow[warp]);
+  __syncthreads();
+  if (tid < cnt) {
+    double b = sh.wbest[0][tid];
+    int r = sh.wrow[0][tid];
+    for (int w = 1; w < GW; w++) {                       // tiles ascend with the warp index: ties keep the smaller row
+      const double ob = sh.wbest[w][tid];
+      const int orow = sh.wrow[w][tid];
+      if (ob > b || (ob == b && orow < r)) { b = ob; r = orow; }
+    }
+    ScanPartial p;
+    p.score = b; p.row = r; p.pad = 0;
+    partials[px.pboff[tid] + blk] = p;
+  }
+}
+
+// one CTA per (UTR, block of SCAN_ROWS candidate rows); TILES: the tile path (its own kernel: the two
+// paths' register allocations do not disturb each other)
+template <typename TT, bool TILES>
 __global__ void __launch_bounds__(GT, 2)
 em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ descs, const UtrDev* __restrict__ utrs,
                const int32_t* __restrict__ utr_chain_off, const void* __restrict__ tensor,
@@ -964,7 +932,8 @@ em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ de
   const int gb = ref.gb;
   for (int first = ref.sb * gb; first < n_list; first += ref.nsb * gb) {
     const int cnt = min(gb, n_list - first);
-    if (cnt <= 8) SCAN_CALL(1);
+    if (TILES) scan_subbatch_tiles<TT>(sh, descs, u, A, v_all, partials, first, cnt, ref.blk, Vs, scan_elems);
+    else if (cnt <= 8) SCAN_CALL(1);
     else if (cnt <= 16) SCAN_CALL(2);
     else if (cnt <= 24) SCAN_CALL(3);
     else SCAN_CALL(4);
@@ -978,14 +947,30 @@ em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ de
 // then the others (block-per-chain kernel).
 template <typename TT>
 static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big,
-                             bool any_scan, bool big_k, const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
+                             bool any_scan, bool big_k, const ScanRef* refs_dev, int64_t n_refs, int64_t n_refs_tile, const UtrDev* utrs_dev,
                              const int32_t* utr_chain_off_dev, const void* tensor, const double* cnt, double* lz,
                              double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
                              double* trace_ws, cudaStream_t st, std::vector<cudaEvent_t>& evs,
                              std::vector<int>& kinds, int& scan_launches, const std::function<void()>& hook,
-                             int hook_step, const EstepPlan& plan) {
+                             const std::function<void()>& hook_mark, int hook_step, const EstepPlan& plan, int n_steps) {
   const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
-  cudaFuncSetAttribute(em_scan_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(em_scan_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(em_scan_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanTileVBytes);
+  // the scan of one step: work items of the chunked path first (n_refs of them), then those of the tile path
+  auto scan_step = [&]() {
+    if (n_refs > 0) {
+      em_scan_kernel<TT, false><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
+                                                                      vbuf, (ScanPartial*)partials, scan_elems);
+      scan_launches++;
+    }
+    if (n_refs_tile > 0) {
+      em_scan_kernel<TT, true><<<(unsigned)n_refs_tile, GT, kScanTileVBytes, st>>>(refs_dev + n_refs, descs_dev, utrs_dev,
+                                                                                    utr_chain_off_dev, tensor, vbuf,
+                                                                                    (ScanPartial*)partials, scan_elems);
+      scan_launches++;
+    }
+    return (n_refs > 0) + (n_refs_tile > 0);
+  };
   int launches = 0;
   static const int warp_steps = getenv("SCAPE_B200_WARP_STEPS") ? atoi(getenv("SCAPE_B200_WARP_STEPS")) : 24;
   static const bool dbg = getenv("SCAPE_B200_DBG") != nullptr;   // print per-launch timings (development aid)
@@ -1032,19 +1017,16 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
     if (!any_scan) {                                   // prune refits: whole chains inside one launch
       estep(0, 1);
     } else {
-      for (int step = 0; step <= SCAPE_B200_NROUND; step++) {
+      for (int step = 0; step < n_steps; step++) {
         estep(step, 0);
-        if (step == SCAPE_B200_NROUND || n_refs == 0) continue;
-        em_scan_kernel<TT><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
-                                                               vbuf, (ScanPartial*)partials, scan_elems);
-        launches++;
-        scan_launches++;
+        if (step == SCAPE_B200_NROUND || n_refs + n_refs_tile == 0) continue;
+        launches += scan_step();
         mark(1);
-        if (hook && step == hook_step) hook();
+        if (hook && step == hook_step) { if (hook_mark) hook_mark(); hook(); }
       }
     }
   }
-  for (int step = 0; !group && step <= SCAPE_B200_NROUND; step++) {
+  for (int step = 0; !group && step < n_steps; step++) {
     // Early steps: most chains run -> one warp per chain (throughput).  Late steps: few chains run
     // and the step time is the latency of ONE chain's E pass -> one CTA per chain (8x shorter
     // fragment loop); CTAs of finished chains exit at once.
@@ -1074,13 +1056,10 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
       launches++;
     }
     mark(0);
-    if (step == SCAPE_B200_NROUND || !any_scan || n_refs == 0) continue;
-    em_scan_kernel<TT><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
-                                                           vbuf, (ScanPartial*)partials, scan_elems);
-    launches++;
-    scan_launches++;
+    if (step == SCAPE_B200_NROUND || !any_scan || n_refs + n_refs_tile == 0) continue;
+    launches += scan_step();
     mark(1);
-    if (hook && step == hook_step) hook();
+    if (hook && step == hook_step) { if (hook_mark) hook_mark(); hook(); }
   }
   if (dbg) {
     cudaStreamSynchronize(st);
@@ -1097,18 +1076,18 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
 
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
                     bool big_k,
-                    const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
+                    const ScanRef* refs_dev, int64_t n_refs, int64_t n_refs_tile, const UtrDev* utrs_dev,
                     const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
                     double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
-                    double* trace_ws, cudaStream_t st, EmStepEvents& ee, const EstepPlan& plan) {
+                    double* trace_ws, cudaStream_t st, EmStepEvents& ee, const EstepPlan& plan, int n_steps) {
   ee.scan_launches = 0;
   if (f32)
-    return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
+    return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, n_refs_tile, utrs_dev,
                                     utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step, plan);
-  return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, utrs_dev,
+                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.mark, ee.hook_step, plan, n_steps);
+  return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, n_refs_tile, utrs_dev,
                                    utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.hook_step, plan);
+                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.mark, ee.hook_step, plan, n_steps);
 }
 
 // After the stream has been synchronised: total E-step and scan kernel time of the last run.

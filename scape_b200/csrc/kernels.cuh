@@ -68,6 +68,7 @@ struct ChainDev {
   double bic;                     // out
   double lb_arr[SCAPE_B200_NROUND];  // out
   double grid_rows;               // out: sum over iterations of candidate rows scanned (W*B)
+  double grid_rows_head;          // out: grid_rows when a resident kernel took the chain over (0 if it ran the whole chain)
   // device working state
   double lw[SCAPE_B200_KCAP + 1];
   double lb_prev, last_a;
@@ -91,7 +92,8 @@ struct ScanDesc {
 struct ScanRef {
   int32_t utr;
   int32_t blk;
-  int16_t sb, nsb, gb, pad;
+  int16_t sb, nsb, gb;
+  int16_t pad;                    // 1: tile path (whole V rows of a sub-batch staged; per-warp chain masks and hulls)
 };
 
 struct LabelDev {
@@ -140,6 +142,8 @@ struct EmStepEvents {
   // called once, on the host, after the launches of step `hook_step` have been issued (the wave
   // scheduler uses it to slot the next wave's likelihood phase under the thinly filled late steps)
   std::function<void()> hook;
+  // recorded on the EM stream where the staged wave's work may start (cheap; `hook` does the host work)
+  std::function<void()> mark;
   int hook_step = 0;
 };
 void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms);
@@ -172,12 +176,18 @@ struct ClusterJob {
   int32_t cpp;           // chains whose V rows fit the kernel's shared-memory budget per pass (1..32)
 };
 constexpr int kClusterTileRows = 32;            // candidate rows per scan task = rows per partial
-constexpr int kClusterVBytes = 96 * 1024;       // dynamic shared memory per CTA: staged V rows (2 CTAs per SM)
+constexpr int kClusterVBytes = 80 * 1024;       // dynamic shared memory per CTA: staged V rows (2 CTAs per SM)
 constexpr int kClusterPassMax = 32;             // chains per pass (one ballot)
 // pitch (in doubles) of a staged V row that holds `len` fragments: multiple of 4, = 4 mod 16
 inline __host__ __device__ int cluster_v_pitch(int len) {
   const int len4 = (len + 3) & ~3;
   return len4 + ((20 - (len4 & 15)) & 15);
+}
+constexpr int kScanTileVBytes = 92 * 1024;      // em_scan_kernel's dynamic shared memory (tile path: staged V rows; 2 CTAs per SM)
+// chains per sub-batch of em_scan_kernel's tile path for a UTR with N fragments (multiple of 8), 0 = does not fit
+inline int scan_tile_chains(int N) {
+  const int rows = int(kScanTileVBytes / sizeof(double)) / cluster_v_pitch(N + 8) - 1;   // one row of zeros
+  return rows < 8 ? 0 : (rows >= 32 ? 32 : rows / 8 * 8);
 }
 // chains per pass for a UTR with N fragments, 0 = does not fit (use the bulk-synchronous kernels)
 inline int cluster_chains_per_pass(int N) {
@@ -187,13 +197,24 @@ inline int cluster_chains_per_pass(int N) {
 cudaError_t launch_em_cluster(const ClusterJob* jobs_dev, int n_jobs, int cluster_size, ChainDev* chains_dev,
                               ScanDesc* descs_dev, const UtrDev* utrs_dev, const void* tensor, bool f32,
                               const double* cnt, double* lz, double* vbuf, void* partials, double* scan_elems,
-                              int32_t* trace_a, int32_t* trace_b, double* trace_ws, cudaStream_t st);
+                              int32_t* trace_a, int32_t* trace_b, double* trace_ws, long long* stats, int solo_max,
+                              cudaStream_t st);
 
 int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* index_dev, int64_t n_small, int64_t n_big, bool any_scan,
                     bool big_k,
-                    const ScanRef* refs_dev, int64_t n_refs, const UtrDev* utrs_dev,
+                    const ScanRef* refs_dev, int64_t n_refs, int64_t n_refs_tile, const UtrDev* utrs_dev,
                     const int32_t* utr_chain_off_dev, const void* tensor, bool f32, const double* cnt, double* lz,
                     double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
-                    double* trace_ws, cudaStream_t st, EmStepEvents& ee, const EstepPlan& plan);
+                    double* trace_ws, cudaStream_t st, EmStepEvents& ee, const EstepPlan& plan,
+                    int n_steps = SCAPE_B200_NROUND + 1);
+// n_steps = SCAPE_B200_NROUND + 1: the whole run (50 x {E step, scan} + the closing E step that applies
+// the last arg-max); n_steps = S <= NROUND: the first S x {E step, scan} only -- the chains then wait
+// for their S-th arg-max to be applied by whoever continues them (em_tail.cu).
+
+// ---- chain-resident EM (em_tail.cu): one CTA per chain, all remaining iterations in one launch ---------
+cudaError_t launch_em_tail(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* list_dev, int first, int n,
+                           int max_n, int prows, const UtrDev* utrs_dev, const void* tensor, bool f32,
+                           const double* cnt, double* lz, const void* partials, int32_t* trace_a, int32_t* trace_b,
+                           double* trace_ws, unsigned long long* stats, cudaStream_t st);
 
 }  // namespace scape

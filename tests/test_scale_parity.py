@@ -110,7 +110,7 @@ def compare(fx, outs):
             lab_total += len(lab)
             worst = dict(alpha=max(worst["alpha"], da), beta=max(worst["beta"], db), ws=max(worst["ws"], dw),
                          lb=max(worst["lb"], dl))
-        exact_path[j] = ok and out.n_lb[k] == fx["n_iter"][j] and out.path[k, 3] == fx["chains_run"][j]
+        exact_path[j] = ok and out.n_lb[k] == fx["n_iter"][j] and out.path[k, 0] == fx["n_path"][j]
     return same_k, within, exact_path, lab_same, lab_total, worst
 
 
@@ -129,7 +129,7 @@ def test_acceptance_gate(suite, policy, dtype, report_line):
         if bad:
             first_div[f] = (bad[0], len(bad), len(idx))
     line = (f"scale parity {suite:6s} {policy:4s} {dtype}: UTRs {n}  K identical {100 * same_k.mean():.2f}%  "
-            f"within tolerance {100 * within.mean():.2f}%  same iterations+chains {100 * exact_path.mean():.2f}%  "
+            f"within tolerance {100 * within.mean():.2f}%  same iterations+sweeps {100 * exact_path.mean():.2f}%  "
             f"labels {100 * lab_same / max(lab_total, 1):.4f}%  worst d_alpha {worst['alpha']:.0f} d_beta {worst['beta']:.1e} "
             f"d_w {worst['ws']:.1e} d_lb {worst['lb']:.1e}  first divergent UTR per file (pos, n_bad, n): {first_div or 'none'}")
     report_line(line)
