@@ -199,6 +199,31 @@ def run_reference(args):
     }))
 
 
+def files_leg(utrs, per_file, local):
+    """The path a `scape infer_pa` user runs, file to file: `prepare_input`-format chunk pickles on disk ->
+    scape_b200.apa_core.infer_files (unpickle the DataFrames, pack CSR columns, fit_batch, build and
+    pickle the Parameters objects) -> result pickles on disk (apa_core.py:1104-1137 per file).  One
+    warm-up call (worker processes, page cache, engine arenas), one timed call."""
+    import shutil
+    import tempfile
+    from scape_b200 import apa_core, synth
+    root = tempfile.mkdtemp(prefix="scape_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        paths = synth.write_chunk_files(utrs, root, per_file=per_file)
+        in_bytes = sum(os.path.getsize(p) for p in paths)
+        apa_core.infer_files(paths, root, device=local)
+        t0 = time.perf_counter()
+        outs = apa_core.infer_files(paths, root, device=local)
+        wall = time.perf_counter() - t0
+        out_bytes = sum(os.path.getsize(o) for o in outs)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return {"value": len(utrs) / wall, "unit": "UTR/s", "wall_s": wall, "chunk_files": len(paths), "input_bytes": in_bytes,
+            "output_bytes": out_bytes,
+            "path": "chunk pickles (tmpfs) -> infer_files: worker processes unpickle / pack, one fit_batch call, worker "
+                    "processes build and pickle scape.apa_core.Parameters -> result pickles"}
+
+
 def make_workload(name, args, rank, world):
     from scape_b200 import synth
     a = argparse.Namespace(**vars(args))
@@ -225,7 +250,7 @@ def make_workload(name, args, rank, world):
     return wl
 
 
-def run_workload(wl, args, steps, warmup, rank, local, world, dist, cpu_arm=None):
+def run_workload(wl, args, steps, warmup, rank, local, world, dist, cpu_arm=None, files=False):
     """W warm-up passes, K timed passes (barrier + synchronize on both sides), one extra un-pipelined
     pass for the per-kernel roofline.  Returns the result dict on rank 0, None elsewhere."""
     from scape_b200 import _lib
@@ -365,6 +390,8 @@ def run_workload(wl, args, steps, warmup, rank, local, world, dist, cpu_arm=None
         res["parity_check"] = {"utrs": len(rows), "K_identical": same_k, "within_north_star_tolerance": ok,
                                "against": "cpu_baseline leg (oracle port), same UTRs and RNG streams as the GPU arm"}
     eng.close()
+    if files and wl["name"] == "cfg2":
+        res["e2e_files"] = files_leg(utrs, wl["per_file"], local)
     return res
 
 
@@ -378,6 +405,7 @@ def main():
     ap.add_argument("--reads", type=int, default=READS)
     ap.add_argument("--per-file", type=int, default=PER_FILE)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-files", action="store_true", help="skip the file-to-file leg (e2e_files)")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg-3 block reported beside the cfg-2 line")
     ap.add_argument("--ref-utrs-per-file", type=int, default=3,
                     help="CPU arm / cpu_baseline leg: leading UTRs of each chunk file fitted per step (bounded sample)")
@@ -401,7 +429,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     res = run_workload(make_workload(args.workload, args, rank, world), args, args.steps, args.warmup, rank, local, world,
-                       dist, cpu_arm)
+                       dist, cpu_arm, files=(world == 1 and not args.no_files))
     if cpu_arm is not None:
         cpu_arm.close()
     if args.workload == "cfg2" and not args.no_cfg3 and args.utrs == N_UTR:

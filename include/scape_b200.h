@@ -142,6 +142,12 @@ int scape_b200_set_tensor_dtype(scape_b200_handle* h, int bytes);
  * Environment override at create time: SCAPE_B200_OVERLAP=0. */
 int scape_b200_set_overlap(scape_b200_handle* h, int on);
 
+/* Host threads this handle may use for its pre-pass / RNG-replay pools (0 = default: the CPUs of the
+ * process divided by LOCAL_WORLD_SIZE).  A process that drives several GPUs gives every handle its
+ * share (scape_b200.apa_core.infer_files(devices=[...])); the reference itself is single-threaded
+ * (apa_core.py:1104-1137).  Environment override at create time: SCAPE_B200_THREADS. */
+int scape_b200_set_host_threads(scape_b200_handle* h, int n);
+
 /* ---- kernel-seam entry points (parity tests; reference seam B3, apa_core.py:23) ------------- */
 
 /* loglik_xlr_t over a theta list (apa_core.py:620-640, taichi_core.py:183-215):

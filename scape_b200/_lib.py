@@ -95,7 +95,7 @@ EXPORTS = [
     "scape_b200_destroy", "scape_b200_fit_batch", "scape_b200_get_timing", "scape_b200_loglik_table",
     "scape_b200_marginal_tensor", "scape_b200_em_chains", "scape_b200_bin_reads", "scape_b200_profile",
     "scape_b200_draw_chains", "scape_b200_rng_draw", "scape_b200_set_argsort_callback",
-    "scape_b200_set_tensor_dtype", "scape_b200_set_overlap", "scape_b200_fp64_peaks",
+    "scape_b200_set_tensor_dtype", "scape_b200_set_overlap", "scape_b200_set_host_threads", "scape_b200_fp64_peaks",
 ]
 
 ARGSORT_FN = C.CFUNCTYPE(None, c_double_p, C.c_int64, c_int64_p)
@@ -132,6 +132,7 @@ def load():
     lib.scape_b200_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     lib.scape_b200_set_tensor_dtype.argtypes = [C.c_void_p, C.c_int]
     lib.scape_b200_set_overlap.argtypes = [C.c_void_p, C.c_int]
+    lib.scape_b200_set_host_threads.argtypes = [C.c_void_p, C.c_int]
     lib.scape_b200_fp64_peaks.argtypes = [C.c_void_p, c_double_p, c_double_p]
     lib.scape_b200_loglik_table.argtypes = [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
                                             C.c_int64, c_double_p, c_double_p]
@@ -262,6 +263,10 @@ class Engine:
         _check(self._lib.scape_b200_create(device, C.byref(params), C.byref(self._h)))
         if tensor_dtype is not None:
             _check(self._lib.scape_b200_set_tensor_dtype(self._h, {"f32": 4, "f64": 8}[tensor_dtype]))
+
+    def set_host_threads(self, n: int):
+        """Host threads of this handle's pre-pass / RNG-replay pools (0 = process default)."""
+        _check(self._lib.scape_b200_set_host_threads(self._h, int(n)))
 
     def set_overlap(self, on: bool):
         """Pipeline the likelihood phase of the next wave under the EM of the current one (default on)."""

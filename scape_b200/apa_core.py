@@ -215,6 +215,19 @@ def _write_result_file(path, fixed_run_mode, gene_infos, n_reads, K, L, alpha, b
 
 
 _io_pool = None
+_engines = {}
+
+
+def _cached_engine(device: int, params, host_threads: int = 0):
+    """One Engine per (device, parameter set), kept across infer_files calls: its device arenas, pinned
+    staging and host pools are expensive to build.  A handle is not re-entrant; callers use a device
+    from one thread at a time."""
+    key = (int(device), bytes(params))
+    eng = _engines.get(key)
+    if eng is None:
+        eng = _engines[key] = _lib.Engine(params, device=device)
+    eng.set_host_threads(host_threads)
+    return eng
 
 
 def _get_io_pool(workers: int):
@@ -418,12 +431,10 @@ def _infer_files_pooled(paths, outs, devices, io_workers, **kwargs):
             batch = ChunkBatch()
             for s, f in enumerate(mine):
                 batch.add_packed(s, *packed[f])
-            engine = _lib.Engine(_lib.make_params(pre_para=pre_para, **kwargs), device=dev)
-            try:
-                off, x, l, r, pa, sid = batch.packed()
-                out = engine.fit(off, x, l, r, pa, sid, np.ones(len(mine), np.uint32))
-            finally:
-                engine.close()
+            engine = _cached_engine(dev, _lib.make_params(pre_para=pre_para, **kwargs),
+                                    host_threads=max(1, (os.cpu_count() or 1) // len(devices)) if len(devices) > 1 else 0)
+            off, x, l, r, pa, sid = batch.packed()
+            out = engine.fit(off, x, l, r, pa, sid, np.ones(len(mine), np.uint32))
             if np.any(out.status != 0):
                 results_to_parameters(batch, out, fixed)      # raises the reference's error for the first bad UTR
             u0 = 0

@@ -329,6 +329,13 @@ int scape_b200_set_tensor_dtype(scape_b200_handle* h, int bytes) {
   return 0;
 }
 
+int scape_b200_set_host_threads(scape_b200_handle* h, int n) {
+  if (!h) return fail(-5, "null handle");
+  if (n < 0) return fail(-5, "host thread count must be >= 0 (0 = the process default)");
+  h->host_threads = n;      // the pools are rebuilt by the next fit if the count changed
+  return 0;
+}
+
 int scape_b200_set_overlap(scape_b200_handle* h, int on) {
   if (!h) return fail(-5, "null handle");
   h->overlap = on != 0;

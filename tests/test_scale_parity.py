@@ -110,7 +110,7 @@ def compare(fx, outs):
             lab_total += len(lab)
             worst = dict(alpha=max(worst["alpha"], da), beta=max(worst["beta"], db), ws=max(worst["ws"], dw),
                          lb=max(worst["lb"], dl))
-        exact_path[j] = ok and out.n_lb[k] == fx["n_iter"][j] and out.path[k, 0] == fx["n_path"][j]
+        exact_path[j] = ok and out.n_lb[k] == fx["n_iter"][j] and out.path[k, 0] == max(int(fx["n_path"][j]), 1)   # (fixed mode: one sweep, no path record)
     return same_k, within, exact_path, lab_same, lab_total, worst
 
 

@@ -140,6 +140,9 @@ class _FakeEngine:
     def close(self):
         pass
 
+    def set_host_threads(self, n):
+        self.host_threads = n
+
     def fit(self, off, x, l, r, pa, sid, seeds, stream_state=None):
         from scape_b200 import _lib
         n_utr = len(off) - 1
@@ -162,6 +165,7 @@ def test_infer_files_worker_processes_write_the_same_pickles(tmp_path, monkeypat
     import pickle
     from scape_b200 import _lib, apa_core, synth
     monkeypatch.setattr(_lib, "Engine", _FakeEngine)
+    monkeypatch.setattr(apa_core, "_engines", {})         # (infer_files keeps one engine per device and parameter set)
     utrs = [synth.make_utr(700 + i, 30 + 17 * (i % 9)) for i in range(36)]
     a_dir, b_dir = tmp_path / "inproc", tmp_path / "pooled"
     a_dir.mkdir(); b_dir.mkdir()
