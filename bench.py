@@ -312,6 +312,7 @@ def run_workload(wl, args, steps, warmup, rank, local, world, dist, cpu_arm=None
     K = steps
     hbm_peak, hbm_src = measured_peaks()
     fp64 = eng.fp64_peaks()                     # measured on this GPU, this run (no FP64 entry in MEASURED_PEAKS.json)
+    sfu = eng.sfu_peaks()                       # FP32 FMA / MUFU / FP64 exp, log streams
     cluster = alone.get("resident_ms", 0.0) > alone["scan_ms"]     # which EM kernel dominates this workload
     if cluster:
         dom_s = alone["resident_ms"] / 1e3
@@ -364,6 +365,17 @@ def run_workload(wl, args, steps, warmup, rank, local, world, dist, cpu_arm=None
         "phases_alone_ms": {k: alone[k] for k in ("table_ms", "tensor_ms", "em_ms", "resident_ms", "estep_ms", "scan_ms", "label_ms",
                                                   "device_busy_ms", "total_ms")},
         "tensor_exp_per_s": alone["tensor_exp"] / (alone["tensor_ms"] / 1e3),
+        "likelihood_rooflines": {
+            "peaks": sfu,
+            "table_kernel": {"exp_per_s": alone["table_exp"] / (alone["table_ms"] / 1e3), "peak_exp_per_s": sfu["exp_f64_gops"] * 1e9,
+                             "frac": alone["table_exp"] / (alone["table_ms"] / 1e3) / (sfu["exp_f64_gops"] * 1e9),
+                             "note": "N*T*13 FP64 exp per UTR (SURVEY 8d) over the kernel's time vs the measured FP64 exp() stream; "
+                                     "entries of reads that cannot reach theta skip the exps (the count is the reference's)"},
+            "tensor_kernels": {"reference_exp_per_s": alone["tensor_exp"] / (alone["tensor_ms"] / 1e3),
+                               "peak_exp_per_s": sfu["exp_f64_gops"] * 1e9,
+                               "x_of_exp_peak": alone["tensor_exp"] / (alone["tensor_ms"] / 1e3) / (sfu["exp_f64_gops"] * 1e9),
+                               "note": "the reference's 307 exp per (fragment, alpha) over the kernels' time; above 1 because the "
+                                       "kernels take ~6 exp + 559 FMA per (fragment, alpha) instead and skip the all-sentinel entries"}},
         "waves_per_step": waves / K,
         "clocks": clocks,
     }

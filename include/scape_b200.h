@@ -106,6 +106,7 @@ typedef struct scape_b200_timing {
   double em_scan_bytes;                           /* tensor bytes the grid search actually loads (fragment hull only) */
   double estep_ms, scan_ms;                       /* em_ms split: E-step kernels / arg-max scan kernels */
   int64_t scan_launches;
+  double table_exp;                               /* exp() evaluations of the theta-table kernel (N T S per UTR) */
   double resident_ms;                             /* em_ms spent in the resident EM kernels (chain-resident tail / cluster-resident): E passes + grid search, many iterations per launch */
   double resident_grid_flops;                     /* algorithmic grid-search flops (2 W_k B N per chain iteration) done inside those kernels */
   int64_t resident_launches;
@@ -130,6 +131,11 @@ int scape_b200_get_timing(scape_b200_handle* h, scape_b200_timing* out);
  * and tensor-core DMMA (mma.m8n8k4.f64) stream.  They are the roofline denominators of the EM
  * kernels; MEASURED_PEAKS.json carries no FP64 figure. */
 int scape_b200_fp64_peaks(scape_b200_handle* h, double* dfma_tflops, double* dmma_tflops);
+/* out4 = {FP32 FMA TFLOP/s, MUFU ex2.approx Gop/s, FP64 exp() Gop/s, FP64 log() Gop/s} of this GPU, measured
+ * with register-resident instruction streams: the roofline denominators of the likelihood phases
+ * (loglik_xlr_t: 13 exp per table entry, taichi_core.py:141-157; get_loglik_marginal_tensor: 307 exp
+ * per (fragment, alpha), taichi_core.py:160-179). */
+int scape_b200_sfu_peaks(scape_b200_handle* h, double* out4);
 
 /* Storage type of the marginal tensor in HBM: 4 = float (default; values are computed in FP64 and
  * rounded once, every sum / product stays FP64), 8 = double (strict mode).  Environment override at

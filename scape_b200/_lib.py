@@ -71,7 +71,7 @@ class Timing(C.Structure):
         ("em_grid_bytes", C.c_double), ("em_grid_flops", C.c_double), ("tensor_exp", C.c_double),
         ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("em_scan_bytes", C.c_double),
         ("estep_ms", C.c_double), ("scan_ms", C.c_double), ("scan_launches", C.c_int64),
-        ("resident_ms", C.c_double), ("resident_grid_flops", C.c_double), ("resident_launches", C.c_int64),
+        ("table_exp", C.c_double), ("resident_ms", C.c_double), ("resident_grid_flops", C.c_double), ("resident_launches", C.c_int64),
     ]
 
     def as_dict(self):
@@ -95,7 +95,7 @@ EXPORTS = [
     "scape_b200_destroy", "scape_b200_fit_batch", "scape_b200_get_timing", "scape_b200_loglik_table",
     "scape_b200_marginal_tensor", "scape_b200_em_chains", "scape_b200_bin_reads", "scape_b200_profile",
     "scape_b200_draw_chains", "scape_b200_rng_draw", "scape_b200_set_argsort_callback",
-    "scape_b200_set_tensor_dtype", "scape_b200_set_overlap", "scape_b200_set_host_threads", "scape_b200_fp64_peaks",
+    "scape_b200_set_tensor_dtype", "scape_b200_set_overlap", "scape_b200_set_host_threads", "scape_b200_fp64_peaks", "scape_b200_sfu_peaks",
 ]
 
 ARGSORT_FN = C.CFUNCTYPE(None, c_double_p, C.c_int64, c_int64_p)
@@ -134,6 +134,7 @@ def load():
     lib.scape_b200_set_overlap.argtypes = [C.c_void_p, C.c_int]
     lib.scape_b200_set_host_threads.argtypes = [C.c_void_p, C.c_int]
     lib.scape_b200_fp64_peaks.argtypes = [C.c_void_p, c_double_p, c_double_p]
+    lib.scape_b200_sfu_peaks.argtypes = [C.c_void_p, c_double_p]
     lib.scape_b200_loglik_table.argtypes = [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p,
                                             C.c_int64, c_double_p, c_double_p]
     lib.scape_b200_marginal_tensor.argtypes = [C.c_void_p, C.c_int64, C.c_int64, c_double_p, C.c_int64, c_double_p,
@@ -319,6 +320,12 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         _check(self._lib.scape_b200_fp64_peaks(self._h, C.byref(a), C.byref(b)))
         return {"dfma_tflops": a.value, "dmma_tflops": b.value}
+
+    def sfu_peaks(self) -> dict:
+        """Measured FP32 FMA TFLOP/s, MUFU ex2 Gop/s and FP64 exp() / log() Gop/s of this GPU."""
+        out = np.zeros(4)
+        _check(self._lib.scape_b200_sfu_peaks(self._h, _dp(out)))
+        return {"ffma_tflops": out[0], "mufu_ex2_gops": out[1], "exp_f64_gops": out[2], "log_f64_gops": out[3]}
 
     def timing(self) -> dict:
         t = Timing()

@@ -110,12 +110,14 @@ struct StagedBufs {
 struct Lane {
   cudaStream_t st = nullptr;       // EM, labels (high priority)
   cudaStream_t st_lik = nullptr;   // uploads, table, tensor of the staged wave (low priority)
+  cudaStream_t st_aux[3] = {nullptr, nullptr, nullptr};   // parts 2..4 of a split bulk-synchronous wave (high priority)
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   StagedBufs staged;
   std::unique_ptr<WorkPool> pool;  // host workers of this lane's wave loop (sleep between regions)
   PinnedBuf<char> h_stage[2];      // pinned upload staging of the staged wave, alternating per wave
   cudaEvent_t ev_mid = nullptr;    // recorded on `st` where the next wave's likelihood phase may start
   int stage_step = 40;
-  DevBuf<double> d_fx, d_fl, d_fr, d_fpa, d_cnt, d_theta, d_table, d_tensor, d_lz, d_v, d_trace_ws;
+  DevBuf<double> d_fx, d_fl, d_fr, d_fpa, d_cnt, d_theta, d_table, d_tensor, d_lz, d_trace_ws;   // d_lz = [log_zmat scratch | V]
   DevBuf<UtrDev> d_utrs;
   DevBuf<RowRef> d_rows, d_trows;
   DevBuf<TileRef> d_tiles;
@@ -132,6 +134,7 @@ struct Lane {
   PinnedBuf<ChainDev> h_chains, h_refits;
   cudaEvent_t ev[8];
   EmStepEvents em_events, em_events2;   // bulk-synchronous runs: all steps / the head of the tail route
+  EmStepEvents em_events_part[3];       // parts 2..4 of a split wave
   PinnedBuf<char> h_runmeta;            // per-run index lists, scan items, cluster jobs (pinned upload staging)
   scape_b200_timing tm;
   std::vector<std::pair<float, float>> busy;   // kernel intervals (ms since the fit's base event)
@@ -139,7 +142,7 @@ struct Lane {
   int rc = 0;
   void release() {
     d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
-    d_table.release(); d_tensor.release(); d_lz.release(); d_v.release(); d_trace_ws.release(); d_utrs.release();
+    d_table.release(); d_tensor.release(); d_lz.release(); d_trace_ws.release(); d_utrs.release();
     d_rows.release(); d_trows.release(); d_tiles.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
     d_refs.release(); d_cjobs.release(); d_clstats.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_lists.release(); d_counts.release();
@@ -159,6 +162,7 @@ struct Lane {
 };
 
 constexpr int kMaxLanes = 4;
+constexpr int kMaxSplit = 4;   // parts a bulk-synchronous wave can be split into (one stream each)
 
 struct scape_b200_handle {
   int device = 0;
@@ -177,6 +181,7 @@ struct scape_b200_handle {
   int host_threads = 0;     // 0 = CPUs of this process / ranks sharing the host
   std::unique_ptr<WorkPool> prep_pool;
   bool overlap = true;      // likelihood phase of wave w+1 runs under the EM of wave w
+  size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside for the EM state (SCAPE_B200_L2_PERSIST_MB, 0 = off)
   bool poison = false;      // SCAPE_B200_POISON=1 (tests): fill the tensor arena with NaN bits before every wave
 };
 
@@ -282,12 +287,30 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   for (Lane& L : h->lanes) {
     CU(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio_hi));
     CU(cudaStreamCreateWithPriority(&L.st_lik, cudaStreamNonBlocking, prio_lo));
+    for (auto& sa : L.st_aux) CU(cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, prio_hi));
+    CU(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
+    for (auto& e : L.ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : L.ev) CU(cudaEventCreate(&e));
     for (auto& e : L.ev_cl) CU(cudaEventCreate(&e));
     for (auto& e : L.staged.ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&L.ev_mid, cudaEventDisableTiming));
     if (const char* s = getenv("SCAPE_B200_STAGE_STEP")) L.stage_step = atoi(s);
     memset(&L.tm, 0, sizeof(L.tm));
+  }
+  {
+    // persisting L2 set-aside for the EM working state (see run_chains)
+    int max_persist = 0, max_window = 0;
+    CU(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device));
+    CU(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device));
+    double want_mb = 0;      // measured: no effect on the E step; opt-in knob
+    if (const char* s = getenv("SCAPE_B200_L2_PERSIST_MB")) want_mb = atof(s);
+    const size_t want = size_t(std::max(0.0, want_mb) * 1024 * 1024);
+    h->l2_persist_bytes = std::min(want, size_t(std::max(0, max_persist)));
+    h->l2_window_max = size_t(std::max(0, max_window));
+    if (h->l2_persist_bytes > 0 && h->l2_window_max > 0)
+      CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_bytes));
+    else
+      h->l2_persist_bytes = 0;
   }
   CU(cudaEventCreate(&h->base_ev));
   CU(cudaEventRecord(h->base_ev, 0));
@@ -309,6 +332,7 @@ int scape_b200_destroy(scape_b200_handle* h) {
   for (Lane& L : h->lanes) {
     cudaStreamSynchronize(L.st);
     cudaStreamSynchronize(L.st_lik);
+    for (auto& sa : L.st_aux) cudaStreamSynchronize(sa);
     L.release();
     for (auto& e : L.ev) cudaEventDestroy(e);
     for (auto& e : L.ev_cl) cudaEventDestroy(e);
@@ -316,6 +340,9 @@ int scape_b200_destroy(scape_b200_handle* h) {
     cudaEventDestroy(L.ev_mid);
     cudaStreamDestroy(L.st);
     cudaStreamDestroy(L.st_lik);
+    for (auto& sa : L.st_aux) cudaStreamDestroy(sa);
+    cudaEventDestroy(L.ev_fork);
+    for (auto& e : L.ev_join) cudaEventDestroy(e);
   }
   cudaEventDestroy(h->base_ev);
   delete h;
@@ -348,6 +375,13 @@ int scape_b200_fp64_peaks(scape_b200_handle* h, double* dfma_tflops, double* dmm
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, h->device));
   if (measure_fp64_peaks(prop.multiProcessorCount, dfma_tflops, dmma_tflops, h->lanes[0].st)) return fail(-100, "peak kernels failed");
+  return 0;
+}
+
+int scape_b200_sfu_peaks(scape_b200_handle* h, double* out4) {
+  if (!h || !out4) return fail(-5, "null argument");
+  CU(cudaSetDevice(h->device));
+  if (measure_sfu_peaks(h->n_sm, out4, h->lanes[0].st)) return fail(-100, "peak kernels failed");
   return 0;
 }
 
@@ -396,7 +430,7 @@ int np_argmin(const std::vector<double>& v) {
 //   cluster  one thread-block cluster per UTR, all iterations in one launch (em_cluster.cu).  Measured
 //            slower than both everywhere (idle warps at the cluster barriers); kept as an experiment.
 //   auto (default)  tail for runs of fewer than SCAPE_B200_TAIL_CHAINS (1500) chains, else bsp
-enum EmRoute : char { kRouteBsp = 0, kRouteCluster = 1, kRouteTail = 2 };
+enum EmRoute : char { kRouteBsp = 0, kRouteCluster = 1, kRouteTail = 2, kRouteBspPart = 3 };   // kRouteBspPart + p: part p + 1 of a split wave
 
 // The chains of a set of UTRs prepared for the bulk-synchronous step kernels: the E-step launch
 // order (few-fragment chains first, sorted by K and N) and the scan's work items.
@@ -547,6 +581,25 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
       if (mode == kRouteTail && u.N <= 4096) route[i] = kRouteTail;
     }
   }
+  // Split a bulk-synchronous wave into two halves that step independently on two streams: one half's
+  // E step (latency-bound, FP64 pipe ~20 % busy) then runs under the other half's scan (tensor-pipe
+  // bound).  UTRs are dealt alternately in order of decreasing cost.  SCAPE_B200_SPLIT=0 switches it
+  // off; runs with traces, few UTRs or weights-only chains are never split.
+  static const int split_env = std::max(1, std::min(kMaxSplit, getenv("SCAPE_B200_SPLIT") ? atoi(getenv("SCAPE_B200_SPLIT")) : 2));
+  int n_parts = 1;
+  if (split_env > 1 && h->overlap && !want_trace && mode == kRouteBsp) {
+    std::vector<std::pair<double, size_t>> order;
+    for (size_t i = 0; i < W; i++)
+      if (route[i] == kRouteBsp) order.emplace_back(-double(utrs_host[i].N) * utrs_host[i].T, i);
+    bool any_weights_only = false;
+    for (size_t i = 0; i < chains.size(); i++) any_weights_only = any_weights_only || chains[i].weights_only;
+    if (order.size() >= size_t(8 * split_env) && !any_weights_only) {
+      std::sort(order.begin(), order.end());
+      n_parts = split_env;
+      for (size_t j = 0; j < order.size(); j++)
+        if (j % size_t(n_parts)) route[order[j].second] = char(kRouteBspPart + int(j % size_t(n_parts)) - 1);
+    }
+  }
   for (size_t i = 0; i < chains.size(); i++) {
     ChainDev& c = chains[i];
     if (i > 0 && c.utr < chains[i - 1].utr) return fail(-5, "internal: chains not ordered by UTR");
@@ -577,8 +630,12 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
                           std::to_string(kScanMaxChains));
     chain_off[i + 1] += chain_off[i];
   }
-  StepSet full, head;                 // all 51 steps / the first tail_step steps before the chain-resident kernel
+  StepSet full, head, parts[kMaxSplit - 1];   // all 51 steps / the first tail_step steps before the chain-resident kernel / parts 2.. of a split wave
   if (int rc = build_step_set(h, chains, utrs_host, chain_off, scans, route, kRouteBsp, full)) return rc;
+  for (int p = 1; p < n_parts; p++)
+    if (int rc = build_step_set(h, chains, utrs_host, chain_off, scans, route, char(kRouteBspPart + p - 1), parts[p - 1])) return rc;
+  size_t parts_index = 0, parts_refs = 0;
+  for (int p = 1; p < n_parts; p++) { parts_index += parts[p - 1].index.size(); parts_refs += parts[p - 1].refs.size(); }
   if (int rc = build_step_set(h, chains, utrs_host, chain_off, scans, route, kRouteTail, head)) return rc;
   // chains of the tail route in UTR order: neighbours in the launch share a tensor (L2)
   std::vector<int32_t> tail_list;
@@ -607,11 +664,28 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     cjobs.swap(sorted);
   }
   // ---- device buffers + uploads ------------------------------------------------------------------
-  const size_t n_index = full.index.size() + head.index.size() + tail_list.size();
-  const size_t n_refs = full.refs.size() + head.refs.size();
+  const size_t n_index = full.index.size() + head.index.size() + tail_list.size() + parts_index;
+  const size_t n_refs = full.refs.size() + head.refs.size() + parts_refs;
   CU(L.d_cjobs.ensure(cjobs.size() + 1));
-  CU(L.d_lz.ensure(size_t(lz)));
-  CU(L.d_v.ensure(size_t(vsz + 8)));
+  // log_zmat scratch and V live in ONE allocation: [lz | V].  They are what every EM iteration reads
+  // and rewrites (a wave's 5,000 chains: ~55 MB + 10 MB), while each scan streams the wave's marginal
+  // tensors (250-400 MB) through the L2 in between and evicts them.  An access-policy window on the EM
+  // stream marks [lz | V] as persisting L2 lines (set-aside sized at create), so the E passes' stale-column
+  // reads and the scan's V staging hit L2 instead of HBM; the tensor keeps streaming through the rest.
+  const size_t lzv_elems = size_t(lz) + size_t(vsz) + 8;
+  CU(L.d_lz.ensure(lzv_elems));
+  double* const d_v = L.d_lz.p + size_t(lz);
+  if (h->l2_persist_bytes > 0) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    const size_t win = std::min(lzv_elems * sizeof(double), h->l2_window_max);
+    attr.accessPolicyWindow.base_ptr = L.d_lz.p;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(h->l2_persist_bytes) / double(std::max<size_t>(win, 1))));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute(L.st, cudaStreamAttributeAccessPolicyWindow, &attr));
+  }
   CU(L.d_chains.ensure(chains.size()));
   CU(L.d_chain_off.ensure(W + 1));
   CU(L.d_descs.ensure(chains.size()));
@@ -627,8 +701,8 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   }
   // the small host arrays go through one pinned blob (pageable sources would make the copies synchronous)
   int32_t *d_idx_full = L.d_chain_idx.p, *d_idx_head = d_idx_full + full.index.size(),
-          *d_tail = d_idx_head + head.index.size();
-  ScanRef *d_refs_full = L.d_refs.p, *d_refs_head = d_refs_full + full.refs.size();
+          *d_tail = d_idx_head + head.index.size(), *d_idx_parts = d_tail + tail_list.size();
+  ScanRef *d_refs_full = L.d_refs.p, *d_refs_head = d_refs_full + full.refs.size(), *d_refs_parts = d_refs_head + head.refs.size();
   {
     auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
     const size_t o_idx = 0, o_refs = o_idx + up16(4 * n_index), o_off = o_refs + up16(sizeof(ScanRef) * n_refs),
@@ -639,9 +713,17 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     std::copy(full.index.begin(), full.index.end(), hi);
     std::copy(head.index.begin(), head.index.end(), hi + full.index.size());
     std::copy(tail_list.begin(), tail_list.end(), hi + full.index.size() + head.index.size());
+    {
+      int32_t* o = hi + full.index.size() + head.index.size() + tail_list.size();
+      for (int p = 1; p < n_parts; p++) o = std::copy(parts[p - 1].index.begin(), parts[p - 1].index.end(), o);
+    }
     ScanRef* hr = (ScanRef*)(b + o_refs);
     std::copy(full.refs.begin(), full.refs.end(), hr);
     std::copy(head.refs.begin(), head.refs.end(), hr + full.refs.size());
+    {
+      ScanRef* o = hr + full.refs.size() + head.refs.size();
+      for (int p = 1; p < n_parts; p++) o = std::copy(parts[p - 1].refs.begin(), parts[p - 1].refs.end(), o);
+    }
     std::copy(chain_off.begin(), chain_off.end(), (int32_t*)(b + o_off));
     std::copy(cjobs.begin(), cjobs.end(), (ClusterJob*)(b + o_jobs));
     CU(cudaMemcpyAsync(L.d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, L.st));
@@ -691,7 +773,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     if (cl_dbg) CU(L.d_clstats.ensure(cjobs.size() * 10));
     CU(cudaEventRecord(L.ev_cl[0], L.st));
     CU(launch_em_cluster(L.d_cjobs.p, int(cjobs.size()), csize, L.d_chains.p, L.d_descs.p, L.d_utrs.p, L.d_tensor.p,
-                         h->tensor_f32, L.d_cnt.p, L.d_lz.p, L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p,
+                         h->tensor_f32, L.d_cnt.p, L.d_lz.p, d_v, L.d_partials.p, L.d_counter.p, L.d_trace_a.p,
                          L.d_trace_b.p, L.d_trace_ws.p, cl_dbg ? L.d_clstats.p : nullptr, solo_max, L.st));
     CU(cudaEventRecord(L.ev_cl[1], L.st));
     resident_timed = true;
@@ -723,7 +805,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
       L.em_events2.hook = nullptr;
       nl += launch_em_steps(L.d_chains.p, L.d_descs.p, d_idx_head, head.n_small, head.n_big, any_scan, head.big_k, d_refs_head,
                             head.n_refs_chunk, int64_t(head.refs.size()) - head.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p,
-                            L.d_lz.p, L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p, L.d_trace_ws.p,
+                            L.d_lz.p, d_v, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p, L.d_trace_ws.p,
                             L.st, L.em_events2, plan, tail_step);
     }
     // ... then every chain that still runs iterates to convergence in a CTA of its own
@@ -752,13 +834,40 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     nl += 1;
     fire_hook();
   }
+  if (n_parts > 1) {
+    // parts 2.. on the auxiliary streams: fork after the uploads, join before the download.  The
+    // group-kernel list / count scratch is not used by runs with a grid search, so the parts share nothing.
+    CU(cudaEventRecord(L.ev_fork, L.st));
+    int32_t* di = d_idx_parts;
+    ScanRef* dr = d_refs_parts;
+    for (int p = 1; p < n_parts; p++) {
+      StepSet& S = parts[p - 1];
+      cudaStream_t sp = L.st_aux[p - 1];
+      EmStepEvents& ee = L.em_events_part[p - 1];
+      ee.hook = nullptr;
+      ee.mark = nullptr;
+      ee.kinds.clear();
+      if (!S.index.empty()) {
+        CU(cudaStreamWaitEvent(sp, L.ev_fork, 0));
+        nl += launch_em_steps(L.d_chains.p, L.d_descs.p, di, S.n_small, S.n_big, any_scan, S.big_k, dr, S.n_refs_chunk,
+                              int64_t(S.refs.size()) - S.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32,
+                              L.d_cnt.p, L.d_lz.p, d_v, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
+                              L.d_trace_ws.p, sp, ee, plan, SCAPE_B200_NROUND + 1);
+        CU(cudaEventRecord(L.ev_join[p - 1], sp));
+      }
+      di += S.index.size();
+      dr += S.refs.size();
+    }
+  }
   if (have_full)
     nl += launch_em_steps(L.d_chains.p, L.d_descs.p, d_idx_full, full.n_small, full.n_big, any_scan, full.big_k, d_refs_full,
                           full.n_refs_chunk, int64_t(full.refs.size()) - full.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p,
-                          L.d_lz.p, L.d_v.p, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p, L.d_trace_ws.p, L.st,
+                          L.d_lz.p, d_v, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p, L.d_trace_ws.p, L.st,
                           L.em_events, plan, SCAPE_B200_NROUND + 1);
   else
     L.em_events.kinds.clear();
+  for (int p = 1; p < n_parts; p++)
+    if (!parts[p - 1].index.empty()) CU(cudaStreamWaitEvent(L.st, L.ev_join[p - 1], 0));
   CU(cudaGetLastError());
   CU(cudaEventRecord(L.ev[5], L.st));
   double scan_elems = 0;
@@ -771,7 +880,9 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   CU(cudaEventElapsedTime(&t0, h->base_ev, L.ev[4]));
   L.tm.em_ms += ms;
   L.busy.emplace_back(t0, t0 + ms);
-  for (const EmStepEvents* ee : {&L.em_events, &L.em_events2}) {
+  for (int p = 1; p < kMaxSplit; p++)
+    if (p >= n_parts) L.em_events_part[p - 1].kinds.clear();
+  for (const EmStepEvents* ee : {&L.em_events, &L.em_events2, &L.em_events_part[0], &L.em_events_part[1], &L.em_events_part[2]}) {
     double e_ms = 0, s_ms = 0;
     em_steps_elapsed(*ee, &e_ms, &s_ms);
     L.tm.estep_ms += e_ms;
@@ -975,6 +1086,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         for (int t = 0; t < d.T; t++) win += std::min(d.T - 1, t + half) - std::max(0, t - half) + 1;
       }
       L.tm.tensor_exp += double(d.N) * win;
+      L.tm.table_exp += double(d.N) * d.T * P.n_s;
     }
     return 0;
   };
@@ -1414,7 +1526,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
     const scape_b200_timing& t = h->lanes[l].tm;
     h->tm.table_ms += t.table_ms; h->tm.tensor_ms += t.tensor_ms; h->tm.em_ms += t.em_ms; h->tm.label_ms += t.label_ms;
     h->tm.host_rng_ms += t.host_rng_ms; h->tm.launches += t.launches; h->tm.waves += t.waves;
-    h->tm.em_grid_bytes += t.em_grid_bytes; h->tm.em_grid_flops += t.em_grid_flops; h->tm.tensor_exp += t.tensor_exp;
+    h->tm.em_grid_bytes += t.em_grid_bytes; h->tm.em_grid_flops += t.em_grid_flops; h->tm.tensor_exp += t.tensor_exp; h->tm.table_exp += t.table_exp;
     h->tm.h2d_bytes += t.h2d_bytes; h->tm.d2h_bytes += t.d2h_bytes; h->tm.em_scan_bytes += t.em_scan_bytes;
     h->tm.estep_ms += t.estep_ms; h->tm.scan_ms += t.scan_ms; h->tm.scan_launches += t.scan_launches;
     h->tm.resident_ms += t.resident_ms; h->tm.resident_launches += t.resident_launches; h->tm.resident_grid_flops += t.resident_grid_flops;

@@ -82,15 +82,22 @@ __global__ void __launch_bounds__(256) table_kernel(const UtrDev* __restrict__ u
       }
       out = (log(acc) + mx) - log(mass);
     } else {
-      // loglik_xlr_t_r_unknown_kernel (taichi_core.py:141-157)
-      const double inv_span = fits ? 1.0 / span : 0.0;
-      double acc = 0.0;
-      for (int j = 0; j < c_mc.n_s; j++) {
-        const double s = c_mc.s_dis[j];
-        acc += 1.0 / s * pdf_normal(x, th + s - mu_f, sigma_f) * inv_span * c_mc.pmf_s[j];
+      // loglik_xlr_t_r_unknown_kernel (taichi_core.py:141-157).  A read that does not fit (l > theta - x)
+      // has lik_l_xt = 0: every term of the sum is exactly +0, the sum is 0 < 1e-300 and the entry is
+      // the sentinel -- 71-74 % of all entries, decided here without the 13 exp (fragments are sorted
+      // by x, so whole warps take the same side).
+      if (!fits) {
+        out = SCAPE_SENTINEL;
+      } else {
+        const double inv_span = 1.0 / span;
+        double acc = 0.0;
+        for (int j = 0; j < c_mc.n_s; j++) {
+          const double s = c_mc.s_dis[j];
+          acc += 1.0 / s * pdf_normal(x, th + s - mu_f, sigma_f) * inv_span * c_mc.pmf_s[j];
+        }
+        if (acc < 1e-300) acc = 0.0;
+        out = (acc <= 0.0) ? SCAPE_SENTINEL : log(acc);
       }
-      if (acc < 1e-300) acc = 0.0;
-      out = (acc <= 0.0) ? SCAPE_SENTINEL : log(acc);
     }
   }
   table[u.table_off + (int64_t)rr.t * u.Npad + n] = out;
@@ -1132,6 +1139,103 @@ __global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters, 
 #pragma unroll
   for (int i = 0; i < 8; i++) s += d[i][0] + d[i][1];
   if (s == 12345.678) out[0] = s;
+}
+
+// FP32 FMA, MUFU (ex2.approx) and FP64 exp() / log() streams: the denominators of the likelihood
+// phases (theta table: 13 exp per entry; marginal tensor: 307 exp per (fragment, alpha) in the
+// reference) -- BASELINE.md section 3 asks for them, MEASURED_PEAKS.json does not have them.
+__global__ void __launch_bounds__(256) peak_ffma_kernel(float* out, int iters, float seed) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = seed + threadIdx.x * 1e-6f + i;
+  const float m = 1.0000001f, c = 1e-7f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i];
+  if (s == 12345.678f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) peak_mufu_kernel(float* out, int iters, float seed) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = seed * 0.01f + threadIdx.x * 1e-6f + 0.1f * i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));   // stays in [1, 2) after one step: 2^x - ... bounded
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] -= 1.0f;                                                 // back into [0, 1): one FADD per MUFU
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i];
+  if (s == 12345.678f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) peak_exp64_kernel(double* out, int iters, double seed) {
+  double a[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = seed + threadIdx.x * 1e-9 + 0.1 * i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = exp(a[i] - 1.0);      // fixed point 1: arguments stay in exp()'s main path
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) s += a[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) peak_log64_kernel(double* out, int iters, double seed) {
+  double a[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = seed + threadIdx.x * 1e-9 + 0.1 * i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = log(a[i] + 2.0);      // fixed point ~1.146
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) s += a[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+// out[0..3] = FP32 FMA TFLOP/s, MUFU ex2 Gop/s, FP64 exp() Gop/s, FP64 log() Gop/s
+int measure_sfu_peaks(int n_sm, double* out, cudaStream_t st) {
+  void* buf = nullptr;
+  if (cudaMalloc(&buf, 64) != cudaSuccess) return -1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = n_sm * 8;
+  auto timed = [&](int which, int iters) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0, st);
+      if (which == 0) peak_ffma_kernel<<<grid, 256, 0, st>>>((float*)buf, iters, 1.0f);
+      else if (which == 1) peak_mufu_kernel<<<grid, 256, 0, st>>>((float*)buf, iters, 1.0f);
+      else if (which == 2) peak_exp64_kernel<<<grid, 256, 0, st>>>((double*)buf, iters, 1.0);
+      else peak_log64_kernel<<<grid, 256, 0, st>>>((double*)buf, iters, 1.0);
+      cudaEventRecord(e1, st);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep) best = std::min(best, ms);
+    }
+    return double(best) * 1e-3;
+  };
+  const double threads = double(grid) * 256.0;
+  out[0] = 2.0 * threads * 8.0 * (1 << 14) / timed(0, 1 << 14) / 1e12;
+  out[1] = threads * 8.0 * (1 << 13) / timed(1, 1 << 13) / 1e9;
+  out[2] = threads * 4.0 * (1 << 10) / timed(2, 1 << 10) / 1e9;
+  out[3] = threads * 4.0 * (1 << 10) / timed(3, 1 << 10) / 1e9;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // returns FP64 TFLOP/s (2 flop per FMA) of CUDA-core DFMA and tensor-core DMMA streams

@@ -148,6 +148,7 @@ struct EmStepEvents {
 };
 void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms);
 int measure_fp64_peaks(int n_sm, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
+int measure_sfu_peaks(int n_sm, double* out4, cudaStream_t st);   // FP32 FMA TFLOP/s, MUFU ex2 Gop/s, FP64 exp Gop/s, FP64 log Gop/s
 constexpr int kWarpEstepMaxN = 384;    // UTRs with at most this many fragments use the warp-per-chain E step (a warp needs ~4 us per 32 fragments: above this the launch is bound by its longest warp)
 // How the E step is launched.  Runs of weights-only chains (prune refits) always use the group
 // kernel (g_small warps per chain for the chains with few fragments, a whole CTA for the others;
