@@ -100,10 +100,12 @@ struct StagedBufs {
   DevBuf<UtrDev> d_utrs;
   DevBuf<RowRef> d_rows, d_trows;
   DevBuf<TileRef> d_tiles;
+  DevBuf<int32_t> d_r2b;                             // read -> fragment map of the wave's UTRs (label expansion)
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // before table, before tensor, after tensor
   void release() {
     d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
     d_table.release(); d_tensor.release(); d_utrs.release(); d_rows.release(); d_trows.release(); d_tiles.release();
+    d_r2b.release();
   }
 };
 
@@ -122,7 +124,9 @@ struct Lane {
   DevBuf<RowRef> d_rows, d_trows;
   DevBuf<TileRef> d_tiles;
   DevBuf<ChainDev> d_chains;
-  DevBuf<int32_t> d_labels, d_trace_a, d_trace_b;
+  DevBuf<int32_t> d_labels, d_trace_a, d_trace_b, d_r2b;
+  DevBuf<int64_t> d_labels64;           // per-read labels of the wave (label_expand_kernel)
+  PinnedBuf<int64_t> h_labels64;
   DevBuf<ScanRef> d_refs;
   DevBuf<ClusterJob> d_cjobs;
   DevBuf<long long> d_clstats;
@@ -132,6 +136,7 @@ struct Lane {
   DevBuf<double> d_partials, d_counter;
   DevBuf<LabelDev> d_jobs;
   PinnedBuf<ChainDev> h_chains, h_refits;
+  PinnedBuf<LabelDev> h_jobs;
   cudaEvent_t ev[8];
   EmStepEvents em_events, em_events2;   // bulk-synchronous runs: all steps / the head of the tail route
   EmStepEvents em_events_part[3];       // parts 2..4 of a split wave
@@ -143,11 +148,11 @@ struct Lane {
   void release() {
     d_fx.release(); d_fl.release(); d_fr.release(); d_fpa.release(); d_cnt.release(); d_theta.release();
     d_table.release(); d_tensor.release(); d_lz.release(); d_trace_ws.release(); d_utrs.release();
-    d_rows.release(); d_trows.release(); d_tiles.release(); d_chains.release(); d_labels.release(); d_trace_a.release(); d_trace_b.release();
+    d_rows.release(); d_trows.release(); d_tiles.release(); d_chains.release(); d_labels.release(); d_r2b.release(); d_labels64.release(); h_labels64.release(); d_trace_a.release(); d_trace_b.release();
     d_refs.release(); d_cjobs.release(); d_clstats.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_lists.release(); d_counts.release();
     d_counter.release(); d_jobs.release();
-    h_chains.release(); h_refits.release(); h_runmeta.release();
+    h_chains.release(); h_refits.release(); h_runmeta.release(); h_jobs.release();
     h_stage[0].release(); h_stage[1].release();
     staged.release();
   }
@@ -157,6 +162,7 @@ struct Lane {
     std::swap(d_fpa, staged.d_fpa); std::swap(d_cnt, staged.d_cnt); std::swap(d_theta, staged.d_theta);
     std::swap(d_table, staged.d_table); std::swap(d_tensor, staged.d_tensor); std::swap(d_utrs, staged.d_utrs);
     std::swap(d_rows, staged.d_rows); std::swap(d_trows, staged.d_trows); std::swap(d_tiles, staged.d_tiles);
+    std::swap(d_r2b, staged.d_r2b);
     for (int i = 0; i < 3; i++) std::swap(ev[i], staged.ev[i]);
   }
 };
@@ -543,9 +549,17 @@ int build_step_set(scape_b200_handle* h, const Chains& chains, const std::vector
 
 // Upload chains, run them to convergence, bring them back.  `utrs_host` is the wave's UtrDev array;
 // chains must be ordered by UTR (they are generated that way).
+// `enqueued` (optional) runs on the host after every launch and the download have been enqueued and
+// before the stream is synchronised: host work that hides under the run, or more work for the stream.
 int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chains, const std::vector<UtrDev>& utrs_host,
-               bool want_trace = false) {
-  if (n_chains == 0) return 0;
+               bool want_trace = false, const std::function<int()>& enqueued = nullptr) {
+  if (n_chains == 0) {                 // nothing to run: the caller's follow-up work still gets its synchronisation
+    if (enqueued) {
+      if (int rc = enqueued()) return rc;
+      CU(cudaStreamSynchronize(L.st));
+    }
+    return 0;
+  }
   struct Span {
     ChainDev* p; size_t n;
     size_t size() const { return n; }
@@ -873,6 +887,8 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   double scan_elems = 0;
   CU(cudaMemcpyAsync(chains.data(), L.d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, L.st));
   CU(cudaMemcpyAsync(&scan_elems, L.d_counter.p, sizeof(double), cudaMemcpyDeviceToHost, L.st));
+  if (enqueued)
+    if (int rc = enqueued()) { cudaStreamSynchronize(L.st); return rc; }
   CU(cudaStreamSynchronize(L.st));
   L.tm.d2h_bytes += double(sizeof(ChainDev) * chains.size());
   float ms = 0, t0 = 0;
@@ -982,7 +998,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     const size_t W = st_wave.size();
     std::vector<UtrDev>& ud = st_ud;
     ud.resize(W);
-    int64_t nf = 0, nt = 0, ntab = 0, nten = 0, n_rows = 0, n_trows = 0, n_tiles = 0;
+    int64_t nf = 0, nt = 0, ntab = 0, nten = 0, n_rows = 0, n_trows = 0, n_tiles = 0, nr = 0;
     int max_n = 0;
     const int i_lo = kTfHalf;
     for (size_t i = 0; i < W; i++) {
@@ -991,6 +1007,8 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       d.N = int32_t(p.n()); d.Npad = pad4(p.n()); d.T = int32_t(p.T()); d.B = int32_t(p.B());
       d.ldR = pad4(int64_t(d.T) * d.B);
       d.frag_off = nf; d.theta_off = nt; d.table_off = ntab; d.tensor_off = nten;
+      d.n_reads = int32_t(p.n_reads); d.pad_ = 0; d.read_off = nr;
+      nr += p.n_reads;
       d.unif_loglik = p.unif_loglik;
       nf += d.Npad; nt += d.T; ntab += int64_t(d.T) * d.Npad; nten += d.ldR * d.N;
       max_n = std::max(max_n, d.Npad);
@@ -1011,7 +1029,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
            o_th = o_c + up16(fb), o_ud = o_th + up16(8 * size_t(nt)), o_rows = o_ud + up16(sizeof(UtrDev) * W),
            o_trows = o_rows + up16(sizeof(RowRef) * size_t(n_rows)),
            o_tiles = o_trows + up16(sizeof(RowRef) * size_t(n_trows)),
-           o_end = o_tiles + up16(sizeof(TileRef) * size_t(n_tiles));
+           o_r2b = o_tiles + up16(sizeof(TileRef) * size_t(n_tiles)), o_end = o_r2b + up16(sizeof(int32_t) * size_t(nr));
     CU(blob.resize(o_end));
     double *hx = (double*)(blob.p + o_x), *hl = (double*)(blob.p + o_l), *hr = (double*)(blob.p + o_r),
            *hpa = (double*)(blob.p + o_pa), *hc = (double*)(blob.p + o_c), *hth = (double*)(blob.p + o_th);
@@ -1030,6 +1048,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         std::copy(p.pa.begin(), p.pa.end(), hpa + d.frag_off);
         std::copy(p.cnt.begin(), p.cnt.end(), hc + d.frag_off);
         std::copy(p.theta.begin(), p.theta.end(), hth + d.theta_off);
+        std::copy(p.read_to_bin.begin(), p.read_to_bin.end(), (int32_t*)(blob.p + o_r2b) + d.read_off);
         hud[i] = d;
         const int i_hi = d.T - 1 - kTfHalf;
         for (int t = 0; t < d.T; t++) rows[ir++] = {int32_t(i), t};
@@ -1050,6 +1069,9 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     CU(cudaMemsetAsync((char*)S.d_tensor.p + size_t(nten) * esz, 0, size_t(slack) * esz, sq));
     CU(S.d_utrs.ensure(W)); CU(S.d_rows.ensure(size_t(n_rows)));
     CU(S.d_trows.ensure(size_t(n_trows) + 1)); CU(S.d_tiles.ensure(size_t(n_tiles) + 1));
+    CU(S.d_r2b.ensure(size_t(nr) + 1));
+    if (nr > 0) CU(cudaMemcpyAsync(S.d_r2b.p, blob.p + o_r2b, sizeof(int32_t) * size_t(nr), cudaMemcpyHostToDevice, sq));
+    L.tm.h2d_bytes += double(sizeof(int32_t) * size_t(nr));
     CU(cudaMemcpyAsync(S.d_fx.p, hx, fb, cudaMemcpyHostToDevice, sq));
     CU(cudaMemcpyAsync(S.d_fl.p, hl, fb, cudaMemcpyHostToDevice, sq));
     CU(cudaMemcpyAsync(S.d_fr.p, hr, fb, cudaMemcpyHostToDevice, sq));
@@ -1160,6 +1182,28 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
   int predraw_rc = 0;
   double predraw_ms = 0;
 
+  // development aid (SCAPE_B200_DBG_HOST=1): wall clock of the wave loop's sections
+  static const bool host_dbg = getenv("SCAPE_B200_DBG_HOST") != nullptr;
+  double hp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double hp_mark = now_ms();
+  auto lap = [&](int k) { const double t = now_ms(); hp[k] += t - hp_mark; hp_mark = t; };
+  struct HostProfile {
+    const bool on; double* hp; int64_t* waves;
+    ~HostProfile() {
+      if (on)
+        fprintf(stderr, "host wall per wave (us): draw %.0f | EM run_chains (incl. GPU wait) %.0f | select+refit draws %.0f | refit run %.0f | "
+                        "labels launch+wait %.0f | assemble+expand %.0f | stage/predraw join %.0f  (%lld waves)\n",
+                1e3 * hp[0] / double(std::max<int64_t>(*waves, 1)), 1e3 * hp[1] / double(std::max<int64_t>(*waves, 1)),
+                1e3 * hp[2] / double(std::max<int64_t>(*waves, 1)), 1e3 * hp[3] / double(std::max<int64_t>(*waves, 1)),
+                1e3 * hp[4] / double(std::max<int64_t>(*waves, 1)), 1e3 * hp[5] / double(std::max<int64_t>(*waves, 1)),
+                1e3 * hp[6] / double(std::max<int64_t>(*waves, 1)), (long long)*waves);
+    }
+  } host_profile{host_dbg, hp, &L.tm.waves};
+  std::function<void()> pending_assemble;     // deferred result assembly of the previous wave
+  struct FlushPending {
+    std::function<void()>& f;
+    ~FlushPending() { if (f) f(); }
+  } flush_pending{pending_assemble};
   if (int rc = stage()) return rc;
   for (;;) {
     if (st_wave.empty()) break;
@@ -1180,6 +1224,8 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     }
     bool timed_lik = false;
 
+    std::vector<LabelDev> jobs;
+    bool labels_enqueued = false, final_sweep = false;
     // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
     for (;;) {
       double tr0 = now_ms();
@@ -1192,6 +1238,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       }
       ChainDev* chains = L.h_chains.p;
       L.tm.host_rng_ms += now_ms() - tr0;
+      lap(0);
       if (n_chains == 0) break;
       if (overlap && !next_staged) {
         L.em_events.hook_step = std::min(L.stage_step, SCAPE_B200_NROUND - 1);
@@ -1205,12 +1252,16 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         };
       }
       {
-        const int rc = run_chains(h, L, chains, n_chains, ud);
+        // the previous wave's results are written out while the GPU runs this wave's EM
+        std::function<int()> cb;
+        if (pending_assemble) cb = [&]() { pending_assemble(); pending_assemble = nullptr; return 0; };
+        const int rc = run_chains(h, L, chains, n_chains, ud, false, cb);
         L.em_events.hook = nullptr;
         L.em_events.mark = nullptr;
         if (rc) return rc;
         if (stage_rc) return stage_rc;
       }
+      lap(1);
       if (!timed_lik) {
         float a = 0, b = 0;
         CU(cudaEventElapsedTime(&a, L.ev[0], L.ev[1]));
@@ -1292,6 +1343,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         for (size_t i = 0; i < W; i++)
           if (!wave[i].done && !need_refit[i] && !P.fixed_run_mode && P.re_run_mode && wave[i].best.K == wave[i].k_max)
             any_rerun = true;
+        final_sweep = !any_rerun;
         if (predraw_on && !any_rerun && next_staged && !st_wave.empty() && !predraw_thread.joinable()) {
           predraw_thread = std::thread([&]() {
             const double t0 = now_ms();
@@ -1300,9 +1352,54 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
           });
         }
       }
-      if (int rc = run_chains(h, L, refits, n_refits, ud)) {
-        if (predraw_thread.joinable()) predraw_thread.join();
-        return rc;
+      lap(2);
+      // ---- labels (get_label :873-881) + per-read expansion (:976), enqueued right behind the prune refits
+      // when this is the last sweep of the wave: the label kernel takes a refitted UTR's parameters
+      // from the refit's device record, so refits + labels cost ONE stream synchronisation
+      auto enqueue_labels = [&]() -> int {
+        std::vector<int32_t> refit_of(W, -1);
+        for (size_t j = 0; j < n_refits; j++) refit_of[refit_owner[j]] = int32_t(j);
+        jobs.assign(W, LabelDev{});
+        int64_t nl = 0;
+        int max_reads = 0;
+        for (size_t i = 0; i < W; i++) {
+          LabelDev& j = jobs[i];
+          memset(&j, 0, sizeof(j));
+          j.utr = int32_t(i); j.K = wave[i].best.K; j.out_off = nl; j.chain = refit_of[i];
+          memcpy(j.a_idx, wave[i].best.a_idx, sizeof(j.a_idx));
+          memcpy(j.b_idx, wave[i].best.b_idx, sizeof(j.b_idx));
+          memcpy(j.ws, wave[i].best.ws, sizeof(j.ws));
+          nl += ud[i].N;
+          max_reads = std::max(max_reads, int(ud[i].n_reads));
+        }
+        const int64_t n_reads_wave = W ? ud[W - 1].read_off + ud[W - 1].n_reads : 0;
+        CU(L.d_jobs.ensure(W));
+        CU(L.d_labels.ensure(size_t(nl) + 1));
+        CU(L.d_labels64.ensure(size_t(n_reads_wave) + 1));
+        CU(L.h_labels64.resize(size_t(n_reads_wave) + 1));
+        CU(L.h_jobs.resize(W));
+        std::copy(jobs.begin(), jobs.end(), L.h_jobs.p);
+        CU(cudaMemcpyAsync(L.d_jobs.p, L.h_jobs.p, sizeof(LabelDev) * W, cudaMemcpyHostToDevice, L.st));
+        CU(cudaEventRecord(L.ev[6], L.st));
+        launch_labels(L.d_jobs.p, int64_t(W), max_n, L.d_utrs.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_chains.p,
+                      L.d_labels.p, L.st);
+        launch_label_expand(L.d_jobs.p, int64_t(W), max_reads, L.d_utrs.p, L.d_labels.p, L.d_r2b.p, L.d_labels64.p, L.st);
+        CU(cudaEventRecord(L.ev[7], L.st));
+        CU(cudaGetLastError());
+        if (n_reads_wave > 0)
+          CU(cudaMemcpyAsync(L.h_labels64.p, L.d_labels64.p, sizeof(int64_t) * size_t(n_reads_wave), cudaMemcpyDeviceToHost, L.st));
+        L.tm.launches += 2;
+        L.tm.h2d_bytes += double(sizeof(LabelDev) * W);
+        L.tm.d2h_bytes += double(sizeof(int64_t) * size_t(n_reads_wave));
+        labels_enqueued = true;
+        return 0;
+      };
+      {
+        const std::function<int()> cb = final_sweep ? std::function<int()>(enqueue_labels) : std::function<int()>();
+        if (int rc = run_chains(h, L, refits, n_refits, ud, false, cb)) {
+          if (predraw_thread.joinable()) predraw_thread.join();
+          return rc;
+        }
       }
       for (size_t j = 0; j < n_refits; j++) {
         WaveUtr& w = wave[refit_owner[j]];
@@ -1328,35 +1425,16 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
           w.done = true;
         }
       }
-      if (!again) break;
+      if (!again) {
+        if (!labels_enqueued) {         // (a sweep that expected a re-run and got none, e.g. K hit SCAPE_B200_KCAP)
+          n_refits = 0;                 // every refit result is already in wave[i].best
+          if (int rc = enqueue_labels()) return rc;
+          CU(cudaStreamSynchronize(L.st));
+        }
+        break;
+      }
     }
-
-    // ---- labels (get_label :873-881) + per-read expansion (:976) --------------------------------
-    std::vector<LabelDev> jobs(W);
-    int64_t nl = 0;
-    for (size_t i = 0; i < W; i++) {
-      LabelDev& j = jobs[i];
-      memset(&j, 0, sizeof(j));
-      j.utr = int32_t(i); j.K = wave[i].best.K; j.out_off = nl;
-      memcpy(j.a_idx, wave[i].best.a_idx, sizeof(j.a_idx));
-      memcpy(j.b_idx, wave[i].best.b_idx, sizeof(j.b_idx));
-      memcpy(j.ws, wave[i].best.ws, sizeof(j.ws));
-      nl += ud[i].N;
-    }
-    CU(L.d_jobs.ensure(W));
-    CU(L.d_labels.ensure(size_t(nl)));
-    CU(cudaMemcpyAsync(L.d_jobs.p, jobs.data(), sizeof(LabelDev) * W, cudaMemcpyHostToDevice, L.st));
-    CU(cudaEventRecord(L.ev[6], L.st));
-    launch_labels(L.d_jobs.p, int64_t(W), max_n, L.d_utrs.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p, L.d_labels.p,
-                L.st);
-    CU(cudaEventRecord(L.ev[7], L.st));
-    CU(cudaGetLastError());
-    L.tm.launches += 1;
-    std::vector<int32_t> lab(static_cast<size_t>(nl));
-    CU(cudaMemcpyAsync(lab.data(), L.d_labels.p, sizeof(int32_t) * size_t(nl), cudaMemcpyDeviceToHost, L.st));
-    CU(cudaStreamSynchronize(L.st));
-    L.tm.h2d_bytes += double(sizeof(LabelDev) * W);
-    L.tm.d2h_bytes += double(sizeof(int32_t) * size_t(nl));
+    lap(3);
     {
       float a = 0;
       CU(cudaEventElapsedTime(&a, L.ev[6], L.ev[7]));
@@ -1365,27 +1443,39 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       CU(cudaEventElapsedTime(&tb, h->base_ev, L.ev[6]));
       L.busy.emplace_back(tb, tb + a);
     }
-    for (size_t i = 0; i < W; i++) {
-      const WaveUtr& w = wave[i];
-      const UtrPrep& p = prep[size_t(w.u)];
-      const int64_t u = w.u;
-      const ChainDev& c = w.best;
-      out->K[u] = c.K;
-      for (int k = 0; k < c.K; k++) {
-        out->alpha[u * SCAPE_B200_KCAP + k] = std::nearbyint(p.theta[size_t(c.a_idx[k])]);   // np.rint (:770)
-        out->beta[u * SCAPE_B200_KCAP + k] = p.betas[size_t(c.b_idx[k])];
+    lap(4);
+    // ---- results: assembled on the host while the GPU runs the next wave's EM (or at the end) ---------
+    {
+      std::shared_ptr<std::vector<WaveUtr>> wv = std::make_shared<std::vector<WaveUtr>>(std::move(wave));
+      std::shared_ptr<std::vector<UtrDev>> udv = std::make_shared<std::vector<UtrDev>>(ud);
+      // the per-read labels leave the pinned download buffer now (the next wave's download reuses it);
+      // everything else is copied out of the wave records later
+      for (size_t i = 0; i < W; i++) {
+        const int64_t u = (*wv)[i].u;
+        memcpy(out->label + bt->read_off[u], L.h_labels64.p + (*udv)[i].read_off, sizeof(int64_t) * size_t((*udv)[i].n_reads));
       }
-      for (int k = 0; k <= c.K; k++) out->ws[u * (SCAPE_B200_KCAP + 1) + k] = c.ws[k];
-      out->bic[u] = c.bic;
-      out->n_lb[u] = c.n_iter;
-      for (int k = 0; k < c.n_iter; k++) out->lb_arr[u * SCAPE_B200_NROUND + k] = c.lb_arr[k];
-      out->path[u * 4 + 0] = w.sweeps; out->path[u * 4 + 1] = w.k_selected;
-      out->path[u * 4 + 2] = c.K; out->path[u * 4 + 3] = w.chains_run;
-      out->em_work[u * 2] = w.work; out->em_work[u * 2 + 1] = w.iters;
-      const int32_t* lb = lab.data() + jobs[i].out_off;
-      int64_t* dst = out->label + bt->read_off[u];
-      for (int64_t r = 0; r < p.n_reads; r++) dst[r] = lb[p.read_to_bin[size_t(r)]];
+      pending_assemble = [&prep, out, wv]() {
+        for (size_t i = 0; i < wv->size(); i++) {
+          const WaveUtr& w = (*wv)[i];
+          const UtrPrep& p = prep[size_t(w.u)];
+          const int64_t u = w.u;
+          const ChainDev& c = w.best;
+          out->K[u] = c.K;
+          for (int k = 0; k < c.K; k++) {
+            out->alpha[u * SCAPE_B200_KCAP + k] = std::nearbyint(p.theta[size_t(c.a_idx[k])]);   // np.rint (:770)
+            out->beta[u * SCAPE_B200_KCAP + k] = p.betas[size_t(c.b_idx[k])];
+          }
+          for (int k = 0; k <= c.K; k++) out->ws[u * (SCAPE_B200_KCAP + 1) + k] = c.ws[k];
+          out->bic[u] = c.bic;
+          out->n_lb[u] = c.n_iter;
+          for (int k = 0; k < c.n_iter; k++) out->lb_arr[u * SCAPE_B200_NROUND + k] = c.lb_arr[k];
+          out->path[u * 4 + 0] = w.sweeps; out->path[u * 4 + 1] = w.k_selected;
+          out->path[u * 4 + 2] = c.K; out->path[u * 4 + 3] = w.chains_run;
+          out->em_work[u * 2] = w.work; out->em_work[u * 2 + 1] = w.iters;
+        }
+      };
     }
+    lap(5);
     if (predraw_thread.joinable()) {
       predraw_thread.join();
       if (predraw_rc) return predraw_rc;
@@ -1394,6 +1484,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     }
     if (!next_staged)
       if (int rc = stage()) return rc;
+    lap(6);
   }
   return 0;
 }

@@ -1278,21 +1278,27 @@ template <typename TT>
 __global__ void __launch_bounds__(256) label_kernel(const LabelDev* __restrict__ jobs,
                                                     const UtrDev* __restrict__ utrs,
                                                     const TT* __restrict__ tensor,
-                                                    const double* __restrict__ cnt, int32_t* __restrict__ labels) {
+                                                    const double* __restrict__ cnt, const ChainDev* __restrict__ chains,
+                                                    int32_t* __restrict__ labels) {
   const LabelDev& jb = jobs[blockIdx.x];
   const UtrDev u = utrs[jb.utr];
   const int n = blockIdx.y * blockDim.x + threadIdx.x;
   if (n >= u.N) return;
-  const int K = jb.K;
+  // final parameters: inline, or the record of a prune refit that ran just before on this stream
+  const ChainDev* src = jb.chain >= 0 ? chains + jb.chain : nullptr;
+  const int K = src ? src->K : jb.K;
+  const int32_t* a_idx = src ? src->a_idx : jb.a_idx;
+  const int32_t* b_idx = src ? src->b_idx : jb.b_idx;
+  const double* ws = src ? src->ws : jb.ws;
   const double c = cnt[u.frag_off + n];
   double lzv[SCAPE_B200_KCAP + 1];
   double m = -CUDART_INF;
   for (int j = 0; j <= K; j++) {
-    const double w = jb.ws[j];
+    const double w = ws[j];
     const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
     double val;
     if (j < K)
-      val = lw + (double)tensor[u.tensor_off + (int64_t)n * u.ldR + (int64_t)jb.a_idx[j] * u.B + jb.b_idx[j]];
+      val = lw + (double)tensor[u.tensor_off + (int64_t)n * u.ldR + (int64_t)a_idx[j] * u.B + b_idx[j]];
     else
       val = lw + u.unif_loglik;
     lzv[j] = val;
@@ -1313,13 +1319,31 @@ __global__ void __launch_bounds__(256) label_kernel(const LabelDev* __restrict__
 }
 
 void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
-                   const double* cnt, int32_t* labels, cudaStream_t st) {
+                   const double* cnt, const ChainDev* chains, int32_t* labels, cudaStream_t st) {
   if (n_jobs <= 0) return;
   dim3 grid((unsigned)n_jobs, (unsigned)((max_n + 255) / 256));
   if (f32)
-    label_kernel<float><<<grid, 256, 0, st>>>(jobs, utrs, (const float*)tensor, cnt, labels);
+    label_kernel<float><<<grid, 256, 0, st>>>(jobs, utrs, (const float*)tensor, cnt, chains, labels);
   else
-    label_kernel<double><<<grid, 256, 0, st>>>(jobs, utrs, (const double*)tensor, cnt, labels);
+    label_kernel<double><<<grid, 256, 0, st>>>(jobs, utrs, (const double*)tensor, cnt, chains, labels);
+}
+
+// label_arr = label_arr_of_the_bins[idx_arr] (apa_core.py:976): per read, int64 like the reference's array
+__global__ void __launch_bounds__(256) label_expand_kernel(const LabelDev* __restrict__ jobs, const UtrDev* __restrict__ utrs,
+                                                           const int32_t* __restrict__ labels,
+                                                           const int32_t* __restrict__ read_to_bin,
+                                                           int64_t* __restrict__ out) {
+  const LabelDev& jb = jobs[blockIdx.x];
+  const UtrDev u = utrs[jb.utr];
+  for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < u.n_reads; r += gridDim.y * blockDim.x)
+    out[u.read_off + r] = (int64_t)labels[jb.out_off + read_to_bin[u.read_off + r]];
+}
+
+void launch_label_expand(const LabelDev* jobs, int64_t n_jobs, int max_reads, const UtrDev* utrs, const int32_t* labels,
+                         const int32_t* read_to_bin, int64_t* labels_per_read, cudaStream_t st) {
+  if (n_jobs <= 0) return;
+  dim3 grid((unsigned)n_jobs, (unsigned)std::min(64, (max_reads + 255) / 256));
+  label_expand_kernel<<<grid, 256, 0, st>>>(jobs, utrs, labels, read_to_bin, labels_per_read);
 }
 
 }  // namespace scape

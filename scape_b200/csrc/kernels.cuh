@@ -35,6 +35,8 @@ namespace scape {
 
 struct UtrDev {
   int32_t N, Npad, T, B;
+  int32_t n_reads, pad_;          // raw reads of the UTR (label expansion)
+  int64_t read_off;               // into the wave's read -> fragment map and per-read label buffer
   int64_t ldR;                    // pitch of the tensor: T*B candidate rows rounded up to 4 (16-byte aligned TMA rows)
   int64_t frag_off;
   int64_t theta_off;
@@ -100,6 +102,8 @@ struct LabelDev {
   int32_t utr;
   int32_t K;
   int64_t out_off;                // into the label buffer (per fragment)
+  int32_t chain;                  // >= 0: take K, alpha, beta, ws from this record of the device chain array (a refit that has just run)
+  int32_t pad_;
   int32_t a_idx[SCAPE_B200_KCAP];
   int32_t b_idx[SCAPE_B200_KCAP];
   double ws[SCAPE_B200_KCAP + 1];
@@ -127,7 +131,10 @@ void launch_table(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int ma
 void launch_tensor(const UtrDev* utrs, const RowRef* rows, int64_t n_rows, int max_n, int n_beta, int max_win,
                    const double* theta, const double* table, void* tensor, bool f32, cudaStream_t st);
 void launch_labels(const LabelDev* jobs, int64_t n_jobs, int max_n, const UtrDev* utrs, const void* tensor, bool f32,
-                   const double* cnt, int32_t* labels, cudaStream_t st);
+                   const double* cnt, const ChainDev* chains, int32_t* labels, cudaStream_t st);
+// label_arr = labels of the fragments expanded by idx_arr (apa_core.py:976): one thread per read
+void launch_label_expand(const LabelDev* jobs, int64_t n_jobs, int max_reads, const UtrDev* utrs, const int32_t* labels,
+                         const int32_t* read_to_bin, int64_t* labels_per_read, cudaStream_t st);
 cudaError_t upload_model_const(const ModelConst& mc);
 constexpr int kTensorSlackRows = 64;   // zeroed fragment rows after the last UTR's tensor: the scan's register ring prefetches past the hull
 constexpr int kScanRows = 256;    // candidate rows per scan CTA (must equal SCAN_ROWS in kernels.cu)
