@@ -123,7 +123,7 @@ class ChunkBatch:
             self.stream.append(stream)
             pos += n
 
-    _layouts: dict = {}       # column names -> (positions of x, l, r, pa, cb_id, read_id; dtypes of the two ids)
+    _layouts: dict = {}       # (column names, dtypes) -> (positions of x, l, r, pa, cb_id, read_id; dtypes of the two ids)
 
     @classmethod
     def _columns_fast(cls, df):
@@ -134,7 +134,13 @@ class ChunkBatch:
         Integer ids come back exactly (checked: integral and below 2**53), otherwise the caller falls
         back to the column-by-column path."""
         try:
-            key = tuple(df.columns.values)
+            # the layout is keyed by column names AND dtypes: a later frame whose ids have another dtype
+            # (e.g. float ids with NaN after int ids) gets its own entry instead of the first frame's
+            try:
+                dkey = tuple(df._mgr.get_dtypes())      # 5 us; df.dtypes costs 45 us per frame
+            except AttributeError:                      # pandas without the block-manager accessor
+                dkey = tuple(df.dtypes)
+            key = (tuple(df.columns.values), dkey)
             lay = cls._layouts.get(key)
             if lay is None:
                 loc = [df.columns.get_loc(n) for n in ("x", "l", "r", "pa", "cb_id", "read_id")]

@@ -553,6 +553,8 @@ int build_step_set(scape_b200_handle* h, const Chains& chains, const std::vector
 // before the stream is synchronised: host work that hides under the run, or more work for the stream.
 int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chains, const std::vector<UtrDev>& utrs_host,
                bool want_trace = false, const std::function<int()>& enqueued = nullptr) {
+  static const bool host_dbg_rc = getenv("SCAPE_B200_DBG_HOST") != nullptr;
+  const double t_rc0 = now_ms();
   if (n_chains == 0) {                 // nothing to run: the caller's follow-up work still gets its synchronisation
     if (enqueued) {
       if (int rc = enqueued()) return rc;
@@ -750,13 +752,22 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   CU(cudaMemsetAsync(L.d_counter.p, 0, sizeof(double), L.st));
   L.tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * n_refs + 4 * (W + 1) + 4 * n_index);
   CU(cudaEventRecord(L.ev[4], L.st));
+  const double t_rc1 = now_ms();
+  {
+    // per-step events only where somebody reads them (un-pipelined passes, SCAPE_B200_STEP_EVENTS=1)
+    static const int ev_env = getenv("SCAPE_B200_STEP_EVENTS") ? atoi(getenv("SCAPE_B200_STEP_EVENTS")) : -1;
+    const bool timing = ev_env >= 0 ? ev_env != 0 : !h->overlap;
+    L.em_events.timing = L.em_events2.timing = timing;
+    for (auto& ee : L.em_events_part) ee.timing = timing;
+  }
   EstepPlan plan;
   {
     static const bool group_steps = getenv("SCAPE_B200_ESTEP") && atoi(getenv("SCAPE_B200_ESTEP")) != 0;
     static const bool warp_pf = getenv("SCAPE_B200_WARP_PF") ? atoi(getenv("SCAPE_B200_WARP_PF")) != 0 : true;
     static const int g_env = getenv("SCAPE_B200_ESTEP_G") ? atoi(getenv("SCAPE_B200_ESTEP_G")) : 0;
-    CU(L.d_lists.ensure(2 * chains.size() + 2));
-    CU(L.d_counts.ensure(2 * (SCAPE_B200_NROUND + 2)));
+    // list / count scratch of the group kernel: one region per concurrently stepping set (split parts, head)
+    CU(L.d_lists.ensure((kMaxSplit + 1) * (2 * chains.size() + 2)));
+    CU(L.d_counts.ensure((kMaxSplit + 1) * 2 * (SCAPE_B200_NROUND + 2)));
     plan.lists = L.d_lists.p;
     plan.counts = L.d_counts.p;
     plan.n_sm = h->n_sm;
@@ -817,10 +828,13 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     // first tail_step iterations bulk-synchronous (E step + batched scan per iteration, no closing E step) ...
     if (tail_step > 0 && !head.index.empty()) {
       L.em_events2.hook = nullptr;
+      EstepPlan hplan = plan;
+      hplan.lists = plan.lists + size_t(kMaxSplit) * (2 * chains.size() + 2);
+      hplan.counts = plan.counts + size_t(kMaxSplit) * 2 * (SCAPE_B200_NROUND + 2);
       nl += launch_em_steps(L.d_chains.p, L.d_descs.p, d_idx_head, head.n_small, head.n_big, any_scan, head.big_k, d_refs_head,
                             head.n_refs_chunk, int64_t(head.refs.size()) - head.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p,
                             L.d_lz.p, d_v, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p, L.d_trace_ws.p,
-                            L.st, L.em_events2, plan, tail_step);
+                            L.st, L.em_events2, hplan, tail_step);
     }
     // ... then every chain that still runs iterates to convergence in a CTA of its own
     fire_mark();
@@ -862,11 +876,14 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
       ee.mark = nullptr;
       ee.kinds.clear();
       if (!S.index.empty()) {
+        EstepPlan pplan = plan;
+        pplan.lists = plan.lists + size_t(p) * (2 * chains.size() + 2);
+        pplan.counts = plan.counts + size_t(p) * 2 * (SCAPE_B200_NROUND + 2);
         CU(cudaStreamWaitEvent(sp, L.ev_fork, 0));
         nl += launch_em_steps(L.d_chains.p, L.d_descs.p, di, S.n_small, S.n_big, any_scan, S.big_k, dr, S.n_refs_chunk,
                               int64_t(S.refs.size()) - S.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32,
                               L.d_cnt.p, L.d_lz.p, d_v, L.d_partials.p, L.d_counter.p, L.d_trace_a.p, L.d_trace_b.p,
-                              L.d_trace_ws.p, sp, ee, plan, SCAPE_B200_NROUND + 1);
+                              L.d_trace_ws.p, sp, ee, pplan, SCAPE_B200_NROUND + 1);
         CU(cudaEventRecord(L.ev_join[p - 1], sp));
       }
       di += S.index.size();
@@ -887,9 +904,21 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   double scan_elems = 0;
   CU(cudaMemcpyAsync(chains.data(), L.d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, L.st));
   CU(cudaMemcpyAsync(&scan_elems, L.d_counter.p, sizeof(double), cudaMemcpyDeviceToHost, L.st));
+  const double t_rc2 = now_ms();
   if (enqueued)
     if (int rc = enqueued()) { cudaStreamSynchronize(L.st); return rc; }
+  const double t_rc3 = now_ms();
   CU(cudaStreamSynchronize(L.st));
+  if (host_dbg_rc && chains.size() >= 1000) {
+    static double acc[5] = {0, 0, 0, 0, 0};
+    static int n_acc = 0;
+    acc[0] += t_rc1 - t_rc0; acc[1] += t_rc2 - t_rc1; acc[2] += t_rc3 - t_rc2; acc[3] += now_ms() - t_rc3;
+    if (++n_acc % 100 == 0) {
+      fprintf(stderr, "run_chains host wall per call (us): prepare+upload %.0f | enqueue launches %.0f | callback %.0f | wait %.0f\n",
+              10 * acc[0], 10 * acc[1], 10 * acc[2], 10 * acc[3]);
+      acc[0] = acc[1] = acc[2] = acc[3] = 0;
+    }
+  }
   L.tm.d2h_bytes += double(sizeof(ChainDev) * chains.size());
   float ms = 0, t0 = 0;
   CU(cudaEventElapsedTime(&ms, L.ev[4], L.ev[5]));

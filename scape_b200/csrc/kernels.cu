@@ -10,6 +10,11 @@
 
 namespace scape {
 
+static bool dbg_env() {
+  static const bool on = getenv("SCAPE_B200_DBG") != nullptr;
+  return on;
+}
+
 cudaError_t upload_model_const_cluster(const ModelConst& mc);   // em_cluster.cu's copy
 cudaError_t upload_model_const_tail(const ModelConst& mc);      // em_tail.cu's copy
 cudaError_t upload_model_const(const ModelConst& mc) {
@@ -959,7 +964,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
                              double* vbuf, void* partials, double* scan_elems, int32_t* trace_a, int32_t* trace_b,
                              double* trace_ws, cudaStream_t st, std::vector<cudaEvent_t>& evs,
                              std::vector<int>& kinds, int& scan_launches, const std::function<void()>& hook,
-                             const std::function<void()>& hook_mark, int hook_step, const EstepPlan& plan, int n_steps) {
+                             const std::function<void()>& hook_mark, int hook_step, const EstepPlan& plan, int n_steps, bool timing) {
   const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
   cudaFuncSetAttribute(em_scan_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(em_scan_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanTileVBytes);
@@ -988,6 +993,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
   kinds.clear();
   size_t ne = 0;
   auto mark = [&](int kind) {
+    if (!timing) return;
     cudaEventRecord(evs[ne++], st);
     kinds.push_back(kind);
   };
@@ -1033,11 +1039,47 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
       }
     }
   }
+  // Late steps (>= warp_steps) of a run with a grid search: few chains still run.  late_group: the group
+  // kernel over device-side lists of the running chains (persistent CTAs, 4 / 8 warps per chain) --
+  // a launch of <= 2 CTAs per SM instead of one CTA per chain of the wave, most of which exit at once.
+  // Measured: no gain (scheduling 5,000 empty CTAs costs ~4 us, scripts/micro/launch_rate.cu).
+  static const bool late_group = getenv("SCAPE_B200_LATE_GROUP") ? atoi(getenv("SCAPE_B200_LATE_GROUP")) != 0 : false;   // opt-in: measured no gain
+  int32_t* hLs[2] = {plan.lists, plan.lists + n_small};
+  int32_t* hLb[2] = {plan.lists + 2 * n_small, plan.lists + 2 * n_small + n_big};
+  int32_t* hcs = plan.counts;
+  int32_t* hcb = plan.counts + (SCAPE_B200_NROUND + 2);
+  if (!group && late_group && n_steps > warp_steps)
+    cudaMemsetAsync(plan.counts, 0, sizeof(int32_t) * 2 * (SCAPE_B200_NROUND + 2), st);
   for (int step = 0; !group && step < n_steps; step++) {
     // Early steps: most chains run -> one warp per chain (throughput).  Late steps: few chains run
-    // and the step time is the latency of ONE chain's E pass -> one CTA per chain (8x shorter
-    // fragment loop); CTAs of finished chains exit at once.
+    // and the step time is the latency of ONE chain's E pass -> several warps per chain.
     const bool wide = step < warp_steps;
+    if (!wide && late_group) {
+      const bool first = step == warp_steps;
+      const unsigned max_grid = (unsigned)(plan.n_sm * 2);
+      if (n_small > 0) {
+        const int Gs = plan.g_small;
+        const unsigned grid_s = (unsigned)std::min<int64_t>((n_small + GW / Gs - 1) / (GW / Gs), max_grid);
+        em_estep_group_kernel<TT><<<grid_s, GT, 0, st>>>(
+            chains_dev, descs_dev, first ? index_dev : hLs[step & 1], hcs + step, first ? (int)n_small : -1, hLs[(step + 1) & 1],
+            hcs + step + 1, Gs, 0, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a, trace_b, trace_ws);
+        launches++;
+      }
+      if (n_big > 0) {
+        const unsigned grid_b = (unsigned)std::min<int64_t>(n_big, max_grid);
+        em_estep_group_kernel<TT><<<grid_b, GT, 0, st>>>(
+            chains_dev, descs_dev, first ? index_dev + n_small : hLb[step & 1], hcb + step, first ? (int)n_big : -1,
+            hLb[(step + 1) & 1], hcb + step + 1, GW, 0, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,
+            trace_b, trace_ws);
+        launches++;
+      }
+      mark(0);
+      if (step == SCAPE_B200_NROUND || !any_scan || n_refs + n_refs_tile == 0) continue;
+      launches += scan_step();
+      mark(1);
+      if (hook && step == hook_step) { if (hook_mark) hook_mark(); hook(); }
+      continue;
+    }
     if (n_small > 0 && wide) {
       if (plan.warp_prefetch)
         em_estep_warp_kernel<TT, false, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
@@ -1091,10 +1133,10 @@ int launch_em_steps(ChainDev* chains_dev, ScanDesc* descs_dev, const int32_t* in
   if (f32)
     return launch_em_steps_t<float>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, n_refs_tile, utrs_dev,
                                     utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.mark, ee.hook_step, plan, n_steps);
+                                    trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.mark, ee.hook_step, plan, n_steps, ee.timing || dbg_env());
   return launch_em_steps_t<double>(chains_dev, descs_dev, index_dev, n_small, n_big, any_scan, big_k, refs_dev, n_refs, n_refs_tile, utrs_dev,
                                    utr_chain_off_dev, tensor, cnt, lz, vbuf, partials, scan_elems, trace_a, trace_b,
-                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.mark, ee.hook_step, plan, n_steps);
+                                   trace_ws, st, ee.evs, ee.kinds, ee.scan_launches, ee.hook, ee.mark, ee.hook_step, plan, n_steps, ee.timing || dbg_env());
 }
 
 // After the stream has been synchronised: total E-step and scan kernel time of the last run.

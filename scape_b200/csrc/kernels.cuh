@@ -152,6 +152,10 @@ struct EmStepEvents {
   // recorded on the EM stream where the staged wave's work may start (cheap; `hook` does the host work)
   std::function<void()> mark;
   int hook_step = 0;
+  // record an event around every launch group (E-step / scan split of em_ms).  Off in the pipelined
+  // production passes: on this platform an API call costs ~15-20 us, and two extra calls per step make
+  // the 101-step loop launch-bound; on for the un-pipelined pass bench.py takes its per-kernel times from.
+  bool timing = true;
 };
 void em_steps_elapsed(const EmStepEvents& ee, double* estep_ms, double* scan_ms);
 int measure_fp64_peaks(int n_sm, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);

@@ -151,3 +151,24 @@ def test_reference_assertion_is_reported():
     x = np.array([-5.0, 10.0, 30.0]); l = np.array([50.0, 50.0, 50.0]); nan = np.full(3, np.nan)
     with pytest.raises(_lib.ScapeB200Error):
         _lib.profile(_lib.make_params(), x, l, nan, nan)
+
+
+def test_chunk_batch_layout_cache_is_per_dtype():
+    """Frames with the same columns but different id dtypes (int ids, then float ids carrying NaN) must
+    each come back with THEIR dtype, like the reference's np.array(data[col]) (apa_core.py:1013-1014)."""
+    import pandas as pd
+    from scape_b200 import synth
+    from scape_b200.apa_core import ChunkBatch
+    u = synth.make_utr(5, 40)
+    a = synth.to_dataframe(u)
+    b = synth.to_dataframe(u)
+    b["cb_id"] = b["cb_id"].astype(float)
+    b.loc[3, "cb_id"] = np.nan
+    batch = ChunkBatch()
+    batch.add("g1", a, 0)
+    batch.add("g2", b, 0)
+    batch.add("g3", a, 0)
+    assert batch.frames[0][0].dtype == np.int64 and np.array_equal(batch.frames[0][0], np.array(a["cb_id"]))
+    assert batch.frames[1][0].dtype == np.float64 and np.isnan(batch.frames[1][0][3])
+    assert np.array_equal(batch.frames[1][0][:3], np.array(b["cb_id"])[:3])
+    assert batch.frames[2][0].dtype == np.int64
