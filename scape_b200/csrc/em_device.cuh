@@ -504,6 +504,7 @@ struct PassCtx {
   int row0[kClusterPassMax], row1[kClusterPassMax], hlo[kClusterPassMax], hhi[kClusterPassMax];
   long long voff[kClusterPassMax], pboff[kClusterPassMax];
   int NA, NB, P;
+  unsigned char wlist[GW][kClusterPassMax];   // per warp: the slots of the chains that cover the warp's current tile, ascending
 };
 
 // scores of one 32-row tile against the nt <= 8 NG chains of the pass that cover it (bit `s` of `mask`:
@@ -544,13 +545,14 @@ __device__ __forceinline__ void scan_tile_mma(const PassCtx& sh, const UtrDev& u
   const int base = t * kClusterTileRows;
   const int tile_end = min(base + kClusterTileRows, Rv);
   const int NA = sh.NA, P = sh.P;
+  const unsigned char* wl = sh.wlist[(threadIdx.x >> 5) & (GW - 1)];
   // B operand of this lane: V[chain slot of column 8 ni + g][fragment k0 + q]; columns past nt read the zero row
   const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
   uint32_t vb[NG];
 #pragma unroll
   for (int ni = 0; ni < NG; ni++) {
     const int idx = 8 * ni + g;
-    const int slot = idx < nt ? (int)__fns(mask, 0, idx + 1) : cntp;
+    const int slot = idx < nt ? (int)wl[idx] : cntp;
     vb[ni] = vs_base + (uint32_t)(slot * P + (h0 - NA) + q) * 8u;
   }
   double acc[4][NG][2];
@@ -612,7 +614,7 @@ __device__ __forceinline__ void scan_tile_mma(const PassCtx& sh, const UtrDev& u
     for (int i = 0; i < 2; i++) {
       const int c = 8 * ni + 2 * q + i;
       const bool live = c < nt;
-      const int slot = live ? (int)__fns(mask, 0, c + 1) : 0;
+      const int slot = live ? (int)wl[c] : 0;
       const int w0 = live ? sh.row0[slot] : 0, w1 = live ? min(sh.row1[slot], tile_end) : 0;
       double b = -CUDART_INF;
       int r = 0x7fffffff;
@@ -642,7 +644,7 @@ __device__ __forceinline__ void scan_tile_mma(const PassCtx& sh, const UtrDev& u
 }
 
 template <typename TT, bool TO_SMEM>
-__device__ __forceinline__ void scan_tile(const PassCtx& sh, const UtrDev& u, const TT* __restrict__ A,
+__device__ __forceinline__ void scan_tile(PassCtx& sh, const UtrDev& u, const TT* __restrict__ A,
                                           const double* Vs, ScanPartial* partials, int t, int cntp,
                                           double* scan_elems, double* wbest, int* wrow) {
   const int lane = threadIdx.x & 31;
@@ -652,6 +654,10 @@ __device__ __forceinline__ void scan_tile(const PassCtx& sh, const UtrDev& u, co
   const unsigned mask = __ballot_sync(0xffffffffu, cover);
   const int nt = __popc(mask);
   if (nt == 0) return;
+  // compact list of the covering chains' slots (MMA column -> slot), per warp
+  __syncwarp();                                   // the previous tile's readers are done
+  if (cover) sh.wlist[(threadIdx.x >> 5) & (GW - 1)][__popc(mask & ((1u << lane) - 1u))] = (unsigned char)lane;
+  __syncwarp();
   int h0 = 1 << 30, h1 = 0;
   if (cover && sh.hhi[lane] >= 0) { h0 = sh.hlo[lane]; h1 = sh.hhi[lane] + 1; }
 #pragma unroll
