@@ -224,14 +224,14 @@ _io_pool = None
 _engines = {}
 
 
-def _cached_engine(device: int, params, host_threads: int = 0):
+def _cached_engine(device: int, params, host_threads: int = 0, tensor_dtype: Optional[str] = None):
     """One Engine per (device, parameter set), kept across infer_files calls: its device arenas, pinned
     staging and host pools are expensive to build.  A handle is not re-entrant; callers use a device
     from one thread at a time."""
-    key = (int(device), bytes(params))
+    key = (int(device), bytes(params), tensor_dtype)
     eng = _engines.get(key)
     if eng is None:
-        eng = _engines[key] = _lib.Engine(params, device=device)
+        eng = _engines[key] = _lib.Engine(params, device=device, tensor_dtype=tensor_dtype)
     eng.set_host_threads(host_threads)
     return eng
 
@@ -438,7 +438,8 @@ def _infer_files_pooled(paths, outs, devices, io_workers, **kwargs):
             for s, f in enumerate(mine):
                 batch.add_packed(s, *packed[f])
             engine = _cached_engine(dev, _lib.make_params(pre_para=pre_para, **kwargs),
-                                    host_threads=max(1, (os.cpu_count() or 1) // len(devices)) if len(devices) > 1 else 0)
+                                    host_threads=max(1, (os.cpu_count() or 1) // len(devices)) if len(devices) > 1 else 0,
+                                    tensor_dtype=kwargs.get("tensor_dtype"))
             off, x, l, r, pa, sid = batch.packed()
             out = engine.fit(off, x, l, r, pa, sid, np.ones(len(mine), np.uint32))
             if np.any(out.status != 0):
