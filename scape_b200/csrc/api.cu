@@ -435,7 +435,10 @@ int np_argmin(const std::vector<double>& v) {
 //            (few RNG streams per GPU), where the step kernels are latency floors.
 //   cluster  one thread-block cluster per UTR, all iterations in one launch (em_cluster.cu).  Measured
 //            slower than both everywhere (idle warps at the cluster barriers); kept as an experiment.
-//   auto (default)  tail for runs of fewer than SCAPE_B200_TAIL_CHAINS (1500) chains, else bsp
+//   auto (default)  tail for runs of fewer than SCAPE_B200_TAIL_CHAINS chains, else bsp.  The default
+//            threshold is 0 (always bsp): the tail route wins a few per cent on small waves of SMALL
+//            UTRs (cfg-2 shape, 12-25 UTRs per wave) but loses badly on small heavy-tailed waves (cfg-3
+//            over 8 GPUs: 24.2k -> 16.0k UTR/s), where a chain's own window no longer sits in L2.
 enum EmRoute : char { kRouteBsp = 0, kRouteCluster = 1, kRouteTail = 2, kRouteBspPart = 3 };   // kRouteBspPart + p: part p + 1 of a split wave
 
 // The chains of a set of UTRs prepared for the bulk-synchronous step kernels: the E-step launch
@@ -576,7 +579,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   std::vector<char> scans(W, 0);
   bool any_scan = false;
   static const char* em_env = getenv("SCAPE_B200_EM");
-  static const size_t tail_chains = getenv("SCAPE_B200_TAIL_CHAINS") ? size_t(atol(getenv("SCAPE_B200_TAIL_CHAINS"))) : 1500;
+  static const size_t tail_chains = getenv("SCAPE_B200_TAIL_CHAINS") ? size_t(atol(getenv("SCAPE_B200_TAIL_CHAINS"))) : 0;
   const char mode = (!em_env || !strcmp(em_env, "auto")) ? (chains.size() < tail_chains ? kRouteTail : kRouteBsp)
                     : !strcmp(em_env, "bsp") ? kRouteBsp : !strcmp(em_env, "cluster") ? kRouteCluster : kRouteTail;
   static const int tail_step = std::max(0, std::min(SCAPE_B200_NROUND, getenv("SCAPE_B200_TAIL_STEP") ? atoi(getenv("SCAPE_B200_TAIL_STEP")) : 8));

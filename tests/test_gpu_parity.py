@@ -261,17 +261,16 @@ def test_scheduling_knobs_do_not_change_a_bit():
     # SCAPE_B200_POISON=1 fills the tensor arena with NaN bits before every wave: whatever the kernels
     # do not write themselves (pitch padding, slack rows the scan's prefetch ring touches) would then
     # poison the grid search -- the digest must not change either.
-    # Three families of EM execution (api.cu run_chains): the default (a few bulk-synchronous steps, then
-    # the chain-resident kernel), all steps bulk-synchronous (SCAPE_B200_EM=bsp), and the cluster-resident
+    # Three families of EM execution (api.cu run_chains): all steps bulk-synchronous (the default), a few
+    # bulk-synchronous steps followed by the chain-resident kernel (SCAPE_B200_EM=tail), and the cluster-resident
     # kernel (SCAPE_B200_EM=cluster, any cluster size).  Their E passes sum a chain's fragments in
     # different orders (one warp / a CTA / G warps), so bits may differ BETWEEN the families (each
     # matches the oracle: test_scale_parity); within a family nothing may.
     families = {
-        # (the batch is small, so the default `auto` mode takes the tail route like SCAPE_B200_EM=tail)
-        "tail": ("", "SCAPE_B200_EM=tail", "SCAPE_B200_PREDRAW=0", "SCAPE_B200_OVERLAP=0", "SCAPE_B200_POISON=1",
-                 "SCAPE_B200_SCAN_SPLIT=0", "SCAPE_B200_WARP_PF=0", "SCAPE_B200_STAGE_CHAIN=0", "SCAPE_B200_SCAN_TILES=1"),
-        "bsp": ("SCAPE_B200_EM=bsp", "SCAPE_B200_EM=bsp SCAPE_B200_SCAN_SPLIT=0", "SCAPE_B200_EM=bsp SCAPE_B200_POISON=1",
-                "SCAPE_B200_EM=bsp SCAPE_B200_SCAN_TILES=1", "SCAPE_B200_TAIL_CHAINS=0"),
+        "bsp": ("", "SCAPE_B200_EM=bsp", "SCAPE_B200_PREDRAW=0", "SCAPE_B200_OVERLAP=0", "SCAPE_B200_POISON=1",
+                "SCAPE_B200_SCAN_SPLIT=0", "SCAPE_B200_SCAN_TILES=1", "SCAPE_B200_SPLIT=1", "SCAPE_B200_STEP_EVENTS=1"),
+        "tail": ("SCAPE_B200_EM=tail", "SCAPE_B200_TAIL_CHAINS=100000", "SCAPE_B200_EM=tail SCAPE_B200_WARP_PF=0",
+                 "SCAPE_B200_EM=tail SCAPE_B200_STAGE_CHAIN=0", "SCAPE_B200_EM=tail SCAPE_B200_POISON=1"),
         "cluster": ("SCAPE_B200_EM=cluster", "SCAPE_B200_EM=cluster SCAPE_B200_CLUSTER=1", "SCAPE_B200_EM=cluster SCAPE_B200_CLUSTER=4",
                     "SCAPE_B200_EM=cluster SCAPE_B200_POISON=1"),
     }
