@@ -211,6 +211,13 @@ static void fill_model_const(const scape_b200_params& P, ModelConst& mc) {
     mc.logpmf_s[i] = std::log(P.pmf_s[i]);
   }
   for (int i = 0; i < P.n_beta; i++) mc.betas[i] = P.betas[i];
+  // exp_nonpos (em_device.cuh): log2(e), 1.5 * 2^52, -ln2_hi, -ln2_lo, 1/13! ... 1/2!, 1, clamp
+  static const double expc[18] = {
+      1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+      1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+      2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664,
+      0.16666666666666666, 0.5, 1.0, -746.0};
+  memcpy(mc.expc, expc, sizeof(expc));
 }
 
 static int check_params(const scape_b200_params& P) {

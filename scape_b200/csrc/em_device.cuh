@@ -208,29 +208,24 @@ __device__ __forceinline__ void estep_epilogue(ChainDev& ch, ScanDesc& sd, const
 // below -745.13, the sentinel's -3.4e38 included) come out right.  Measured against long-double expl on 2e7
 // arguments in [-750, 0]: max error 0.88 ulp (CUDA's exp(): 1 ulp), exp_nonpos(0) == 1.  CUDA's general exp()
 // costs about twice the instructions and carries branches for its special cases (BSSY / BSYNC pairs).
+// The constants sit in the uploaded model constants (c_mc.expc, filled by fill_model_const in api.cu), so
+// they are constant-bank operands of the DFMAs: as literals -- or as an initialised __constant__ array,
+// which the compiler folds back into literals -- every one costs two UMOVs in front of its DFMA (2,177
+// UMOVs for 2,813 DFMAs in the warp E step).
+#define c_expc c_mc.expc
 __device__ __forceinline__ double exp_nonpos(double x) {
-  x = fmax(x, -746.0);
-  const double MAGIC = 6755399441055744.0;       // 1.5 * 2^52
-  const double t = fma(x, 1.4426950408889634074, MAGIC);
+  x = fmax(x, c_expc[17]);
+  const double t = fma(x, c_expc[0], c_expc[1]);   // c[1] = 1.5 * 2^52: rounds x log2(e) to an integer in the low word
   const int k = __double2loint(t);
-  const double kd = t - MAGIC;
-  double r = fma(kd, -6.93147180369123816490e-01, x);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;              // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);
-  p = fma(p, r, 2.505210838544172e-08);
-  p = fma(p, r, 2.755731922398589e-07);
-  p = fma(p, r, 2.7557319223985893e-06);
-  p = fma(p, r, 2.48015873015873e-05);
-  p = fma(p, r, 0.0001984126984126984);
-  p = fma(p, r, 0.001388888888888889);
-  p = fma(p, r, 0.008333333333333333);
-  p = fma(p, r, 0.041666666666666664);
-  p = fma(p, r, 0.16666666666666666);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const int k1 = k >> 1, k2 = k - k1;             // k in [-1077, 0]: both factors stay normal
+  const double kd = t - c_expc[1];
+  double r = fma(kd, c_expc[2], x);                // Cody-Waite: -ln2_hi, -ln2_lo
+  r = fma(kd, c_expc[3], r);
+  double p = c_expc[4];                             // 1/13! ... 1/2!, 1, 1
+#pragma unroll
+  for (int i = 5; i <= 15; i++) p = fma(p, r, c_expc[i]);
+  p = fma(p, r, c_expc[16]);
+  p = fma(p, r, c_expc[16]);
+  const int k1 = k >> 1, k2 = k - k1;               // k in [-1077, 0]: both factors stay normal
   p *= __hiloint2double((k1 + 1023) << 20, 0);
   p *= __hiloint2double((k2 + 1023) << 20, 0);
   return p;

@@ -52,6 +52,7 @@ struct ModelConst {
   double pmf_s[SCAPE_B200_MAX_S];
   double logpmf_s[SCAPE_B200_MAX_S];
   double betas[SCAPE_B200_MAX_BETA];
+  double expc[18];                // constants of exp_nonpos (em_device.cuh): uploaded, so that they are c[bank][offset] operands
 };
 
 struct ChainDev {
