@@ -18,6 +18,7 @@ Suites (BASELINE.json configs):
            normal-mode result of their own first UTR
   kmax8    2 files x 50 UTRs x 500 reads (indices 2000..2099), n_max_apa 8
   kmax10   2 files x 50 UTRs x 500 reads (indices 2100..2199), n_max_apa 10
+  cfg5     the stress corner: one UTR with 1,000,000 reads and one with 300,000, n_max_apa 10
 
 Per UTR: K, alpha, beta, ws, bic, lb_arr[-1], n_iter, n_frag, n_theta, chains_run, the (k_max,
 k_selected, K) path of every sweep, the per-read labels (int8), and `rng_off` = number of 32-bit
@@ -75,6 +76,8 @@ def suites():
     out["cfg4"] = dict(params={}, files=[[(i, int(counts[i]), bool(counts[i] >= cut)) for i in range(f * 50, f * 50 + 50)]
                                          for f in range(4)], pre=[FIXED_PRE, FIXED_PRE, "first", "first"])
     out["kmax8"] = dict(params={"n_max_apa": 8}, files=[[(2000 + f * 50 + i, 500, False) for i in range(50)] for f in range(2)])
+    # cfg-5 corner: one UTR with a million reads (N ~ 11,500 fragments) and one with 300k, n_max_apa 10
+    out["cfg5"] = dict(params={"n_max_apa": 10}, files=[[(900000, 1000000, True)], [(900001, 300000, True)]])
     out["kmax10"] = dict(params={"n_max_apa": 10}, files=[[(2100 + f * 50 + i, 500, False) for i in range(50)] for f in range(2)])
     return out
 

@@ -222,16 +222,20 @@ def _write_result_file(path, fixed_run_mode, gene_infos, n_reads, K, L, alpha, b
 
 _io_pool = None
 _engines = {}
+_engines_lock = __import__("threading").Lock()
 
 
 def _cached_engine(device: int, params, host_threads: int = 0, tensor_dtype: Optional[str] = None):
     """One Engine per (device, parameter set), kept across infer_files calls: its device arenas, pinned
     staging and host pools are expensive to build.  A handle is not re-entrant; callers use a device
     from one thread at a time."""
+    import threading
     key = (int(device), bytes(params), tensor_dtype)
-    eng = _engines.get(key)
-    if eng is None:
-        eng = _engines[key] = _lib.Engine(params, device=device, tensor_dtype=tensor_dtype)
+    with _engines_lock:
+        eng = _engines.get(key)
+        if eng is None:
+            eng = _engines[key] = _lib.Engine(params, device=device, tensor_dtype=tensor_dtype)
+            eng.fit_lock = threading.Lock()          # a handle is not re-entrant (two threads given the same device)
     eng.set_host_threads(host_threads)
     return eng
 
@@ -441,7 +445,8 @@ def _infer_files_pooled(paths, outs, devices, io_workers, **kwargs):
                                     host_threads=max(1, (os.cpu_count() or 1) // len(devices)) if len(devices) > 1 else 0,
                                     tensor_dtype=kwargs.get("tensor_dtype"))
             off, x, l, r, pa, sid = batch.packed()
-            out = engine.fit(off, x, l, r, pa, sid, np.ones(len(mine), np.uint32))
+            with getattr(engine, "fit_lock", _engines_lock):
+                out = engine.fit(off, x, l, r, pa, sid, np.ones(len(mine), np.uint32))
             if np.any(out.status != 0):
                 results_to_parameters(batch, out, fixed)      # raises the reference's error for the first bad UTR
             u0 = 0

@@ -177,7 +177,8 @@ struct scape_b200_handle {
   ModelConst mc;
   Lane lanes[kMaxLanes];
   int n_lanes = 1;
-  bool tensor_fast = false;   // default grid shape: interior alpha rows use the constant-weight kernel
+  bool tensor_fast = false;   // default grid shape: alpha rows use the constant-weight kernel
+  bool tensor_fast_edges = false;  // ... including the rows whose windows are clipped by the grid ends (SCAPE_B200_TENSOR_EDGES=0: generic kernel)
   double tf_g[kTfB * kTfW], tf_lp[kTfB * kTfW], tf_lps[kTfB];
   int tf_hw[kTfB];
   cudaEvent_t base_ev = nullptr;
@@ -293,6 +294,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
           h->tf_g[j * kTfW + d] = std::abs(d - kTfHalf) <= hw ? std::exp(h->tf_lp[j * kTfW + d] - h->tf_lps[j]) : 0.0;
       }
       h->tensor_fast = true;
+      if (const char* s2 = getenv("SCAPE_B200_TENSOR_EDGES")) h->tensor_fast_edges = atoi(s2) != 0;
     }
   }
   int prio_lo = 0, prio_hi = 0;
@@ -656,6 +658,10 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
                           std::to_string(kScanMaxChains));
     chain_off[i + 1] += chain_off[i];
   }
+  // The chain records are complete (offsets assigned): their upload (4.8 MB for a cfg-2 wave) starts now and
+  // runs while the host builds the launch lists below.
+  CU(L.d_chains.ensure(chains.size()));
+  CU(cudaMemcpyAsync(L.d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, L.st));
   StepSet full, head, parts[kMaxSplit - 1];   // all 51 steps / the first tail_step steps before the chain-resident kernel / parts 2.. of a split wave
   if (int rc = build_step_set(h, chains, utrs_host, chain_off, scans, route, kRouteBsp, full)) return rc;
   for (int p = 1; p < n_parts; p++)
@@ -712,7 +718,6 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     CU(cudaStreamSetAttribute(L.st, cudaStreamAttributeAccessPolicyWindow, &attr));
   }
-  CU(L.d_chains.ensure(chains.size()));
   CU(L.d_chain_off.ensure(W + 1));
   CU(L.d_descs.ensure(chains.size()));
   CU(cudaMemsetAsync(L.d_descs.p, 0, sizeof(ScanDesc) * chains.size(), L.st));
@@ -752,7 +757,6 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     }
     std::copy(chain_off.begin(), chain_off.end(), (int32_t*)(b + o_off));
     std::copy(cjobs.begin(), cjobs.end(), (ClusterJob*)(b + o_jobs));
-    CU(cudaMemcpyAsync(L.d_chains.p, chains.data(), sizeof(ChainDev) * chains.size(), cudaMemcpyHostToDevice, L.st));
     CU(cudaMemcpyAsync(L.d_chain_off.p, b + o_off, sizeof(int32_t) * (W + 1), cudaMemcpyHostToDevice, L.st));
     if (n_index) CU(cudaMemcpyAsync(L.d_chain_idx.p, hi, sizeof(int32_t) * n_index, cudaMemcpyHostToDevice, L.st));
     if (n_refs) CU(cudaMemcpyAsync(L.d_refs.p, hr, sizeof(ScanRef) * n_refs, cudaMemcpyHostToDevice, L.st));
@@ -1053,7 +1057,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       max_n = std::max(max_n, d.Npad);
       // marginal tensor: interior alpha rows go to the constant-weight kernel in tiles, the rest
       // (window clipped by the grid ends) to the generic kernel
-      const int n_int = h->tensor_fast ? std::max(0, d.T - 2 * kTfHalf) : 0;
+      const int n_int = !h->tensor_fast ? 0 : h->tensor_fast_edges ? d.T : std::max(0, d.T - 2 * kTfHalf);
       n_rows += d.T;
       n_trows += d.T - n_int;
       n_tiles += (n_int + kTfTile - 1) / kTfTile;
@@ -1089,12 +1093,13 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         std::copy(p.theta.begin(), p.theta.end(), hth + d.theta_off);
         std::copy(p.read_to_bin.begin(), p.read_to_bin.end(), (int32_t*)(blob.p + o_r2b) + d.read_off);
         hud[i] = d;
-        const int i_hi = d.T - 1 - kTfHalf;
+        const bool all_fast = h->tensor_fast && h->tensor_fast_edges;
+        const int t_lo = all_fast ? 0 : i_lo, t_hi = all_fast ? d.T - 1 : d.T - 1 - kTfHalf;
         for (int t = 0; t < d.T; t++) rows[ir++] = {int32_t(i), t};
         for (int t = 0; t < d.T; t++)
-          if (!h->tensor_fast || t < i_lo || t > i_hi) trows[it++] = {int32_t(i), t};
+          if (!h->tensor_fast || t < t_lo || t > t_hi) trows[it++] = {int32_t(i), t};
         if (h->tensor_fast)
-          for (int t = i_lo; t <= i_hi; t += kTfTile) tiles[il++] = {int32_t(i), t, std::min(kTfTile, i_hi - t + 1)};
+          for (int t = t_lo; t <= t_hi; t += kTfTile) tiles[il++] = {int32_t(i), t, std::min(kTfTile, t_hi - t + 1)};
       }
       if (ir != n_rows || it != n_trows || il != n_tiles) return fail(-5, "internal: wave row lists out of step");
     }
@@ -1764,7 +1769,7 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
     CU(upload_tensor_fast_tables(h->tf_g, h->tf_lp, h->tf_lps, h->tf_hw));
     std::vector<RowRef> edge;
     std::vector<TileRef> tiles;
-    const int i_lo = kTfHalf, i_hi = d.T - 1 - kTfHalf;
+    const int i_lo = h->tensor_fast_edges ? 0 : kTfHalf, i_hi = h->tensor_fast_edges ? d.T - 1 : d.T - 1 - kTfHalf;
     for (int t = 0; t < d.T; t++)
       if (t < i_lo || t > i_hi) edge.push_back({0, t});
     for (int t = i_lo; t <= i_hi; t += kTfTile) tiles.push_back({0, t, std::min(kTfTile, i_hi - t + 1)});

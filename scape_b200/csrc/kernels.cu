@@ -1,5 +1,6 @@
 // See kernels.cuh for the kernel list, the reference lines each kernel follows and the HBM layout.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -270,44 +271,90 @@ __constant__ double c_tf_g[TF_B * TF_W];     // weights on the widest window, 0 
 __constant__ double c_tf_lp[TF_B * TF_W];    // log pdf (for the exact fallback)
 __constant__ double c_tf_lps[TF_B];
 __constant__ int c_tf_hw[TF_B];              // half width of beta_j's window in grid points
+__constant__ double c_tf_pre[TF_B * (TF_W + 1)];   // prefix sums of exp(lp[j][d]) over d: clipped-window normalisers of the edge rows
 
 cudaError_t upload_tensor_fast_tables(const double* g, const double* lp, const double* lps, const int* hw) {
   cudaError_t e = cudaMemcpyToSymbol(c_tf_g, g, sizeof(double) * TF_B * TF_W);
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_tf_lp, lp, sizeof(double) * TF_B * TF_W);
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_tf_lps, lps, sizeof(double) * TF_B);
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_tf_hw, hw, sizeof(int) * TF_B);
+  if (e == cudaSuccess) {
+    // prefix sums of exp(lp) in theta order (0 outside beta_j's own window)
+    double pre[TF_B * (TF_W + 1)];
+    for (int j = 0; j < TF_B; j++) {
+      pre[j * (TF_W + 1)] = 0.0;
+      for (int d = 0; d < TF_W; d++) {
+        const bool in = d >= TF_HALF - hw[j] && d <= TF_HALF + hw[j];
+        pre[j * (TF_W + 1) + d + 1] = pre[j * (TF_W + 1) + d] + (in ? std::exp(lp[j * TF_W + d]) : 0.0);
+      }
+    }
+    e = cudaMemcpyToSymbol(c_tf_pre, pre, sizeof(pre));
+  }
   return e;
 }
 
+
+// Alpha rows whose widest window is clipped by the grid ends (the first and last 21 rows of a UTR) take
+// the same kernel: grid points outside [0, T) contribute nothing (e = 0, dead), and the weights of a
+// clipped window are the full-window weights times exp(lps_full - lps_clip), lps_clip = log of the sum
+// of exp(lp) over the points that exist (call_logp_theta_sum_kernel sums exactly those,
+// taichi_core.py:160-169, 221-222), so
+//     res = log(sum_d e_d g_full[j][d]) + M + (lps_full[j] - lps_clip[j][row]).
+// lps_clip comes from a prefix-sum table (one log per (row, beta) of the tile, not per fragment).
 template <typename TT>
 __global__ void __launch_bounds__(TF_THREADS) tensor_interior_kernel(const UtrDev* __restrict__ utrs,
                                                               const TileRef* __restrict__ tiles,
                                                               const double* __restrict__ table,
                                                               TT* __restrict__ tensor) {
   extern __shared__ double sm_e[];             // [TF_COLS][TF_THREADS]: this thread's exp(table - M) column
+  __shared__ double s_dl[TF_TI][TF_B];         // edge tiles: lps_full - lps_clip per (row of the tile, beta)
+  __shared__ int s_lo[TF_TI][TF_B], s_hi[TF_TI][TF_B];   // edge tiles: first / last existing point of beta_j's window (index d)
   const TileRef tr = tiles[blockIdx.x];
   const UtrDev u = utrs[tr.utr];
   const int tid = threadIdx.x;
   const int n = blockIdx.y * blockDim.x + tid;
+  if ((int)(blockIdx.y * blockDim.x) >= u.N) return;   // CTA-uniform
+  const bool edge = tr.i0 < TF_HALF || tr.i0 + tr.cnt - 1 > u.T - 1 - TF_HALF;
+  if (edge) {
+    for (int e = tid; e < tr.cnt * TF_B; e += TF_THREADS) {
+      const int ii = e / TF_B, j = e - ii * TF_B;
+      const int hw = c_tf_hw[j], row = tr.i0 + ii;
+      const int lo = TF_HALF - min(hw, row), hi = TF_HALF + min(hw, u.T - 1 - row);   // existing points of the window, as d
+      s_lo[ii][j] = lo;
+      s_hi[ii][j] = hi;
+      s_dl[ii][j] = c_tf_lps[j] - log(c_tf_pre[j * (TF_W + 1) + hi + 1] - c_tf_pre[j * (TF_W + 1) + lo]);
+    }
+    __syncthreads();
+  }
   if (n >= u.N) return;                        // no barrier below: every thread only touches its own column
   const int64_t ld = u.Npad;
-  const double* tab = table + u.table_off + n + (int64_t)(tr.i0 - TF_HALF) * ld;
+  const int c_first = tr.i0 - TF_HALF;         // grid index of column 0 (negative at the left edge)
+  const double* tab = table + u.table_off + n;
   const int cols = tr.cnt + TF_W - 1;
-  double M = tab[0];
-  uint64_t live = tab[0] > -1e30 ? 1ull : 0ull;        // bit c: theta column c is compatible with this fragment
-  for (int c = 1; c < cols; c++) {
-    const double v = tab[(int64_t)c * ld];
+  double M = -CUDART_INF;
+  uint64_t live = 0ull;                        // bit c: theta column c exists and is compatible with this fragment
+  for (int c = 0; c < cols; c++) {
+    const int gc = c_first + c;
+    if (gc < 0 || gc >= u.T) continue;
+    const double v = tab[(int64_t)gc * ld];
     M = fmax(M, v);
     live |= (v > -1e30 ? 1ull : 0ull) << c;
   }
   TT* out = tensor + u.tensor_off + (int64_t)n * u.ldR + (int64_t)tr.i0 * TF_B;
+  if (tr.i0 + tr.cnt == u.T)                   // the tile with the last alpha row also writes the pitch padding (finite)
+    for (int64_t c = (int64_t)u.T * TF_B; c < u.ldR; c++) tensor[u.tensor_off + (int64_t)n * u.ldR + c] = TT(0);
   if (M < -1e30) {                             // incompatible with every theta of the tile: all sentinel
     for (int e = 0; e < tr.cnt * TF_B; e++) out[e] = TT(SCAPE_SENTINEL);
     return;
   }
   for (int c = 0; c < cols; c++) {
-    const double a = tab[(int64_t)c * ld] - M;
-    sm_e[c * TF_THREADS + tid] = (a > -746.0) ? exp(a) : 0.0;
+    const int gc = c_first + c;
+    double ev = 0.0;
+    if (gc >= 0 && gc < u.T) {
+      const double a = tab[(int64_t)gc * ld] - M;
+      ev = (a > -746.0) ? exp(a) : 0.0;
+    }
+    sm_e[c * TF_THREADS + tid] = ev;
   }
   for (int ii = 0; ii < tr.cnt; ii++) {
     double acc[TF_B];
@@ -323,24 +370,26 @@ __global__ void __launch_bounds__(TF_THREADS) tensor_interior_kernel(const UtrDe
     for (int j = 0; j < TF_B; j++) {
       double res;
       const int hw = c_tf_hw[j];
+      const double dl = edge ? s_dl[ii][j] : 0.0;
       if (acc[j] > 1e-290) {
-        res = log(acc[j]) + M;
+        res = (log(acc[j]) + M) + dl;
       } else if ((live & (((2ull << (2 * hw)) - 1ull) << (ii + TF_HALF - hw))) == 0ull) {
         // beta_j's own window holds incompatible thetas only (the common case at the edge of the
         // fragment's compatible range): the exact path below would return the sentinel
         res = SCAPE_SENTINEL;
       } else {
-        // exact two-pass log-sum-exp over beta_j's own window (taichi_core.py:41-54, 172-179)
-        const double* col = tab + (int64_t)(ii + TF_HALF - hw) * ld;
-        const double* lp = c_tf_lp + j * TF_W + (TF_HALF - hw);
-        const double lps = c_tf_lps[j];
-        double m = (col[0] + lp[0]) - lps;
-        for (int d = 1; d <= 2 * hw; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
+        // exact two-pass log-sum-exp over beta_j's own (existing) window (taichi_core.py:41-54, 172-179)
+        const int lo = edge ? s_lo[ii][j] : TF_HALF - hw, hi = edge ? s_hi[ii][j] : TF_HALF + hw;
+        const double* col = tab + (int64_t)(c_first + ii) * ld;     // column of d = 0 for this row
+        const double* lp = c_tf_lp + j * TF_W;
+        const double lps = c_tf_lps[j] - dl;
+        double m = -CUDART_INF;
+        for (int d = lo; d <= hi; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
         if (m < -1e30) {
           res = SCAPE_SENTINEL;                // log(w) + sentinel == sentinel in FP64
         } else {
           double sum = 0.0;
-          for (int d = 0; d <= 2 * hw; d++) {
+          for (int d = lo; d <= hi; d++) {
             const double a = ((col[(int64_t)d * ld] + lp[d]) - lps) - m;
             if (a > -746.0) sum += exp(a);
           }

@@ -328,3 +328,35 @@ def test_cli_writes_reference_format_pickles(tmp_path, golden):
         assert np.array_equal(g.cb_id_arr, us[i].cb_id) and np.array_equal(g.readID_arr, us[i].read_id)
         assert g.alpha_arr.dtype == np.int64 and g.label_arr.dtype == np.int64
         check_against_golden(g, spec["utrs"][i], golden["labels"][f"synth8/{i}"], tight=True, lb_rtol=1e-7, ws_atol=1e-6)
+
+
+def test_infer_files_on_the_gpu_equals_one_infer_pa_per_file(tmp_path):
+    """The many-file entry point on real hardware, through the worker-process I/O path and with the files
+    dealt over two handles (both on device 0 here): the result files must hold exactly what one
+    `scape infer_pa`-style call per file gives (same streams, seed 1 per file)."""
+    import pickle
+    from scape_b200 import apa_core
+    us = [synth.make_utr(9100 + i, 120 + 40 * (i % 5)) for i in range(24)]
+    paths = synth.write_chunk_files(us, str(tmp_path), per_file=4, stem="many")
+    outs = apa_core.infer_files(paths, str(tmp_path), devices=[0, 0], io_workers=2)
+    assert len(outs) == 6
+
+    def load(path):
+        recs = []
+        with open(path, "rb") as fh:
+            while True:
+                try:
+                    recs.append(pickle.load(fh))
+                except EOFError:
+                    return recs
+
+    for f, (pin, pout) in enumerate(zip(paths, outs)):
+        want = fit_chunks([apa_core.read_chunk_file(pin)], seeds=[1])[0]
+        got = load(pout)
+        assert len(got) == len(want) == 4
+        for g, w in zip(got, want):
+            assert g.gene_info_str == w.gene_info_str and g.K == w.K and g.L == w.L and g.title == w.title
+            assert np.array_equal(g.alpha_arr, w.alpha_arr) and np.array_equal(g.beta_arr, w.beta_arr)
+            assert np.array_equal(g.ws, w.ws) and g.lb_arr == w.lb_arr and g.bic == w.bic
+            assert np.array_equal(g.label_arr, w.label_arr) and g.label_arr.dtype == np.int64
+            assert np.array_equal(g.cb_id_arr, w.cb_id_arr) and np.array_equal(g.readID_arr, w.readID_arr)
