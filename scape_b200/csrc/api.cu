@@ -114,6 +114,8 @@ struct Lane {
   cudaStream_t st_lik = nullptr;   // uploads, table, tensor of the staged wave (low priority)
   cudaStream_t st_aux[3] = {nullptr, nullptr, nullptr};   // parts 2..4 of a split bulk-synchronous wave (high priority)
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t st_big[4] = {nullptr, nullptr, nullptr, nullptr};   // per part: CTA-per-chain E-step kernel beside the warp-per-chain one (EstepPlan::st_big)
+  cudaEvent_t ev_big[4][2] = {};
   StagedBufs staged;
   std::unique_ptr<WorkPool> pool;  // host workers of this lane's wave loop (sleep between regions)
   PinnedBuf<char> h_stage[2];      // pinned upload staging of the staged wave, alternating per wave
@@ -178,7 +180,7 @@ struct scape_b200_handle {
   Lane lanes[kMaxLanes];
   int n_lanes = 1;
   bool tensor_fast = false;   // default grid shape: alpha rows use the constant-weight kernel
-  bool tensor_fast_edges = false;  // ... including the rows whose windows are clipped by the grid ends (SCAPE_B200_TENSOR_EDGES=0: generic kernel)
+  bool tensor_fast_edges = true;   // ... including the rows whose windows are clipped by the grid ends (SCAPE_B200_TENSOR_EDGES=0: generic kernel)
   double tf_g[kTfB * kTfW], tf_lp[kTfB * kTfW], tf_lps[kTfB];
   int tf_hw[kTfB];
   cudaEvent_t base_ev = nullptr;
@@ -305,6 +307,9 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
     for (auto& sa : L.st_aux) CU(cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, prio_hi));
     CU(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
     for (auto& e : L.ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& sb : L.st_big) CU(cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, prio_hi));
+    for (auto& eb : L.ev_big)
+      for (auto& e : eb) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : L.ev) CU(cudaEventCreate(&e));
     for (auto& e : L.ev_cl) CU(cudaEventCreate(&e));
     for (auto& e : L.staged.ev) CU(cudaEventCreate(&e));
@@ -348,6 +353,7 @@ int scape_b200_destroy(scape_b200_handle* h) {
     cudaStreamSynchronize(L.st);
     cudaStreamSynchronize(L.st_lik);
     for (auto& sa : L.st_aux) cudaStreamSynchronize(sa);
+    for (auto& sb : L.st_big) cudaStreamSynchronize(sb);
     L.release();
     for (auto& e : L.ev) cudaEventDestroy(e);
     for (auto& e : L.ev_cl) cudaEventDestroy(e);
@@ -358,6 +364,9 @@ int scape_b200_destroy(scape_b200_handle* h) {
     for (auto& sa : L.st_aux) cudaStreamDestroy(sa);
     cudaEventDestroy(L.ev_fork);
     for (auto& e : L.ev_join) cudaEventDestroy(e);
+    for (auto& sb : L.st_big) cudaStreamDestroy(sb);
+    for (auto& eb : L.ev_big)
+      for (auto& e : eb) cudaEventDestroy(e);
   }
   cudaEventDestroy(h->base_ev);
   delete h;
@@ -793,6 +802,14 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     // depend on the composition of its wave
     plan.g_small = (g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) ? g_env : 4;
   }
+  // SCAPE_B200_ESTEP_FORK (default 1): the two E-step kernels of a wide step on two streams (EstepPlan::st_big)
+  static const bool estep_fork = getenv("SCAPE_B200_ESTEP_FORK") ? atoi(getenv("SCAPE_B200_ESTEP_FORK")) != 0 : true;
+  auto fork_plan = [&](EstepPlan& pl, int part) {
+    if (!estep_fork) return;
+    pl.st_big = L.st_big[part];
+    pl.ev_big[0] = L.ev_big[part][0];
+    pl.ev_big[1] = L.ev_big[part][1];
+  };
   // The wave scheduler's hook (staging the next wave's likelihood phase on the low-priority stream)
   // fires at a step of the bulk-synchronous loop of `full`; a run without one releases it before its
   // resident kernel, so the staged wave's table / tensor kernels fill the SMs as this wave's CTAs retire.
@@ -893,6 +910,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
         EstepPlan pplan = plan;
         pplan.lists = plan.lists + size_t(p) * (2 * chains.size() + 2);
         pplan.counts = plan.counts + size_t(p) * 2 * (SCAPE_B200_NROUND + 2);
+        fork_plan(pplan, p);
         CU(cudaStreamWaitEvent(sp, L.ev_fork, 0));
         nl += launch_em_steps(L.d_chains.p, L.d_descs.p, di, S.n_small, S.n_big, any_scan, S.big_k, dr, S.n_refs_chunk,
                               int64_t(S.refs.size()) - S.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32,
@@ -904,6 +922,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
       dr += S.refs.size();
     }
   }
+  if (have_full) fork_plan(plan, 0);
   if (have_full)
     nl += launch_em_steps(L.d_chains.p, L.d_descs.p, d_idx_full, full.n_small, full.n_big, any_scan, full.big_k, d_refs_full,
                           full.n_refs_chunk, int64_t(full.refs.size()) - full.n_refs_chunk, L.d_utrs.p, L.d_chain_off.p, L.d_tensor.p, h->tensor_f32, L.d_cnt.p,
@@ -1762,7 +1781,7 @@ extern "C" int scape_b200_marginal_tensor(scape_b200_handle* h, int64_t n_frag, 
   CU(cudaMemcpyAsync(L.d_utrs.p, &d, sizeof(d), cudaMemcpyHostToDevice, L.st));
   CU(cudaMemcpyAsync(L.d_rows.p, rows.data(), sizeof(RowRef) * rows.size(), cudaMemcpyHostToDevice, L.st));
   // same dispatch as fit_batch: interior rows of a default-shaped regular grid take the constant-weight kernel
-  bool fast = h->tensor_fast && n_beta == kTfB && maxwin == kTfW && n_theta > 2 * kTfHalf;
+  bool fast = h->tensor_fast && n_beta == kTfB && (h->tensor_fast_edges || (maxwin == kTfW && n_theta > 2 * kTfHalf));
   for (int j = 0; fast && j < kTfB; j++) fast = betas[j] == h->P.betas[j];
   for (int64_t t = 1; fast && t < n_theta; t++) fast = theta[t] - theta[t - 1] == double(h->P.theta_step);
   if (fast) {

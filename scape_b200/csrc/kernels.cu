@@ -1129,6 +1129,22 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
       if (hook && step == hook_step) { if (hook_mark) hook_mark(); hook(); }
       continue;
     }
+    // wide steps: the CTA-per-chain kernel (many-fragment chains, the longer latency floor) first, on its
+    // own stream when the plan has one; the warp-per-chain kernel runs beside it
+    const int64_t n_blk = wide ? n_big : n_small + n_big;
+    const bool fork = wide && n_small > 0 && n_blk > 0 && plan.st_big != nullptr;
+    if (n_blk > 0) {
+      cudaStream_t sb = fork ? plan.st_big : st;
+      if (fork) {
+        cudaEventRecord(plan.ev_big[0], st);               // behind the previous step's scan
+        cudaStreamWaitEvent(sb, plan.ev_big[0], 0);
+      }
+      em_estep_kernel<TT><<<(unsigned)n_blk, GT, 0, sb>>>(chains_dev, descs_dev, wide ? index_dev + n_small : index_dev,
+                                                           utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
+                                                           trace_a, trace_b, trace_ws, plan.stage_chain);
+      launches++;
+      if (fork) cudaEventRecord(plan.ev_big[1], sb);
+    }
     if (n_small > 0 && wide) {
       if (plan.warp_prefetch)
         em_estep_warp_kernel<TT, false, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
@@ -1146,13 +1162,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
         launches++;
       }
     }
-    const int64_t n_blk = wide ? n_big : n_small + n_big;
-    if (n_blk > 0) {
-      em_estep_kernel<TT><<<(unsigned)n_blk, GT, 0, st>>>(chains_dev, descs_dev, wide ? index_dev + n_small : index_dev,
-                                                           utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials,
-                                                           trace_a, trace_b, trace_ws, plan.stage_chain);
-      launches++;
-    }
+    if (fork) cudaStreamWaitEvent(st, plan.ev_big[1], 0);
     mark(0);
     if (step == SCAPE_B200_NROUND || !any_scan || n_refs + n_refs_tile == 0) continue;
     launches += scan_step();

@@ -176,6 +176,11 @@ struct EstepPlan {
   bool group_steps = false;
   bool warp_prefetch = true;
   int stage_chain = 1;          // E-step kernels work on a shared-memory copy of the chain record
+  // wide steps launch two independent E-step kernels (warp per chain / CTA per chain): with st_big set,
+  // the CTA-per-chain kernel goes to that stream (forked after the previous scan, joined before the
+  // next), so that a step's E time is the longer of the two latency floors instead of their sum
+  cudaStream_t st_big = nullptr;
+  cudaEvent_t ev_big[2] = {nullptr, nullptr};
 };
 // ---- cluster-resident EM (em_cluster.cu) -----------------------------------------------------------
 // One thread-block cluster per UTR runs every chain of the UTR through all its EM iterations inside

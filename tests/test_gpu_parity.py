@@ -39,6 +39,8 @@ def _rel_err_on_finite(got, want):
     fin = want > -1e30
     assert np.array_equal(fin, got > -1e30), "sentinel pattern differs"
     assert np.all(got[~fin] == so.SENTINEL)
+    if not fin.any():
+        return 0.0
     return float(np.max(np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1e-300)))
 
 
@@ -90,6 +92,27 @@ def test_marginal_fast_and_generic_kernels_agree(engine):
         del os.environ["SCAPE_B200_TENSOR_FAST"]
     assert _rel_err_on_finite(slow, m.tensor) < TOL[engine.dtype]["tensor"]
     assert np.array_equal(fast > -1e30, slow > -1e30)
+    # the rows whose windows are clipped by the grid ends: constant-weight kernel (default) vs generic kernel
+    os.environ["SCAPE_B200_TENSOR_EDGES"] = "0"
+    try:
+        with _lib.Engine(_lib.make_params(), tensor_dtype=engine.dtype) as edge_engine:
+            mixed = edge_engine.marginal_tensor(m.theta, m.betas, m.table)
+    finally:
+        del os.environ["SCAPE_B200_TENSOR_EDGES"]
+    assert _rel_err_on_finite(mixed, m.tensor) < TOL[engine.dtype]["tensor"]
+    assert np.array_equal(fast > -1e30, mixed > -1e30)
+
+
+@pytest.mark.parametrize("n_theta", [1, 5, 22, 42, 43, 50])
+def test_marginal_tensor_on_grids_shorter_than_the_widest_window(engine, n_theta):
+    """Every alpha row of a short UTR has its windows clipped on one side or both (a grid of fewer
+    than 43 points never holds a whole beta = 70 window)."""
+    m = _model(synth.make_utr(3, 300), with_tensor=False)
+    theta = m.theta[:n_theta]
+    table = np.ascontiguousarray(m.table[:, :n_theta])
+    want = so.get_loglik_marginal_tensor(theta, m.betas, table)
+    got = engine.marginal_tensor(theta, m.betas, table)
+    assert _rel_err_on_finite(got, want) < TOL[engine.dtype]["tensor"]
 
 
 def test_marginal_tensor_on_irregular_fixed_mode_grid(engine):
@@ -268,7 +291,7 @@ def test_scheduling_knobs_do_not_change_a_bit():
     # matches the oracle: test_scale_parity); within a family nothing may.
     families = {
         "bsp": ("", "SCAPE_B200_EM=bsp", "SCAPE_B200_PREDRAW=0", "SCAPE_B200_OVERLAP=0", "SCAPE_B200_POISON=1",
-                "SCAPE_B200_SCAN_SPLIT=0", "SCAPE_B200_SCAN_TILES=1", "SCAPE_B200_SPLIT=1", "SCAPE_B200_STEP_EVENTS=1"),
+                "SCAPE_B200_SCAN_SPLIT=0", "SCAPE_B200_SCAN_TILES=1", "SCAPE_B200_SPLIT=1", "SCAPE_B200_STEP_EVENTS=1", "SCAPE_B200_ESTEP_FORK=0"),
         "tail": ("SCAPE_B200_EM=tail", "SCAPE_B200_TAIL_CHAINS=100000", "SCAPE_B200_EM=tail SCAPE_B200_WARP_PF=0",
                  "SCAPE_B200_EM=tail SCAPE_B200_STAGE_CHAIN=0", "SCAPE_B200_EM=tail SCAPE_B200_POISON=1"),
         "cluster": ("SCAPE_B200_EM=cluster", "SCAPE_B200_EM=cluster SCAPE_B200_CLUSTER=1", "SCAPE_B200_EM=cluster SCAPE_B200_CLUSTER=4",

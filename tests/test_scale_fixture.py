@@ -38,7 +38,10 @@ def test_suite_composition():
     for name, kmax in (("kmax8", 8), ("kmax10", 10)):
         fx, meta = _load(name)
         assert len(fx["index"]) == 100 and meta["params"]["n_max_apa"] == kmax
-    for name in ("cfg2", "cfg3", "cfg4", "kmax8", "kmax10"):
+    fx, meta = _load("cfg5")                       # giant UTRs (BASELINE.json configs[4], the stress sweep's far corner): 1M and 300k reads at n_max_apa = 10
+    assert sorted(int(r) for r in fx["reads"]) == [300000, 1000000] and meta["params"]["n_max_apa"] == 10
+    assert np.all(fx["chains_run"] >= 100)
+    for name in ("cfg2", "cfg3", "cfg4", "kmax8", "kmax10", "cfg5"):
         fx, meta = _load(name)
         assert not meta["errors"]
         # rng_off is cumulative within a file and restarts with every file

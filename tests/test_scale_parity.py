@@ -28,7 +28,7 @@ from _helpers import GOLD, PrePara
 pytestmark = pytest.mark.gpu
 
 SCALE = os.path.join(GOLD, "scale")
-SUITES = ["cfg2", "cfg3", "cfg4", "kmax8", "kmax10"]
+SUITES = ["cfg2", "cfg3", "cfg4", "kmax8", "kmax10", "cfg5"]
 
 
 def load_suite(name):
