@@ -798,6 +798,8 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     plan.warp_prefetch = warp_pf;
     static const int stage_chain = getenv("SCAPE_B200_STAGE_CHAIN") ? atoi(getenv("SCAPE_B200_STAGE_CHAIN")) : 1;
     plan.stage_chain = stage_chain;
+    static const int wpc_env = getenv("SCAPE_B200_WARP_WPC") ? atoi(getenv("SCAPE_B200_WARP_WPC")) : 2;   // measured: 2 warps per chain, cfg-2 E step -12 %, value +3 %; 4: no gain
+    plan.warp_wpc = (wpc_env == 1 || wpc_env == 2 || wpc_env == 4) ? wpc_env : 2;
     // 4 warps per chain for the small class whatever else is in the wave: a chain's sums must not
     // depend on the composition of its wave
     plan.g_small = (g_env == 1 || g_env == 2 || g_env == 4 || g_env == 8) ? g_env : 4;

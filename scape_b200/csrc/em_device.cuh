@@ -336,11 +336,27 @@ __device__ __forceinline__ void estep_compute(const FragIn<NK, TT>& f, int n, in
 }
 
 // Warp-per-chain E step (small fragment counts): no block barriers, reductions by shuffles.
-template <int NK, typename TT, bool PF>
+// WPC > 1: WPC warps share a chain (fragments dealt round-robin over 32 WPC lanes); the warps' sums
+// meet once per pass in shared memory behind a named barrier and are added in warp order.  A chain's
+// pass is a serial loop of N / (32 WPC) fragment passes, and a launch lasts as long as its longest chain.
+struct EPairShared {
+  double red[2][4][SCAPE_B200_KCAP + 4];     // [pass parity (guard retry)][warp of the chain][sum]
+  int hull[2][4][2];
+  int go;
+};
+__device__ __forceinline__ void pair_sync(int bar_id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+}
+
+template <int NK, typename TT, bool PF, int WPC = 1>
 __device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, const TT* __restrict__ A,
-                               const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ V) {
+                               const double* __restrict__ cnt, double* __restrict__ lz, double* __restrict__ V,
+                               EPairShared* ps = nullptr, int bar_id = 0) {
   constexpr int K = NK - 1;
+  constexpr int STRIDE = 32 * WPC;
   const int lane = threadIdx.x & 31;
+  const int sub = WPC > 1 ? ((threadIdx.x >> 5) & (WPC - 1)) : 0;
+  const int tig = sub * 32 + lane;
   const int N = u.N, npad = u.Npad, B = u.B;
   const int64_t R = u.ldR;
   const int it = ch.n_iter;
@@ -348,16 +364,16 @@ __device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, cons
     for (int j = 0; j < NK; j++) {
       const double w = ch.ws[j];
       const double lw = (w <= 0.0) ? SCAPE_SENTINEL : log(w);
-      if (lane == 0) ch.lw[j] = lw;
+      if (tig == 0) ch.lw[j] = lw;
       if (j < K) {
         const int64_t rj = (int64_t)ch.a_idx[j] * B + ch.b_idx[j];
-        for (int n = lane; n < N; n += 32) lz[(int64_t)j * npad + n] = lw + (double)A[(int64_t)n * R + rj];
+        for (int n = tig; n < N; n += STRIDE) lz[(int64_t)j * npad + n] = lw + (double)A[(int64_t)n * R + rj];
       } else {
         const double val = lw + u.unif_loglik;
-        for (int n = lane; n < N; n += 32) lz[(int64_t)j * npad + n] = val;
+        for (int n = tig; n < N; n += STRIDE) lz[(int64_t)j * npad + n] = val;
       }
     }
-    __syncwarp();
+    if (WPC > 1) pair_sync(bar_id, STRIDE); else __syncwarp();
   }
   const int k = ch.k_order[it];
   const double lwk = ch.lw[k];
@@ -375,17 +391,17 @@ __device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, cons
       // DRAM / L2 latency) are in flight while this one is computed -- ncu: 54 % of the stall
       // samples of the unpipelined loop sit on the first use of those loads
       FragIn<NK, TT> cur, nxt;
-      int n = lane;
+      int n = tig;
       if (n < N) estep_load<NK, TT>(cur, n, k, rk, npad, R, A, cnt, lz);
       while (n < N) {
-        const int nn = n + 32;
+        const int nn = n + STRIDE;
         if (nn < N) estep_load<NK, TT>(nxt, nn, k, rk, npad, R, A, cnt, lz);
         estep_compute<NK, TT>(cur, n, k, lwk, guard, npad, lz, V, red, h_lo, h_hi);
         cur = nxt;
         n = nn;
       }
     } else {
-      for (int n = lane; n < N; n += 32) estep_fragment<NK, TT>(n, k, lwk, rk, guard, npad, R, A, cnt, lz, V, red, h_lo, h_hi);
+      for (int n = tig; n < N; n += STRIDE) estep_fragment<NK, TT>(n, k, lwk, rk, guard, npad, R, A, cnt, lz, V, red, h_lo, h_hi);
     }
 #pragma unroll
     for (int j = 0; j < NK + 3; j++) {
@@ -394,19 +410,41 @@ __device__ void estep_warp_run(ChainDev& ch, ScanDesc& sd, const UtrDev& u, cons
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       red[j] = x;
     }
-    if (!guard && red[NK] < 1e-8) {          // mstep guard (:526-529), uniform across the warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      h_lo = min(h_lo, __shfl_xor_sync(0xffffffffu, h_lo, o));
+      h_hi = max(h_hi, __shfl_xor_sync(0xffffffffu, h_hi, o));
+    }
+    if (WPC > 1) {
+      const int par = guard ? 1 : 0;         // the retry pass uses the other half: no barrier between the two
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NK + 3; j++) ps->red[par][sub][j] = red[j];
+        ps->hull[par][sub][0] = h_lo;
+        ps->hull[par][sub][1] = h_hi;
+      }
+      pair_sync(bar_id, STRIDE);
+#pragma unroll
+      for (int j = 0; j < NK + 3; j++) {
+        double x = ps->red[par][0][j];
+#pragma unroll
+        for (int w = 1; w < WPC; w++) x += ps->red[par][w][j];
+        red[j] = x;
+      }
+#pragma unroll
+      for (int w = 0; w < WPC; w++) {
+        h_lo = min(h_lo, ps->hull[par][w][0]);
+        h_hi = max(h_hi, ps->hull[par][w][1]);
+      }
+    }
+    if (!guard && red[NK] < 1e-8) {          // mstep guard (:526-529), uniform across the chain's warps
       guard = true;
       continue;
     }
     break;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    h_lo = min(h_lo, __shfl_xor_sync(0xffffffffu, h_lo, o));
-    h_hi = max(h_hi, __shfl_xor_sync(0xffffffffu, h_hi, o));
-  }
   __syncwarp();
-  if (lane == 0) estep_epilogue<NK>(ch, sd, u, red, k, it, h_lo, h_hi);
+  if (tig == 0) estep_epilogue<NK>(ch, sd, u, red, k, it, h_lo, h_hi);
 }
 
 // ---- G warps per chain: named-barrier groups (used by em_estep_group_kernel and the cluster kernel) ----

@@ -571,68 +571,88 @@ em_estep_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ i
 // one WARP per chain (8 chains per CTA) for UTRs with few fragments: no block barriers at all.
 // BIGK = false handles K = 1..7 (every normal run) with 4 CTAs per SM; BIGK = true handles the
 // K = 8..15 chains that only re-runs can create and may use twice the registers.
-template <typename TT, bool BIGK, bool PF>
+// WPC = 2 / 4: that many warps per chain (8 / WPC chains per CTA), see estep_warp_run; the chain record
+// is always staged in shared memory then, and the first warp of a chain does the serial parts.
+template <typename TT, bool BIGK, bool PF, int WPC = 1>
 __global__ void __launch_bounds__(GT, BIGK ? 2 : (PF ? 3 : 4))
 em_estep_warp_kernel(ChainDev* chains, ScanDesc* descs, const int32_t* __restrict__ index, int n_index,
                      const UtrDev* __restrict__ utrs, const void* __restrict__ tensor,
                      const double* __restrict__ cnt_all, double* lz_all, double* v_all,
                      const ScanPartial* __restrict__ partials, int32_t* trace_a, int32_t* trace_b,
                      double* trace_ws, int stage) {
-  __shared__ ChainDev s_ch[GW];
-  const int slot = blockIdx.x * GW + (threadIdx.x >> 5);
-  if (slot >= n_index) return;
+  constexpr int CPB = GW / WPC;                          // chains per CTA
+  __shared__ ChainDev s_ch[CPB];
+  __shared__ EPairShared s_pair[WPC > 1 ? CPB : 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cs = warp / WPC, sub = warp % WPC, tig = sub * 32 + lane;
+  const int slot = blockIdx.x * CPB + cs;
+  if (slot >= n_index) return;                           // (every exit up to the E pass is uniform across a chain's warps)
   ChainDev& gch = chains[index[slot]];
   ScanDesc& sd = descs[index[slot]];
   if (gch.state == 0) return;
   if ((gch.K > 7) != BIGK) return;
-  ChainDev& ch = stage ? s_ch[threadIdx.x >> 5] : gch;
+  if (WPC > 1) stage = 1;
+  ChainDev& ch = stage ? s_ch[cs] : gch;
   if (stage) {
-    copy_chain(&ch, &gch, threadIdx.x & 31, 32);
-    __syncwarp();
+    copy_chain(&ch, &gch, tig, 32 * WPC);
+    if (WPC > 1) pair_sync(cs + 1, 32 * WPC); else __syncwarp();
   }
   const UtrDev u = utrs[ch.utr];
-  if (!apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws)) {
-    if (stage) { __syncwarp(); copy_chain(&gch, &ch, threadIdx.x & 31, 32); }
+  int go;
+  if (WPC > 1) {
+    if (sub == 0) {
+      go = apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws);
+      if (lane == 0) s_pair[cs].go = go;
+    }
+    pair_sync(cs + 1, 32 * WPC);
+    go = s_pair[cs].go;
+  } else {
+    go = apply_pending(ch, sd, u, partials, trace_a, trace_b, trace_ws);
+  }
+  if (!go) {
+    if (stage && sub == 0) { __syncwarp(); copy_chain(&gch, &ch, lane, 32); }
     return;
   }
   const TT* A = (const TT*)tensor + u.tensor_off;
   const double* cnt = cnt_all + u.frag_off;
   double* lz = lz_all + ch.lz_off;
   double* V = v_all + ch.v_off;
+  EPairShared* ps = &s_pair[WPC > 1 ? cs : 0];
   {
     if (!BIGK) {
       switch (ch.K) {
-        case 1: estep_warp_run<2, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 2: estep_warp_run<3, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 3: estep_warp_run<4, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 4: estep_warp_run<5, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 5: estep_warp_run<6, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 6: estep_warp_run<7, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 7: estep_warp_run<8, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 1: estep_warp_run<2, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 2: estep_warp_run<3, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 3: estep_warp_run<4, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 4: estep_warp_run<5, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 5: estep_warp_run<6, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 6: estep_warp_run<7, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 7: estep_warp_run<8, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
         default: break;
       }
     } else {
       switch (ch.K) {
-        case 8: estep_warp_run<9, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 9: estep_warp_run<10, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 10: estep_warp_run<11, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 11: estep_warp_run<12, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 12: estep_warp_run<13, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 13: estep_warp_run<14, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 14: estep_warp_run<15, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
-        case 15: estep_warp_run<16, TT, PF>(ch, sd, u, A, cnt, lz, V); break;
+        case 8: estep_warp_run<9, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 9: estep_warp_run<10, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 10: estep_warp_run<11, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 11: estep_warp_run<12, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 12: estep_warp_run<13, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 13: estep_warp_run<14, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 14: estep_warp_run<15, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
+        case 15: estep_warp_run<16, TT, PF, WPC>(ch, sd, u, A, cnt, lz, V, ps, cs + 1); break;
         default: break;
       }
     }
+    if (sub != 0) return;                                // the chain's first warp ran the epilogue
     __syncwarp();
-    if ((threadIdx.x & 31) == 0 && ch.weights_only && ch.trace_off >= 0) {
+    if (lane == 0 && ch.weights_only && ch.trace_off >= 0) {
       const int64_t o = ch.trace_off + (int64_t)(ch.n_iter - 1) * (SCAPE_B200_KCAP + 1);
       for (int j = 0; j < ch.K; j++) { trace_a[o + j] = ch.a_idx[j]; trace_b[o + j] = ch.b_idx[j]; }
       for (int j = 0; j <= ch.K; j++) trace_ws[o + j] = ch.ws[j];
     }
     __syncwarp();
   }
-  if (stage) copy_chain(&gch, &ch, threadIdx.x & 31, 32);
+  if (stage) copy_chain(&gch, &ch, lane, 32);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1033,7 +1053,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
     return (n_refs > 0) + (n_refs_tile > 0);
   };
   int launches = 0;
-  static const int warp_steps = getenv("SCAPE_B200_WARP_STEPS") ? atoi(getenv("SCAPE_B200_WARP_STEPS")) : 24;
+  static const int warp_steps = getenv("SCAPE_B200_WARP_STEPS") ? atoi(getenv("SCAPE_B200_WARP_STEPS")) : 32;   // (24 with one warp per chain; 32 measured best with two: E step -4 %)
   static const bool dbg = getenv("SCAPE_B200_DBG") != nullptr;   // print per-launch timings (development aid)
   // events around every launch group: [E step | scan] per step; read back by em_steps_elapsed()
   evs.resize(size_t(2 * (SCAPE_B200_NROUND + 1) + 1));
@@ -1145,7 +1165,20 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
       launches++;
       if (fork) cudaEventRecord(plan.ev_big[1], sb);
     }
-    if (n_small > 0 && wide) {
+    if (n_small > 0 && wide && plan.warp_wpc > 1) {
+      const int cpb = GW / plan.warp_wpc;
+      const unsigned g = (unsigned)((n_small + cpb - 1) / cpb);
+#define SCAPE_WARP_ARGS chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a, trace_b, trace_ws, plan.stage_chain
+      if (plan.warp_wpc == 2) em_estep_warp_kernel<TT, false, true, 2><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);
+      else em_estep_warp_kernel<TT, false, true, 4><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);
+      launches++;
+      if (big_k) {
+        if (plan.warp_wpc == 2) em_estep_warp_kernel<TT, true, true, 2><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);
+        else em_estep_warp_kernel<TT, true, true, 4><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);
+        launches++;
+      }
+#undef SCAPE_WARP_ARGS
+    } else if (n_small > 0 && wide) {
       if (plan.warp_prefetch)
         em_estep_warp_kernel<TT, false, true><<<(unsigned)((n_small + GW - 1) / GW), GT, 0, st>>>(
             chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a,

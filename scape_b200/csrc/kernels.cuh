@@ -176,6 +176,7 @@ struct EstepPlan {
   bool group_steps = false;
   bool warp_prefetch = true;
   int stage_chain = 1;          // E-step kernels work on a shared-memory copy of the chain record
+  int warp_wpc = 1;             // warps per chain of the warp E-step kernel (1, 2 or 4)
   // wide steps launch two independent E-step kernels (warp per chain / CTA per chain): with st_big set,
   // the CTA-per-chain kernel goes to that stream (forked after the previous scan, joined before the
   // next), so that a step's E time is the longer of the two latency floors instead of their sum
