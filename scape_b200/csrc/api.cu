@@ -296,6 +296,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
           h->tf_g[j * kTfW + d] = std::abs(d - kTfHalf) <= hw ? std::exp(h->tf_lp[j * kTfW + d] - h->tf_lps[j]) : 0.0;
       }
       h->tensor_fast = true;
+      for (int j = 0; j < kTfB; j++) h->tensor_fast = h->tensor_fast && h->tf_hw[j] == tf_default_hw(j);   // the kernel's compile-time windows
       if (const char* s2 = getenv("SCAPE_B200_TENSOR_EDGES")) h->tensor_fast_edges = atoi(s2) != 0;
     }
   }

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(TF_THREADS) tensor_interior_kernel(const UtrDe
     for (int d = 0; d < TF_W; d++) {
       const double e = sm_e[(ii + d) * TF_THREADS + tid];
 #pragma unroll
-      for (int j = 0; j < TF_B; j++) acc[j] = fma(e, c_tf_g[j * TF_W + d], acc[j]);   // constant operand
+      for (int j = 0; j < TF_B; j++)           // weights outside beta_j's own window are 0: skipped at compile time (307 of 559 FMAs remain)
+        if (d >= TF_HALF - tf_default_hw(j) && d <= TF_HALF + tf_default_hw(j)) acc[j] = fma(e, c_tf_g[j * TF_W + d], acc[j]);   // constant operand
     }
 #pragma unroll
     for (int j = 0; j < TF_B; j++) {

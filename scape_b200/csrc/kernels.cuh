@@ -123,6 +123,12 @@ struct TileRef {
   int32_t cnt;
 };
 constexpr int kTfB = 13, kTfW = 43, kTfHalf = 21, kTfTile = 8;
+// half widths (grid points) of the 13 beta windows of the default grid (betas 5..65 step 5, theta step 9:
+// floor(3 beta / 9), taichi_core.py:221-222): the constant-weight kernel skips the zero weights at compile time
+__host__ __device__ constexpr int tf_default_hw(int j) {
+  return j == 0 ? 1 : j == 1 ? 3 : j == 2 ? 5 : j == 3 ? 6 : j == 4 ? 8 : j == 5 ? 10 : j == 6 ? 11 : j == 7 ? 13 :
+         j == 8 ? 15 : j == 9 ? 16 : j == 10 ? 18 : j == 11 ? 20 : 21;
+}
 cudaError_t upload_tensor_fast_tables(const double* g, const double* lp, const double* lps, const int* hw);
 void launch_tensor_interior(const UtrDev* utrs, const TileRef* tiles, int64_t n_tiles, int max_n, const double* table,
                             void* tensor, bool f32, cudaStream_t st);
