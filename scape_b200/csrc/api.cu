@@ -143,6 +143,17 @@ struct Lane {
   EmStepEvents em_events, em_events2;   // bulk-synchronous runs: all steps / the head of the tail route
   EmStepEvents em_events_part[3];       // parts 2..4 of a split wave
   PinnedBuf<char> h_runmeta;            // per-run index lists, scan items, cluster jobs (pinned upload staging)
+  // a run whose results are collected later (the prune refits + labels of a wave finish on the GPU while
+  // the host prepares the next wave): its own pinned staging and events, so the next run can be
+  // enqueued behind it on the same stream without a host synchronisation in between
+  PinnedBuf<char> h_runmeta2;
+  PinnedBuf<double> h_scalars;          // [0] scan element counter of a normal run, [1] of a deferred one
+  cudaEvent_t ev_def[3] = {nullptr, nullptr, nullptr};   // deferred run: begin, end of the EM, everything downloaded
+  struct Deferred {
+    bool active = false;
+    ChainDev* chains = nullptr;
+    size_t n = 0;
+  } deferred;
   scape_b200_timing tm;
   std::vector<std::pair<float, float>> busy;   // kernel intervals (ms since the fit's base event)
   std::string err;
@@ -154,7 +165,7 @@ struct Lane {
     d_refs.release(); d_cjobs.release(); d_clstats.release(); d_descs.release(); d_chain_off.release(); d_chain_idx.release(); d_partials.release();
     d_lists.release(); d_counts.release();
     d_counter.release(); d_jobs.release();
-    h_chains.release(); h_refits.release(); h_runmeta.release(); h_jobs.release();
+    h_chains.release(); h_refits.release(); h_runmeta.release(); h_runmeta2.release(); h_scalars.release(); h_jobs.release();
     h_stage[0].release(); h_stage[1].release();
     staged.release();
   }
@@ -178,7 +189,14 @@ struct scape_b200_handle {
   scape_b200_params P;
   ModelConst mc;
   Lane lanes[kMaxLanes];
-  int n_lanes = 1;
+  // Lanes: independent wave loops (host thread, streams, buffers) over disjoint sets of RNG streams.
+  // Between two waves a lane's host does selection, the next wave's draws and launch lists (~1.2 ms for a
+  // cfg-2 wave) while its streams are empty; with two lanes the other lane's EM fills the GPU meanwhile
+  // (measured: e2e +8 % at 100 streams, +15 % at 12).  Un-pipelined passes (overlap off) use one lane.
+  // Fewer streams per GPU want more lanes (12 streams: 4,567 / 4,694 / 4,820 UTR/s e2e with 2 / 3 / 4 lanes;
+  // 100 streams: 11,619 with 2, 11,363 with 3): n_lanes = 0 picks 4 lanes up to 40 streams, else 2.
+  int n_lanes = 0;            // SCAPE_B200_LANES; 0 = by the batch's stream count
+  int lanes_in_use = 1;       // of the running fit
   bool tensor_fast = false;   // default grid shape: alpha rows use the constant-weight kernel
   bool tensor_fast_edges = true;   // ... including the rows whose windows are clipped by the grid ends (SCAPE_B200_TENSOR_EDGES=0: generic kernel)
   double tf_g[kTfB * kTfW], tf_lp[kTfB * kTfW], tf_lps[kTfB];
@@ -312,6 +330,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
     for (auto& eb : L.ev_big)
       for (auto& e : eb) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : L.ev) CU(cudaEventCreate(&e));
+    for (auto& e : L.ev_def) CU(cudaEventCreate(&e));
     for (auto& e : L.ev_cl) CU(cudaEventCreate(&e));
     for (auto& e : L.staged.ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&L.ev_mid, cudaEventDisableTiming));
@@ -342,7 +361,7 @@ int scape_b200_create(int device, const scape_b200_params* params, scape_b200_ha
   if (const char* s = getenv("SCAPE_B200_TENSOR")) h->tensor_f32 = (strcmp(s, "f64") != 0);
   if (const char* s = getenv("SCAPE_B200_OVERLAP")) h->overlap = atoi(s) != 0;
   if (const char* s = getenv("SCAPE_B200_POISON")) h->poison = atoi(s) != 0;
-  if (const char* s = getenv("SCAPE_B200_LANES")) h->n_lanes = std::max(1, std::min(kMaxLanes, atoi(s)));
+  if (const char* s = getenv("SCAPE_B200_LANES")) h->n_lanes = std::max(0, std::min(kMaxLanes, atoi(s)));
   *out = h;
   return 0;
 }
@@ -357,6 +376,7 @@ int scape_b200_destroy(scape_b200_handle* h) {
     for (auto& sb : L.st_big) cudaStreamSynchronize(sb);
     L.release();
     for (auto& e : L.ev) cudaEventDestroy(e);
+    for (auto& e : L.ev_def) cudaEventDestroy(e);
     for (auto& e : L.ev_cl) cudaEventDestroy(e);
     for (auto& e : L.staged.ev) cudaEventDestroy(e);
     cudaEventDestroy(L.ev_mid);
@@ -573,15 +593,25 @@ int build_step_set(scape_b200_handle* h, const Chains& chains, const std::vector
 // chains must be ordered by UTR (they are generated that way).
 // `enqueued` (optional) runs on the host after every launch and the download have been enqueued and
 // before the stream is synchronised: host work that hides under the run, or more work for the stream.
+// `defer`: return once everything is enqueued (no synchronisation, no accounting); the caller collects the
+// run with finish_deferred_run() before it touches the chains or starts another deferred run.
 int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chains, const std::vector<UtrDev>& utrs_host,
-               bool want_trace = false, const std::function<int()>& enqueued = nullptr) {
+               bool want_trace = false, const std::function<int()>& enqueued = nullptr, bool defer = false) {
   static const bool host_dbg_rc = getenv("SCAPE_B200_DBG_HOST") != nullptr;
   const double t_rc0 = now_ms();
+  if (defer) {
+    if (L.deferred.active) return fail(-5, "internal: a deferred run is still open");
+    L.deferred.active = true;
+    L.deferred.chains = chains_p;
+    L.deferred.n = n_chains;
+  }
+  CU(L.h_scalars.resize(2));
   if (n_chains == 0) {                 // nothing to run: the caller's follow-up work still gets its synchronisation
     if (enqueued) {
       if (int rc = enqueued()) return rc;
-      CU(cudaStreamSynchronize(L.st));
+      if (!defer) CU(cudaStreamSynchronize(L.st));
     }
+    if (defer) CU(cudaEventRecord(L.ev_def[2], L.st));
     return 0;
   }
   struct Span {
@@ -623,7 +653,10 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   // E step (latency-bound, FP64 pipe ~20 % busy) then runs under the other half's scan (tensor-pipe
   // bound).  UTRs are dealt alternately in order of decreasing cost.  SCAPE_B200_SPLIT=0 switches it
   // off; runs with traces, few UTRs or weights-only chains are never split.
-  static const int split_env = std::max(1, std::min(kMaxSplit, getenv("SCAPE_B200_SPLIT") ? atoi(getenv("SCAPE_B200_SPLIT")) : 2));
+  // (default: 2 parts with a single lane; with several lanes the lanes already interleave, and splitting their
+  // half-size waves again measured slower: 10,951 vs 11,619 UTR/s e2e on cfg-2)
+  static const int split_knob = getenv("SCAPE_B200_SPLIT") ? atoi(getenv("SCAPE_B200_SPLIT")) : 0;
+  const int split_env = std::max(1, std::min(kMaxSplit, split_knob > 0 ? split_knob : (h->lanes_in_use > 1 ? 1 : 2)));
   int n_parts = 1;
   if (split_env > 1 && h->overlap && !want_trace && mode == kRouteBsp) {
     std::vector<std::pair<double, size_t>> order;
@@ -748,8 +781,9 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
     const size_t o_idx = 0, o_refs = o_idx + up16(4 * n_index), o_off = o_refs + up16(sizeof(ScanRef) * n_refs),
                  o_jobs = o_off + up16(4 * (W + 1)), o_end = o_jobs + up16(sizeof(ClusterJob) * cjobs.size());
-    CU(L.h_runmeta.resize(o_end + 16));
-    char* b = L.h_runmeta.p;
+    PinnedBuf<char>& meta = defer ? L.h_runmeta2 : L.h_runmeta;
+    CU(meta.resize(o_end + 16));
+    char* b = meta.p;
     int32_t* hi = (int32_t*)(b + o_idx);
     std::copy(full.index.begin(), full.index.end(), hi);
     std::copy(head.index.begin(), head.index.end(), hi + full.index.size());
@@ -775,7 +809,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   }
   CU(cudaMemsetAsync(L.d_counter.p, 0, sizeof(double), L.st));
   L.tm.h2d_bytes += double(sizeof(ChainDev) * chains.size() + sizeof(ScanRef) * n_refs + 4 * (W + 1) + 4 * n_index);
-  CU(cudaEventRecord(L.ev[4], L.st));
+  CU(cudaEventRecord(defer ? L.ev_def[0] : L.ev[4], L.st));
   const double t_rc1 = now_ms();
   {
     // per-step events only where somebody reads them (un-pipelined passes, SCAPE_B200_STEP_EVENTS=1)
@@ -936,14 +970,20 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   for (int p = 1; p < n_parts; p++)
     if (!parts[p - 1].index.empty()) CU(cudaStreamWaitEvent(L.st, L.ev_join[p - 1], 0));
   CU(cudaGetLastError());
-  CU(cudaEventRecord(L.ev[5], L.st));
-  double scan_elems = 0;
+  CU(cudaEventRecord(defer ? L.ev_def[1] : L.ev[5], L.st));
+  // (pinned destinations: a pageable one would make the copy call wait for the whole run)
+  double& scan_elems = L.h_scalars.p[defer ? 1 : 0];
   CU(cudaMemcpyAsync(chains.data(), L.d_chains.p, sizeof(ChainDev) * chains.size(), cudaMemcpyDeviceToHost, L.st));
   CU(cudaMemcpyAsync(&scan_elems, L.d_counter.p, sizeof(double), cudaMemcpyDeviceToHost, L.st));
   const double t_rc2 = now_ms();
   if (enqueued)
     if (int rc = enqueued()) { cudaStreamSynchronize(L.st); return rc; }
   const double t_rc3 = now_ms();
+  L.tm.launches += nl;
+  if (defer) {
+    CU(cudaEventRecord(L.ev_def[2], L.st));
+    return 0;
+  }
   CU(cudaStreamSynchronize(L.st));
   if (host_dbg_rc && chains.size() >= 1000) {
     static double acc[5] = {0, 0, 0, 0, 0};
@@ -976,7 +1016,6 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     L.tm.resident_ms += cms;
     L.tm.resident_launches += 1;
   }
-  L.tm.launches += nl;
   for (auto& c : chains)
     if (c.error) return fail(-7, "non-finite grid-search scores (a NaN reached max_alpha_beta)");
   for (auto& c : chains) {
@@ -986,6 +1025,30 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
     if (route[size_t(c.utr)] != kRouteBsp) L.tm.resident_grid_flops += (c.grid_rows - c.grid_rows_head) * double(u.N) * 2.0;
   }
   L.tm.em_scan_bytes += scan_elems * (h->tensor_f32 ? 4.0 : 8.0);   // what the batched scans really load
+  return 0;
+}
+
+// Collect a deferred run: wait for its downloads, then the accounting run_chains does after its own
+// synchronisation (deferred runs are never timed per step and never take the resident routes).
+int finish_deferred_run(scape_b200_handle* h, Lane& L, const std::vector<UtrDev>& utrs_host) {
+  if (!L.deferred.active) return 0;
+  L.deferred.active = false;
+  CU(cudaEventSynchronize(L.ev_def[2]));
+  if (L.deferred.n == 0) return 0;
+  L.tm.d2h_bytes += double(sizeof(ChainDev) * L.deferred.n);
+  float ms = 0, t0 = 0;
+  CU(cudaEventElapsedTime(&ms, L.ev_def[0], L.ev_def[1]));
+  CU(cudaEventElapsedTime(&t0, h->base_ev, L.ev_def[0]));
+  L.tm.em_ms += ms;
+  L.busy.emplace_back(t0, t0 + ms);
+  for (size_t i = 0; i < L.deferred.n; i++) {
+    const ChainDev& c = L.deferred.chains[i];
+    if (c.error) return fail(-7, "non-finite grid-search scores (a NaN reached max_alpha_beta)");
+    const UtrDev& u = utrs_host[size_t(c.utr)];
+    L.tm.em_grid_bytes += c.grid_rows * double(u.N) * 8.0;
+    L.tm.em_grid_flops += c.grid_rows * double(u.N) * 2.0;
+  }
+  L.tm.em_scan_bytes += L.h_scalars.p[1] * (h->tensor_f32 ? 4.0 : 8.0);
   return 0;
 }
 
@@ -1265,11 +1328,17 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
                 1e3 * hp[6] / double(std::max<int64_t>(*waves, 1)), (long long)*waves);
     }
   } host_profile{host_dbg, hp, &L.tm.waves};
-  std::function<void()> pending_assemble;     // deferred result assembly of the previous wave
+  std::function<int()> pending_assemble;      // deferred collection (refits, labels) + result assembly of the previous wave
   struct FlushPending {
-    std::function<void()>& f;
-    ~FlushPending() { if (f) f(); }
+    std::function<int()>& f;
+    ~FlushPending() { if (f) f(); }            // (error paths: the stream is drained, the results are dropped with the error)
   } flush_pending{pending_assemble};
+  // The prune refits + labels of a wave's last sweep are not waited for: the host goes on to the next
+  // wave (draws joined, chain records, launch lists, uploads) while they run, and collects them from the
+  // next run's `enqueued` callback.  Off in un-pipelined / per-step-timed passes.
+  static const bool defer_env = getenv("SCAPE_B200_DEFER") ? atoi(getenv("SCAPE_B200_DEFER")) != 0 : true;
+  static const int ev_env_lane = getenv("SCAPE_B200_STEP_EVENTS") ? atoi(getenv("SCAPE_B200_STEP_EVENTS")) : -1;
+  const bool defer_ok = defer_env && overlap && !(ev_env_lane >= 0 ? ev_env_lane != 0 : !overlap);
   if (int rc = stage()) return rc;
   for (;;) {
     if (st_wave.empty()) break;
@@ -1292,6 +1361,9 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
 
     std::vector<LabelDev> jobs;
     bool labels_enqueued = false, final_sweep = false;
+    size_t deferred_refits = 0;
+    std::vector<size_t> deferred_owner;
+    bool wave_deferred = false;
     // ---- sweeps: main K range, then re-run ranges while K == n_max (apa_core.py:1023-1030) -------
     for (;;) {
       double tr0 = now_ms();
@@ -1320,7 +1392,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       {
         // the previous wave's results are written out while the GPU runs this wave's EM
         std::function<int()> cb;
-        if (pending_assemble) cb = [&]() { pending_assemble(); pending_assemble = nullptr; return 0; };
+        if (pending_assemble) cb = [&]() { const int rc = pending_assemble(); pending_assemble = nullptr; return rc; };
         const int rc = run_chains(h, L, chains, n_chains, ud, false, cb);
         L.em_events.hook = nullptr;
         L.em_events.mark = nullptr;
@@ -1460,12 +1532,21 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
         labels_enqueued = true;
         return 0;
       };
+      const bool deferred = final_sweep && defer_ok;
       {
         const std::function<int()> cb = final_sweep ? std::function<int()>(enqueue_labels) : std::function<int()>();
-        if (int rc = run_chains(h, L, refits, n_refits, ud, false, cb)) {
+        if (int rc = run_chains(h, L, refits, n_refits, ud, false, cb, deferred)) {
           if (predraw_thread.joinable()) predraw_thread.join();
           return rc;
         }
+      }
+      if (deferred) {
+        // (a last sweep never asks for a re-run: refitted UTRs have K < k_max, the others were checked above)
+        for (size_t i = 0; i < W; i++) wave[i].done = true;
+        deferred_refits = n_refits;
+        deferred_owner = refit_owner;
+        wave_deferred = true;
+        break;
       }
       for (size_t j = 0; j < n_refits; j++) {
         WaveUtr& w = wave[refit_owner[j]];
@@ -1501,26 +1582,43 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
       }
     }
     lap(3);
-    {
+    // label timing + the per-read labels out of the pinned download buffer (the next wave's download reuses it)
+    auto collect_labels = [h, &L, out, bt](const std::vector<WaveUtr>& wv, const std::vector<UtrDev>& udv) -> int {
       float a = 0;
       CU(cudaEventElapsedTime(&a, L.ev[6], L.ev[7]));
       L.tm.label_ms += a;
       float tb = 0;
       CU(cudaEventElapsedTime(&tb, h->base_ev, L.ev[6]));
       L.busy.emplace_back(tb, tb + a);
-    }
-    lap(4);
+      for (size_t i = 0; i < wv.size(); i++) {
+        const int64_t u = wv[i].u;
+        memcpy(out->label + bt->read_off[u], L.h_labels64.p + udv[i].read_off, sizeof(int64_t) * size_t(udv[i].n_reads));
+      }
+      return 0;
+    };
     // ---- results: assembled on the host while the GPU runs the next wave's EM (or at the end) ---------
     {
       std::shared_ptr<std::vector<WaveUtr>> wv = std::make_shared<std::vector<WaveUtr>>(std::move(wave));
       std::shared_ptr<std::vector<UtrDev>> udv = std::make_shared<std::vector<UtrDev>>(ud);
-      // the per-read labels leave the pinned download buffer now (the next wave's download reuses it);
-      // everything else is copied out of the wave records later
-      for (size_t i = 0; i < W; i++) {
-        const int64_t u = (*wv)[i].u;
-        memcpy(out->label + bt->read_off[u], L.h_labels64.p + (*udv)[i].read_off, sizeof(int64_t) * size_t((*udv)[i].n_reads));
-      }
-      pending_assemble = [&prep, out, wv]() {
+      if (!wave_deferred)
+        if (int rc = collect_labels(*wv, *udv)) return rc;
+      lap(4);
+      const size_t n_def = deferred_refits;
+      const std::vector<size_t> owner = deferred_owner;
+      pending_assemble = [&prep, out, wv, udv, h, &L, wave_deferred, n_def, owner, collect_labels]() -> int {
+        if (wave_deferred) {
+          // the refits + labels enqueued a wave ago: wait for their downloads (long there by now)
+          if (int rc = finish_deferred_run(h, L, *udv)) return rc;
+          const ChainDev* refits = L.h_refits.p;
+          for (size_t j = 0; j < n_def; j++) {
+            WaveUtr& w = (*wv)[owner[j]];
+            w.best = refits[j];
+            w.chains_run += 1;
+            w.work += double(refits[j].n_iter) * (*udv)[owner[j]].N * (refits[j].K + 1);
+            w.iters += refits[j].n_iter;
+          }
+          if (int rc = collect_labels(*wv, *udv)) return rc;
+        }
         for (size_t i = 0; i < wv->size(); i++) {
           const WaveUtr& w = (*wv)[i];
           const UtrPrep& p = prep[size_t(w.u)];
@@ -1539,6 +1637,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
           out->path[u * 4 + 2] = c.K; out->path[u * 4 + 3] = w.chains_run;
           out->em_work[u * 2] = w.work; out->em_work[u * 2 + 1] = w.iters;
         }
+        return 0;
       };
     }
     lap(5);
@@ -1551,6 +1650,11 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
     if (!next_staged)
       if (int rc = stage()) return rc;
     lap(6);
+  }
+  if (pending_assemble) {
+    const int rc = pending_assemble();
+    pending_assemble = nullptr;
+    if (rc) return rc;
   }
   return 0;
 }
@@ -1648,7 +1752,9 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   for (int64_t u = 0; u < U; u++) stream_of[size_t(u)] = bt->stream_id[u];
 
   // ---- lanes: streams are dealt round-robin, every lane runs its waves in its own thread ---------
-  const int n_lanes = std::max(1, std::min(h->n_lanes, S));
+  const int lanes_wanted = h->n_lanes > 0 ? h->n_lanes : (S <= 40 ? 4 : 2);
+  const int n_lanes = std::max(1, std::min(h->overlap ? lanes_wanted : 1, S));
+  h->lanes_in_use = n_lanes;
   std::vector<std::vector<int>> lane_streams(static_cast<size_t>(n_lanes));
   for (int s = 0; s < S; s++) lane_streams[size_t(s % n_lanes)].push_back(s);
   const int total_threads = h->host_threads > 0 ? h->host_threads : default_host_threads();
