@@ -194,7 +194,8 @@ struct scape_b200_handle {
   // cfg-2 wave) while its streams are empty; with two lanes the other lane's EM fills the GPU meanwhile
   // (measured: e2e +8 % at 100 streams, +15 % at 12).  Un-pipelined passes (overlap off) use one lane.
   // Fewer streams per GPU want more lanes (12 streams: 4,567 / 4,694 / 4,820 UTR/s e2e with 2 / 3 / 4 lanes;
-  // 100 streams: 11,619 with 2, 11,363 with 3): n_lanes = 0 picks 4 lanes up to 40 streams, else 2.
+  // 100 streams: 11,619 with 2, 11,363 with 3; a 25-stream slice of the heavy-tailed cfg-3: 4,197 with 2, 3,982
+  // with 4, 3,718 with 1): n_lanes = 0 picks 4 lanes up to 16 streams, 3 up to 40, else 2.
   int n_lanes = 0;            // SCAPE_B200_LANES; 0 = by the batch's stream count
   int lanes_in_use = 1;       // of the running fit
   bool tensor_fast = false;   // default grid shape: alpha rows use the constant-weight kernel
@@ -1752,7 +1753,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
   for (int64_t u = 0; u < U; u++) stream_of[size_t(u)] = bt->stream_id[u];
 
   // ---- lanes: streams are dealt round-robin, every lane runs its waves in its own thread ---------
-  const int lanes_wanted = h->n_lanes > 0 ? h->n_lanes : (S <= 40 ? 4 : 2);
+  const int lanes_wanted = h->n_lanes > 0 ? h->n_lanes : (S <= 16 ? 4 : S <= 40 ? 3 : 2);
   const int n_lanes = std::max(1, std::min(h->overlap ? lanes_wanted : 1, S));
   h->lanes_in_use = n_lanes;
   std::vector<std::vector<int>> lane_streams(static_cast<size_t>(n_lanes));
