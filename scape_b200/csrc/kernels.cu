@@ -367,35 +367,43 @@ __global__ void __launch_bounds__(TF_THREADS) tensor_interior_kernel(const UtrDe
       for (int j = 0; j < TF_B; j++)           // weights outside beta_j's own window are 0: skipped at compile time (307 of 559 FMAs remain)
         if (d >= TF_HALF - tf_default_hw(j) && d <= TF_HALF + tf_default_hw(j)) acc[j] = fma(e, c_tf_g[j * TF_W + d], acc[j]);   // constant operand
     }
+    unsigned need = 0;                         // betas that take the exact path below
 #pragma unroll
     for (int j = 0; j < TF_B; j++) {
-      double res;
-      const int hw = c_tf_hw[j];
+      double res = SCAPE_SENTINEL;
+      const int hw = tf_default_hw(j);
       const double dl = edge ? s_dl[ii][j] : 0.0;
       if (acc[j] > 1e-290) {
         res = (log(acc[j]) + M) + dl;
-      } else if ((live & (((2ull << (2 * hw)) - 1ull) << (ii + TF_HALF - hw))) == 0ull) {
-        // beta_j's own window holds incompatible thetas only (the common case at the edge of the
-        // fragment's compatible range): the exact path below would return the sentinel
-        res = SCAPE_SENTINEL;
-      } else {
-        // exact two-pass log-sum-exp over beta_j's own (existing) window (taichi_core.py:41-54, 172-179)
-        const int lo = edge ? s_lo[ii][j] : TF_HALF - hw, hi = edge ? s_hi[ii][j] : TF_HALF + hw;
-        const double* col = tab + (int64_t)(c_first + ii) * ld;     // column of d = 0 for this row
-        const double* lp = c_tf_lp + j * TF_W;
-        const double lps = c_tf_lps[j] - dl;
-        double m = -CUDART_INF;
-        for (int d = lo; d <= hi; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
-        if (m < -1e30) {
-          res = SCAPE_SENTINEL;                // log(w) + sentinel == sentinel in FP64
-        } else {
-          double sum = 0.0;
-          for (int d = lo; d <= hi; d++) {
-            const double a = ((col[(int64_t)d * ld] + lp[d]) - lps) - m;
-            if (a > -746.0) sum += exp(a);
-          }
-          res = log(sum) + m;
+      } else if ((live & (((2ull << (2 * hw)) - 1ull) << (ii + TF_HALF - hw))) != 0ull) {
+        need |= 1u << j;
+      }
+      // (else: beta_j's own window holds incompatible thetas only -- the common case at the edge of the
+      // fragment's compatible range -- and the exact path would return the sentinel)
+      out[ii * TF_B + j] = TT(res);
+    }
+    // exact two-pass log-sum-exp over beta_j's own (existing) window (taichi_core.py:41-54, 172-179): rare,
+    // and ONE copy of the code behind the 13 unrolled common paths (inlined into each of them it spread
+    // the hot path over 190 KB of instructions: 27 % of the stall samples were instruction fetch)
+    while (need) {
+      const int j = __ffs(need) - 1;
+      need &= need - 1;
+      const int hw = c_tf_hw[j];
+      const double dl = edge ? s_dl[ii][j] : 0.0;
+      const int lo = edge ? s_lo[ii][j] : TF_HALF - hw, hi = edge ? s_hi[ii][j] : TF_HALF + hw;
+      const double* col = tab + (int64_t)(c_first + ii) * ld;     // column of d = 0 for this row
+      const double* lp = c_tf_lp + j * TF_W;
+      const double lps = c_tf_lps[j] - dl;
+      double m = -CUDART_INF;
+      for (int d = lo; d <= hi; d++) m = fmax(m, (col[(int64_t)d * ld] + lp[d]) - lps);
+      double res = SCAPE_SENTINEL;             // log(w) + sentinel == sentinel in FP64
+      if (m >= -1e30) {
+        double sum = 0.0;
+        for (int d = lo; d <= hi; d++) {
+          const double a = ((col[(int64_t)d * ld] + lp[d]) - lps) - m;
+          if (a > -746.0) sum += exp(a);
         }
+        res = log(sum) + m;
       }
       out[ii * TF_B + j] = TT(res);
     }
