@@ -172,3 +172,22 @@ def test_chunk_batch_layout_cache_is_per_dtype():
     assert batch.frames[1][0].dtype == np.float64 and np.isnan(batch.frames[1][0][3])
     assert np.array_equal(batch.frames[1][0][:3], np.array(b["cb_id"])[:3])
     assert batch.frames[2][0].dtype == np.int64
+
+
+def test_chunk_batch_packed_into_scratch_equals_fresh_arrays():
+    """`packed(scratch)` (pooled infer_files: columns concatenated into arrays kept on the engine) returns
+    the same columns as `packed()`, also when a smaller batch reuses the scratch of a bigger one."""
+    from scape_b200 import synth
+    from scape_b200.apa_core import ChunkBatch
+    scratch = {}
+    for ids in ([5, 6, 7, 8], [9], []):
+        batch = ChunkBatch()
+        for k, i in enumerate(ids):
+            u = synth.make_utr(i, 60 + 10 * k)
+            batch.add(u.gene_info_str, synth.to_dataframe(u), k % 2)
+        fresh = batch.packed()
+        kept = batch.packed(scratch)
+        assert len(fresh) == len(kept)
+        for a, b in zip(fresh, kept):
+            assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+    assert len(scratch["cols"]) == 4
