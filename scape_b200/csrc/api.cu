@@ -598,7 +598,7 @@ int build_step_set(scape_b200_handle* h, const Chains& chains, const std::vector
 // run with finish_deferred_run() before it touches the chains or starts another deferred run.
 int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chains, const std::vector<UtrDev>& utrs_host,
                bool want_trace = false, const std::function<int()>& enqueued = nullptr, bool defer = false) {
-  static const bool host_dbg_rc = getenv("SCAPE_B200_DBG_HOST") != nullptr;
+  static const bool host_dbg_rc = scape_env_on("SCAPE_B200_DBG_HOST");
   const double t_rc0 = now_ms();
   if (defer) {
     if (L.deferred.active) return fail(-5, "internal: a deferred run is still open");
@@ -857,7 +857,7 @@ int run_chains(scape_b200_handle* h, Lane& L, ChainDev* chains_p, size_t n_chain
   auto fire_hook = [&]() { if (hook_pending) { hook_pending = false; L.em_events.hook(); } };
   int nl = 0;
   bool resident_timed = false;
-  static const bool cl_dbg = getenv("SCAPE_B200_DBG") != nullptr;
+  static const bool cl_dbg = scape_env_on("SCAPE_B200_DBG");
   if (!cjobs.empty()) {
     static const int c_env = getenv("SCAPE_B200_CLUSTER") ? atoi(getenv("SCAPE_B200_CLUSTER")) : 0;
     int csize = 8;
@@ -1313,7 +1313,7 @@ int run_lane(FitShared& F, Lane& L, const std::vector<int>& my_streams) {
   double predraw_ms = 0;
 
   // development aid (SCAPE_B200_DBG_HOST=1): wall clock of the wave loop's sections
-  static const bool host_dbg = getenv("SCAPE_B200_DBG_HOST") != nullptr;
+  static const bool host_dbg = scape_env_on("SCAPE_B200_DBG_HOST");
   double hp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double hp_mark = now_ms();
   auto lap = [&](int k) { const double t = now_ms(); hp[k] += t - hp_mark; hp_mark = t; };

@@ -12,7 +12,7 @@
 namespace scape {
 
 static bool dbg_env() {
-  static const bool on = getenv("SCAPE_B200_DBG") != nullptr;
+  static const bool on = scape_env_on("SCAPE_B200_DBG");
   return on;
 }
 
@@ -1063,7 +1063,7 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
   };
   int launches = 0;
   static const int warp_steps = getenv("SCAPE_B200_WARP_STEPS") ? atoi(getenv("SCAPE_B200_WARP_STEPS")) : 32;   // (24 with one warp per chain; 32 measured best with two: E step -4 %)
-  static const bool dbg = getenv("SCAPE_B200_DBG") != nullptr;   // print per-launch timings (development aid)
+  static const bool dbg = scape_env_on("SCAPE_B200_DBG");   // print per-launch timings (development aid)
   // events around every launch group: [E step | scan] per step; read back by em_steps_elapsed()
   evs.resize(size_t(2 * (SCAPE_B200_NROUND + 1) + 1));
   for (auto& e : evs)

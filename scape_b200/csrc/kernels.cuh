@@ -28,6 +28,14 @@
 
 #include "../../include/scape_b200.h"
 
+#include <cstdlib>
+#include <cstring>
+// development-aid switches: on when the variable is set to anything but "" or "0"
+inline bool scape_env_on(const char* name) {
+  const char* s = getenv(name);
+  return s && *s && strcmp(s, "0") != 0;
+}
+
 namespace scape {
 
 #define SCAPE_SENTINEL (-3.4028234663852886e38)
