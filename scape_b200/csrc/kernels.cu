@@ -1178,7 +1178,8 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
       const int cpb = GW / plan.warp_wpc;
       const unsigned g = (unsigned)((n_small + cpb - 1) / cpb);
 #define SCAPE_WARP_ARGS chains_dev, descs_dev, index_dev, (int)n_small, utrs_dev, tensor, cnt, lz, vbuf, (const ScanPartial*)partials, trace_a, trace_b, trace_ws, plan.stage_chain
-      if (plan.warp_wpc == 2) em_estep_warp_kernel<TT, false, true, 2><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);
+      if (plan.warp_wpc == 2 && !plan.warp_prefetch) em_estep_warp_kernel<TT, false, false, 2><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);   // 64 registers, 4 CTAs per SM
+      else if (plan.warp_wpc == 2) em_estep_warp_kernel<TT, false, true, 2><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);
       else em_estep_warp_kernel<TT, false, true, 4><<<g, GT, 0, st>>>(SCAPE_WARP_ARGS);
       launches++;
       if (big_k) {
