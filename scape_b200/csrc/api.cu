@@ -1769,6 +1769,7 @@ extern "C" int scape_b200_fit_batch(scape_b200_handle* h, const scape_b200_batch
     L.busy.clear();
     L.rc = 0;
     L.err.clear();
+    L.deferred = Lane::Deferred{};     // (a fit that ended with an error may have left one open)
   }
   {
     std::vector<std::thread> workers;
