@@ -763,7 +763,22 @@ struct ScanShared {
 // B fragments from V staged in shared memory with a conflict-free pitch.  The operand reuse that a
 // CUDA-core version has to buy with shared-memory broadcasts (128 B/clk/SM, i.e. <= 1 FMA pair per
 // 4 SM cycles) happens inside the MMA datapath here.
-template <int NG, typename TT>
+// f32 -> f64 of a tensor element.  F2F.F64.F32 runs on the XU pipe (16 per clock and SM); for the finite,
+// normal values a tensor holds (log-likelihoods and the float sentinel) the widening is also an exponent
+// re-bias and a mantissa shift in integer instructions.  CVT: 0 = all on the XU pipe, 1 = rows with odd mi
+// in integer instructions, 2 = all in integer instructions.  (+-0, which only the pitch padding holds,
+// would come out as 2^-127; those columns are never candidate rows, and slack fragments meet V = 0.)
+template <int CVT>
+__device__ __forceinline__ double scan_widen(float f, int mi) {
+  if (CVT == 0 || (CVT == 1 && (mi & 1) == 0)) return (double)f;
+  const uint32_t x = __float_as_uint(f);
+  const uint32_t hi = (((x & 0x7fffffffu) >> 3) + 0x38000000u) | (x & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(x << 29));
+}
+template <int CVT>
+__device__ __forceinline__ double scan_widen(double d, int) { return d; }
+
+template <int NG, typename TT, int CVT = 0>
 __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __restrict__ descs, const UtrDev& u,
                                               const TT* __restrict__ A, const double* __restrict__ v_all,
                                               ScanPartial* partials, int first, int cnt, int blk, double* Vs,
@@ -851,7 +866,7 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __
         double a[4];
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
-          a[mi] = (double)pre[p][mi];
+          a[mi] = scan_widen<CVT>(pre[p][mi], mi);
           pre[p][mi] = __ldg(pp[mi]);
           pp[mi] += kstep;
         }
@@ -873,7 +888,7 @@ __device__ __forceinline__ void scan_subbatch(ScanShared& sh, const ScanDesc* __
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-          for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], (double)pre[p][mi], b[ni]);
+          for (int ni = 0; ni < NG; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], scan_widen<CVT>(pre[p][mi], mi), b[ni]);
       }
     }
   }
@@ -979,7 +994,7 @@ __device__ __forceinline__ void scan_subbatch_tiles(ScanShared& sh, const ScanDe
 
 // one CTA per (UTR, block of SCAN_ROWS candidate rows); TILES: the tile path (its own kernel: the two
 // paths' register allocations do not disturb each other)
-template <typename TT, bool TILES>
+template <typename TT, bool TILES, int CVT = 0>
 __global__ void __launch_bounds__(GT, 2)
 em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ descs, const UtrDev* __restrict__ utrs,
                const int32_t* __restrict__ utr_chain_off, const void* __restrict__ tensor,
@@ -1018,7 +1033,7 @@ em_scan_kernel(const ScanRef* __restrict__ refs, const ScanDesc* __restrict__ de
   }
   double* Vs = sm_dyn;                                           // [SCAN_GB][SCAN_VPITCH]
   const TT* A = (const TT*)tensor + u.tensor_off;
-#define SCAN_CALL(G) scan_subbatch<G, TT>(sh, descs, u, A, v_all, partials, first, cnt, ref.blk, Vs, scan_elems)
+#define SCAN_CALL(G) scan_subbatch<G, TT, CVT>(sh, descs, u, A, v_all, partials, first, cnt, ref.blk, Vs, scan_elems)
   const int gb = ref.gb;
   for (int first = ref.sb * gb; first < n_list; first += ref.nsb * gb) {
     const int cnt = min(gb, n_list - first);
@@ -1044,13 +1059,26 @@ static int launch_em_steps_t(ChainDev* chains_dev, ScanDesc* descs_dev, const in
                              std::vector<int>& kinds, int& scan_launches, const std::function<void()>& hook,
                              const std::function<void()>& hook_mark, int hook_step, const EstepPlan& plan, int n_steps, bool timing) {
   const size_t smem = (size_t)SCAN_GB * SCAN_VPITCH * sizeof(double);
+  // f32 -> f64 widening of the tensor elements in the scan: SCAPE_B200_SCAN_CVT = 0 XU pipe, 1 half in integer
+  // instructions, 2 all (only with f32 storage; identical values)
+  static const int scan_cvt_env = getenv("SCAPE_B200_SCAN_CVT") ? atoi(getenv("SCAPE_B200_SCAN_CVT")) : 0;
+  const int scan_cvt = sizeof(TT) == 4 ? scan_cvt_env : 0;
   cudaFuncSetAttribute(em_scan_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (scan_cvt == 1) cudaFuncSetAttribute(em_scan_kernel<TT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (scan_cvt == 2) cudaFuncSetAttribute(em_scan_kernel<TT, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(em_scan_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanTileVBytes);
   // the scan of one step: work items of the chunked path first (n_refs of them), then those of the tile path
   auto scan_step = [&]() {
     if (n_refs > 0) {
-      em_scan_kernel<TT, false><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
-                                                                      vbuf, (ScanPartial*)partials, scan_elems);
+      if (scan_cvt == 1)
+        em_scan_kernel<TT, false, 1><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
+                                                                           vbuf, (ScanPartial*)partials, scan_elems);
+      else if (scan_cvt == 2)
+        em_scan_kernel<TT, false, 2><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
+                                                                           vbuf, (ScanPartial*)partials, scan_elems);
+      else
+        em_scan_kernel<TT, false><<<(unsigned)n_refs, GT, smem, st>>>(refs_dev, descs_dev, utrs_dev, utr_chain_off_dev, tensor,
+                                                                        vbuf, (ScanPartial*)partials, scan_elems);
       scan_launches++;
     }
     if (n_refs_tile > 0) {
