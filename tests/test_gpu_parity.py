@@ -292,7 +292,8 @@ def test_scheduling_knobs_do_not_change_a_bit():
     families = {
         "bsp": ("", "SCAPE_B200_EM=bsp", "SCAPE_B200_PREDRAW=0", "SCAPE_B200_OVERLAP=0", "SCAPE_B200_POISON=1",
                 "SCAPE_B200_SCAN_SPLIT=0", "SCAPE_B200_SCAN_TILES=1", "SCAPE_B200_SPLIT=1", "SCAPE_B200_STEP_EVENTS=1", "SCAPE_B200_ESTEP_FORK=0", "SCAPE_B200_DEFER=0",
-                "SCAPE_B200_LANES=1", "SCAPE_B200_LANES=1 SCAPE_B200_SPLIT=1", "SCAPE_B200_LANES=3", "SCAPE_B200_LANES=2 SCAPE_B200_SPLIT=2"),
+                "SCAPE_B200_LANES=1", "SCAPE_B200_LANES=1 SCAPE_B200_SPLIT=1", "SCAPE_B200_LANES=3", "SCAPE_B200_LANES=2 SCAPE_B200_SPLIT=2",
+                "SCAPE_B200_SCAN_CVT=2"),
         # warps per chain of the warp E-step kernel (default 2): another summation tree each
         "bsp_wpc1": ("SCAPE_B200_WARP_WPC=1", "SCAPE_B200_WARP_WPC=1 SCAPE_B200_SPLIT=1", "SCAPE_B200_WARP_WPC=1 SCAPE_B200_WARP_PF=0"),
         "bsp_wpc4": ("SCAPE_B200_WARP_WPC=4", "SCAPE_B200_WARP_WPC=4 SCAPE_B200_POISON=1"),
