@@ -100,7 +100,9 @@ class ChunkBatch:
 
     def add(self, gene_info_str, df, stream: int):
         self.gene_info.append(gene_info_str)
-        got = self._columns_fast(df)
+        got = self._columns_blocks(df)
+        if got is None:
+            got = self._columns_fast(df)
         if got is None:                       # non-numeric extra columns etc.: column by column
             got = [np.asarray(df[name], dtype=np.float64) for name in ("x", "l", "r", "pa")] + \
                   [np.array(df["cb_id"]), np.array(df["read_id"])]
@@ -123,6 +125,51 @@ class ChunkBatch:
             self.n_reads.append(int(n))
             self.stream.append(stream)
             pos += n
+
+    _block_layouts: dict = {}  # block signature -> (columns Index, [(block, row) of x, l, r, pa, cb_id, read_id])
+
+    @classmethod
+    def _columns_blocks(cls, df):
+        """x, l, r, pa (float64) and cb_id, read_id (their own dtype, like the reference's
+        np.array(data[col]), apa_core.py:1013-1014) straight from the frame's block manager: a
+        prepare_input frame is one int64 block (x, l, cb_id, read_id, junction) and one float64 block (r, pa,
+        seg1_en, seg2_en) whose rows ARE the columns, so nothing is interleaved or converted except x and
+        l (int64 -> float64, exact below 2**53 like any float64 view of them).  ~15 us per frame against
+        ~150 us through DataFrame.to_numpy.  Uses pandas internals (`_mgr.blocks`, `mgr_locs`): anything
+        unexpected returns None and the caller takes the documented-API paths."""
+        try:
+            blocks = df._mgr.blocks
+            sig = tuple((str(b.dtype), b.mgr_locs.as_array.tobytes()) for b in blocks)
+            cols = df.columns
+            ent = cls._block_layouts.get(sig)
+            if ent is None or not (cols is ent[0] or cols.equals(ent[0])):
+                loc = [cols.get_loc(n) for n in ("x", "l", "r", "pa", "cb_id", "read_id")]
+                if not all(isinstance(j, (int, np.integer)) for j in loc):
+                    return None
+                where = {}
+                for bi, b in enumerate(blocks):
+                    for ri, j in enumerate(b.mgr_locs.as_array):
+                        where[int(j)] = (bi, ri)
+                plan = [where[int(j)] for j in loc]
+                for bi, _ in plan:
+                    v = blocks[bi].values
+                    if type(v) is not np.ndarray or v.ndim != 2 or v.dtype.kind not in "iuf":
+                        return None
+                ent = (cols, plan)
+                cls._block_layouts[sig] = ent
+            out = []
+            for k, (bi, ri) in enumerate(ent[1]):
+                row = blocks[bi].values[ri]
+                if k < 4:
+                    out.append(np.ascontiguousarray(row, dtype=np.float64))
+                else:
+                    out.append(np.array(row))
+            n = len(out[0])
+            if any(len(c) != n or c.ndim != 1 for c in out):
+                return None
+            return out
+        except Exception:                                   # internals moved: documented-API paths
+            return None
 
     _layouts: dict = {}       # (column names, dtypes) -> (positions of x, l, r, pa, cb_id, read_id; dtypes of the two ids)
 

@@ -191,3 +191,40 @@ def test_chunk_batch_packed_into_scratch_equals_fresh_arrays():
         for a, b in zip(fresh, kept):
             assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
     assert len(scratch["cols"]) == 4
+
+
+def test_chunk_batch_block_path_equals_column_by_column():
+    """`ChunkBatch._columns_blocks` (columns straight from the block manager) returns what the reference's
+    per-column reads return (np.array(data[col]), apa_core.py:1007-1014): plain frames, float ids with
+    NaN, reordered columns, an extra non-numeric column, a float32 column."""
+    import pandas as pd
+    from scape_b200 import synth
+    from scape_b200.apa_core import ChunkBatch
+    u = synth.make_utr(7, 80)
+    base = synth.to_dataframe(u)
+    frames = [base]
+    f = base.copy(); f["cb_id"] = f["cb_id"].astype(float); f.loc[2, "cb_id"] = np.nan; frames.append(f)
+    frames.append(base[list(reversed(base.columns))])
+    f = base.copy(); f["note"] = "a"; frames.append(f)
+    f = base.copy(); f["r"] = f["r"].astype(np.float32); frames.append(f)
+    frames.append(base.iloc[:0])
+    import pickle
+    frames = [pickle.loads(pickle.dumps(f)) for f in frames]      # like frames read from a chunk file
+    for df in frames:
+        got = ChunkBatch._columns_blocks(df)
+        assert got is not None
+        for name, col in zip(("x", "l", "r", "pa"), got[:4]):
+            want = np.asarray(df[name], dtype=np.float64)
+            assert col.dtype == np.float64 and col.flags.c_contiguous and np.array_equal(col, want, equal_nan=True)
+        for name, col in zip(("cb_id", "read_id"), got[4:]):
+            want = np.array(df[name])
+            assert col.dtype == want.dtype and np.array_equal(col, want, equal_nan=True)
+        batch = ChunkBatch()
+        batch.add("g", df, 0)
+        assert batch.n_reads == [len(df)]
+    # a frame the block path cannot serve (object column among the wanted ones) falls through
+    f = base.copy(); f["pa"] = f["pa"].astype(object)
+    assert ChunkBatch._columns_blocks(f) is None
+    batch = ChunkBatch()
+    batch.add("g", f, 0)
+    assert np.array_equal(batch.cols[3][0], np.asarray(base["pa"], dtype=np.float64), equal_nan=True)
