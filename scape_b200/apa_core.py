@@ -98,6 +98,15 @@ class ChunkBatch:
         self.n_reads: List[int] = []
         self.stream: List[int] = []
 
+    def add_columns(self, gene_info_str, got, stream: int):
+        """One UTR from its six columns: x, l, r, pa as float64, cb_id and read_id in their own dtype."""
+        self.gene_info.append(gene_info_str)
+        for c, col in zip(self.cols, got[:4]):
+            c.append(col)
+        self.frames.append((got[4], got[5]))
+        self.n_reads.append(len(got[0]))
+        self.stream.append(stream)
+
     def add(self, gene_info_str, df, stream: int):
         self.gene_info.append(gene_info_str)
         got = self._columns_blocks(df)
@@ -253,12 +262,113 @@ def read_chunk_file(path) -> list:
                 return out
 
 
+# ---- chunk files without building DataFrames ------------------------------------------------------
+# A prepare_input chunk file is a stream of pickled (gene_info_str, DataFrame) tuples
+# (input_processor.py:224-259, read back at apa_core.py:1117-1132).  Half of what a worker process spends
+# on a file is pandas rebuilding 100 DataFrames (block manager, arrow-backed column Index) that are
+# taken apart again two lines later.  `_LightUnpickler` reads the same pickles with stand-ins for the
+# pandas classes that only keep what was pickled: the blocks' ndarrays, their placements and the column
+# names.  It knows the layout pandas has written since 1.3 (`_unpickle_block`, `BlockManager(blocks,
+# axes)`); anything else raises and the file is read with pickle.load + pandas as before.
+class _LightFrame:
+    def __setstate__(self, state):
+        self.state = state
+
+
+class _LightMgr:
+    def __init__(self, blocks, axes):
+        self.blocks, self.axes = blocks, axes
+
+
+class _LightStrings:                 # pandas.arrays.ArrowStringArray stand-in: keeps the pyarrow array
+    def __setstate__(self, state):
+        self.state = state
+
+    def tolist(self):
+        return self.state["_pa_array"].to_pylist()
+
+
+def _light_block(values, placement, ndim=2):
+    return values, placement
+
+
+def _light_index(cls, d):
+    return d                         # {'data': names, 'name': ...} or a RangeIndex's {'start', 'stop', 'step'}
+
+
+class _LightUnpickler(pickle.Unpickler):
+    _swap = {
+        ("pandas", "DataFrame"): _LightFrame, ("pandas.core.frame", "DataFrame"): _LightFrame,
+        ("pandas.core.internals.managers", "BlockManager"): _LightMgr,
+        ("pandas._libs.internals", "_unpickle_block"): _light_block,
+        ("pandas.core.indexes.base", "_new_Index"): _light_index,
+        ("pandas.arrays", "ArrowStringArray"): _LightStrings,
+        ("pandas.core.arrays.string_arrow", "ArrowStringArray"): _LightStrings,
+    }
+
+    def find_class(self, module, name):
+        got = self._swap.get((module, name))
+        return got if got is not None else super().find_class(module, name)
+
+
+def _light_columns(frame):
+    """x, l, r, pa (float64) and cb_id, read_id (own dtype) of one light frame, like
+    ChunkBatch._columns_blocks; raises on anything that is not the expected layout."""
+    mgr = frame.state["_mgr"]
+    if type(mgr) is not _LightMgr or len(mgr.axes) != 2:
+        raise ValueError("unexpected manager")
+    names = mgr.axes[0]["data"]
+    names = names.tolist() if hasattr(names, "tolist") else list(names)
+    rows = mgr.axes[1]
+    if "stop" in rows:                                   # RangeIndex
+        n = len(range(int(rows.get("start") or 0), int(rows["stop"]), int(rows.get("step") or 1)))
+    else:
+        n = len(rows["data"])
+    where = {}
+    for values, placement in mgr.blocks:
+        locs = range(*placement.indices(len(names))) if isinstance(placement, slice) else np.asarray(placement).tolist()
+        for ri, j in enumerate(locs):
+            where[int(j)] = (values, ri)
+    if sorted(where) != list(range(len(names))):
+        raise ValueError("block placements do not cover the columns")
+    out = []
+    for k, want in enumerate(("x", "l", "r", "pa", "cb_id", "read_id")):
+        if names.count(want) != 1:
+            raise ValueError("column " + want)
+        values, ri = where[names.index(want)]
+        if type(values) is not np.ndarray or values.ndim != 2 or values.dtype.kind not in "iuf" or values.shape[1] != n:
+            raise ValueError("column " + want + " is not a plain numeric block row")
+        row = values[ri]
+        out.append(np.ascontiguousarray(row, dtype=np.float64) if k < 4 else np.array(row))
+    return out
+
+
+def _read_chunk_light(path):
+    """[(gene_info_str, [x, l, r, pa, cb_id, read_id]), ...] of a chunk file without pandas objects."""
+    out = []
+    with open(path, 'rb') as fh:
+        while True:
+            try:
+                gene_info_str, frame = _LightUnpickler(fh).load()
+            except EOFError:
+                return out
+            if type(frame) is not _LightFrame:
+                raise ValueError("not a DataFrame pickle")
+            out.append((gene_info_str, _light_columns(frame)))
+
+
 def _load_chunk_packed(path):
     """Unpickle one chunk file and pack it (runs in a worker process for many-file calls): the
-    DataFrames stay in the worker, a handful of flat arrays come back."""
+    DataFrames stay in the worker (or are never built, `_read_chunk_light`), a handful of flat arrays
+    come back."""
     b = ChunkBatch()
-    for gene_info_str, df in read_chunk_file(path):
-        b.add(gene_info_str, df, 0)
+    try:
+        for gene_info_str, cols6 in _read_chunk_light(path):
+            b.add_columns(gene_info_str, cols6, 0)
+    except Exception:                                    # another pickle layout: pandas reads it
+        b = ChunkBatch()
+        for gene_info_str, df in read_chunk_file(path):
+            b.add(gene_info_str, df, 0)
     cat = lambda parts, dt=None: (np.concatenate(parts) if parts else np.zeros(0, dt or np.float64))
     cols = [cat(c) for c in b.cols]
     cb = cat([f[0] for f in b.frames], np.int64)

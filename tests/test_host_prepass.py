@@ -228,3 +228,59 @@ def test_chunk_batch_block_path_equals_column_by_column():
     batch = ChunkBatch()
     batch.add("g", f, 0)
     assert np.array_equal(batch.cols[3][0], np.asarray(base["pa"], dtype=np.float64), equal_nan=True)
+
+
+def test_chunk_files_read_without_dataframes_equal_the_pandas_path(tmp_path):
+    """`_read_chunk_light` (stand-ins for the pandas classes while unpickling) yields the same columns as
+    pickle.load + pandas, frame by frame; layouts it does not know make `_load_chunk_packed` fall back."""
+    import pickle
+    import pandas as pd
+    from scape_b200 import apa_core, synth
+    us = [synth.make_utr(i, 40 + 7 * i) for i in range(6)]
+    frames = [synth.to_dataframe(u) for u in us]
+    frames[1]["cb_id"] = frames[1]["cb_id"].astype(float)
+    frames[1].loc[3, "cb_id"] = np.nan
+    frames[2] = frames[2][list(reversed(frames[2].columns))]
+    frames[3]["note"] = "a"
+    frames[4]["r"] = frames[4]["r"].astype(np.float32)
+    frames[5] = frames[5].iloc[:0]
+    path = tmp_path / "demo.100.1.1.input.pkl"
+    with open(path, "wb") as fh:
+        for u, df in zip(us, frames):
+            pickle.dump((u.gene_info_str, df), fh)
+    light = apa_core._read_chunk_light(str(path))
+    heavy = apa_core.read_chunk_file(str(path))
+    assert [g for g, _ in light] == [g for g, _ in heavy]
+    for (_, cols), (_, df) in zip(light, heavy):
+        for name, col in zip(("x", "l", "r", "pa"), cols[:4]):
+            want = np.asarray(df[name], dtype=np.float64)
+            assert col.dtype == np.float64 and np.array_equal(col, want, equal_nan=True)
+        for name, col in zip(("cb_id", "read_id"), cols[4:]):
+            want = np.array(df[name])
+            assert col.dtype == want.dtype and np.array_equal(col, want, equal_nan=True)
+    # the packed form (what a worker process returns) is the same through both readers
+    a = apa_core._load_chunk_packed(str(path))
+    b = apa_core.ChunkBatch()
+    for g, df in heavy:
+        b.add(g, df, 0)
+    assert a[0] == b.gene_info and a[1] == b.n_reads
+    for got, parts in zip(a[2:6], b.cols):
+        assert np.array_equal(got, np.concatenate(parts), equal_nan=True)
+    assert np.array_equal(a[6], np.concatenate([f[0] for f in b.frames]), equal_nan=True)
+    assert np.array_equal(a[7], np.concatenate([f[1] for f in b.frames]))
+    # a file whose wanted column is not a numeric block row: the light reader refuses, the packed loader falls back
+    bad = frames[0].copy()
+    bad["pa"] = bad["pa"].astype(object)
+    path2 = tmp_path / "odd.100.1.1.input.pkl"
+    with open(path2, "wb") as fh:
+        pickle.dump((us[0].gene_info_str, bad), fh)
+    with pytest.raises(Exception):
+        apa_core._read_chunk_light(str(path2))
+    got = apa_core._load_chunk_packed(str(path2))
+    assert np.array_equal(got[5], np.asarray(frames[0]["pa"], dtype=np.float64), equal_nan=True)
+    # a file that holds something else than (str, DataFrame) tuples
+    path3 = tmp_path / "other.100.1.1.input.pkl"
+    with open(path3, "wb") as fh:
+        pickle.dump((us[0].gene_info_str, {"x": 1}), fh)
+    with pytest.raises(Exception):
+        apa_core._read_chunk_light(str(path3))
