@@ -396,6 +396,93 @@ def _write_result_file(path, fixed_run_mode, gene_infos, n_reads, K, L, alpha, b
     return path
 
 
+# ---- big arrays between the worker processes and this one: tmpfs files instead of pipes -----------------
+# A packed chunk file is ~2.4 MB of columns and a result file needs ~1.2 MB of labels and ids; through the
+# executor's pipes this process receives / sends them at ~1 GB/s, one file after the other (0.25 s + 0.1 s
+# for 100 cfg-2 files, a quarter of the whole call).  The workers therefore exchange them through files in
+# a tmpfs directory, which both sides map; only names and small per-UTR arrays travel through the pipes.
+_SHM_DIR = os.environ.get("SCAPE_B200_SHM_DIR", "/dev/shm")
+
+
+def _shm_ok() -> bool:
+    return bool(_SHM_DIR) and os.path.isdir(_SHM_DIR) and os.access(_SHM_DIR, os.W_OK)
+
+
+def _shm_write(arrays) -> str:
+    """The arrays back to back in a new tmpfs file (each one 8-byte aligned); returns its name."""
+    import tempfile
+    fd, name = tempfile.mkstemp(prefix="scape_b200_", dir=_SHM_DIR)
+    try:
+        with os.fdopen(fd, "wb") as fh:
+            for a in arrays:
+                a = np.ascontiguousarray(a)
+                fh.write(memoryview(a).cast("B"))
+                pad = (-a.nbytes) % 8
+                if pad:
+                    fh.write(b"\0" * pad)
+    except BaseException:
+        _shm_unlink(name)
+        raise
+    return name
+
+
+def _shm_read(name: str, specs):
+    """The arrays `_shm_write` put into `name`, as read-only views of one mapping; specs = [(dtype str, n)]."""
+    total = sum(np.dtype(d).itemsize * n + (-(np.dtype(d).itemsize * n)) % 8 for d, n in specs)
+    if total == 0:
+        return [np.zeros(0, np.dtype(d)) for d, _ in specs]
+    mm = np.memmap(name, dtype=np.uint8, mode="r", shape=(total,))
+    out, pos = [], 0
+    for d, n in specs:
+        nb = np.dtype(d).itemsize * n
+        out.append(np.frombuffer(mm, dtype=np.dtype(d), count=n, offset=pos))
+        pos += nb + (-nb) % 8
+    return out
+
+
+def _shm_unlink(name):
+    try:
+        os.unlink(name)
+    except OSError:
+        pass
+
+
+def _load_chunk_shm(path):
+    """`_load_chunk_packed` in a worker process, the six columns left in a tmpfs file for the parent."""
+    gene_infos, n_reads, x, l, r, pa, cb, rid = _load_chunk_packed(path)
+    n = len(x)
+    if n == 0 or not _shm_ok():
+        return ("inline", gene_infos, n_reads, x, l, r, pa, cb, rid)
+    try:
+        name = _shm_write([x, l, r, pa, cb, rid])
+    except OSError:                                       # tmpfs full: through the pipe after all
+        return ("inline", gene_infos, n_reads, x, l, r, pa, cb, rid)
+    return ("shm", gene_infos, n_reads, name, n, cb.dtype.str, rid.dtype.str)
+
+
+def _open_chunk(rec):
+    """What `_load_chunk_packed` returns, from a `_load_chunk_shm` record (+ the tmpfs file's name and the id
+    dtypes, for `_write_result_file_shm`; None for inline records)."""
+    if rec[0] == "inline":
+        return rec[1:] + (None,)
+    _, gene_infos, n_reads, name, n, cb_dt, rid_dt = rec
+    x, l, r, pa, cb, rid = _shm_read(name, [("<f8", n)] * 4 + [(cb_dt, n), (rid_dt, n)])
+    return gene_infos, n_reads, x, l, r, pa, cb, rid, (name, n, cb_dt, rid_dt)
+
+
+def _write_result_file_shm(path, fixed_run_mode, gene_infos, n_reads, K, L, alpha, beta, ws, bic, n_lb, lb_arr,
+                           label_ref, ids_ref):
+    """`_write_result_file` with the per-read arrays taken from tmpfs files: label_ref = (file, first read,
+    reads) into the fit's int64 label array, ids_ref = the chunk's `_load_chunk_shm` file."""
+    lname, first, n = label_ref
+    label = np.memmap(lname, dtype=np.int64, mode="r")[first:first + n] if n else np.zeros(0, np.int64)
+    name, n_ids, cb_dt, rid_dt = ids_ref
+    cb, rid = _shm_read(name, [("<f8", n_ids)] * 4 + [(cb_dt, n_ids), (rid_dt, n_ids)])[4:]
+    # (np.array: the Parameters own their arrays, like the reference's; the mappings go away with this call)
+    return _write_result_file(path, fixed_run_mode, gene_infos, n_reads, K, L, alpha, beta, ws, bic, n_lb, lb_arr,
+                              np.array(label), np.array(cb), np.array(rid))
+
+
 _io_pool = None
 _engines = {}
 _engines_lock = __import__("threading").Lock()
@@ -600,7 +687,30 @@ def _infer_files_pooled(paths, outs, devices, io_workers, **kwargs):
     pool = _get_io_pool(io_workers)
     fixed = bool(kwargs.get("fixed_run_mode", False))
     pre_para = _load_pre_para(kwargs) if fixed else None
-    packed = list(pool.map(_load_chunk_packed, paths))
+    shm_files: List[str] = []
+    try:
+        return _infer_files_pooled_run(pool, paths, outs, devices, fixed, pre_para, shm_files, **kwargs)
+    finally:
+        for name in shm_files:
+            _shm_unlink(name)
+
+
+def _infer_files_pooled_run(pool, paths, outs, devices, fixed, pre_para, shm_files, **kwargs):
+    import threading
+    from . import shard
+    loads = [pool.submit(_load_chunk_shm, p) for p in paths]
+    records, first_error = [], None
+    for fut in loads:                   # every record is collected, so that every tmpfs file gets unlinked
+        try:
+            rec = fut.result()
+            if rec[0] == "shm":
+                shm_files.append(rec[3])
+            records.append(rec)
+        except BaseException as e:
+            first_error = first_error or e
+    if first_error is not None:
+        raise first_error
+    packed = [_open_chunk(rec) for rec in records]
     if len(devices) > 1:
         hints = [int(np.max(p[2]) + np.max(p[3]) + 50) if len(p[2]) else 2000 for p in packed]   # max x + max l of the file
         costs = shard.stream_costs([p[1] for p in packed], [[h] * len(p[1]) for h, p in zip(hints, packed)])
@@ -616,7 +726,7 @@ def _infer_files_pooled(paths, outs, devices, io_workers, **kwargs):
                 return
             batch = ChunkBatch()
             for s, f in enumerate(mine):
-                batch.add_packed(s, *packed[f])
+                batch.add_packed(s, *packed[f][:8])
             engine = _cached_engine(dev, _lib.make_params(pre_para=pre_para, **kwargs),
                                     host_threads=max(1, (os.cpu_count() or 1) // len(devices)) if len(devices) > 1 else 0,
                                     tensor_dtype=kwargs.get("tensor_dtype"))
@@ -627,14 +737,27 @@ def _infer_files_pooled(paths, outs, devices, io_workers, **kwargs):
                 out = engine.fit(off, x, l, r, pa, sid, np.ones(len(mine), np.uint32))
             if np.any(out.status != 0):
                 results_to_parameters(batch, out, fixed)      # raises the reference's error for the first bad UTR
+            # the fit's per-read labels go to the workers through one tmpfs file (when the chunks came that way)
+            label_file = None
+            if _shm_ok() and any(packed[f][8] is not None for f in mine) and len(out.label):
+                try:
+                    label_file = _shm_write([np.asarray(out.label, dtype=np.int64)])
+                    with flock:
+                        shm_files.append(label_file)
+                except OSError:
+                    label_file = None
             u0 = 0
             for f in mine:
-                gene_infos, n_reads, cb, rid = packed[f][0], packed[f][1], packed[f][6], packed[f][7]
+                gene_infos, n_reads, cb, rid, ids_ref = packed[f][0], packed[f][1], packed[f][6], packed[f][7], packed[f][8]
                 n_utr = len(gene_infos)
                 us = slice(u0, u0 + n_utr)
                 rs = slice(int(off[u0]), int(off[u0 + n_utr]))
-                fut = pool.submit(_write_result_file, outs[f], fixed, gene_infos, n_reads, out.K[us], out.L[us], out.alpha[us],
-                                  out.beta[us], out.ws[us], out.bic[us], out.n_lb[us], out.lb_arr[us], out.label[rs], cb, rid)
+                small = (outs[f], fixed, gene_infos, n_reads, out.K[us], out.L[us], out.alpha[us], out.beta[us], out.ws[us],
+                         out.bic[us], out.n_lb[us], out.lb_arr[us])
+                if label_file is not None and ids_ref is not None:
+                    fut = pool.submit(_write_result_file_shm, *small, (label_file, rs.start, rs.stop - rs.start), ids_ref)
+                else:
+                    fut = pool.submit(_write_result_file, *small, out.label[rs], np.array(cb), np.array(rid))
                 with flock:
                     futures.append(fut)
                 u0 += n_utr

@@ -1,6 +1,8 @@
 """libscape_b200's host pre-pass (no GPU): binning, coverage profile, peaks and the numpy-legacy
 RNG replay must be bit-identical to numpy / scipy / the oracle, because every later result depends
 on the initial draws (hard part #1)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -284,3 +286,38 @@ def test_chunk_files_read_without_dataframes_equal_the_pandas_path(tmp_path):
         pickle.dump((us[0].gene_info_str, {"x": 1}), fh)
     with pytest.raises(Exception):
         apa_core._read_chunk_light(str(path3))
+
+
+def test_tmpfs_exchange_of_packed_chunks(tmp_path, monkeypatch):
+    """Worker processes hand the packed columns of a chunk file to the parent through a tmpfs file
+    (`_load_chunk_shm` / `_open_chunk`); without a usable directory the record carries the arrays itself.
+    Both forms equal `_load_chunk_packed`; the file layout survives odd sizes and dtypes."""
+    import pickle
+    from scape_b200 import apa_core, synth
+    us = [synth.make_utr(i, 33 + i) for i in range(3)]
+    path = synth.write_chunk_files(us, str(tmp_path), per_file=100)[0]
+    want = apa_core._load_chunk_packed(path)
+    monkeypatch.setattr(apa_core, "_SHM_DIR", str(tmp_path))
+    rec = apa_core._load_chunk_shm(path)
+    assert rec[0] == "shm" and os.path.exists(rec[3])
+    got = apa_core._open_chunk(rec)
+    assert got[8] == (rec[3], len(want[2]), want[6].dtype.str, want[7].dtype.str)
+    os.unlink(rec[3])                                   # the mapping outlives the name
+    assert got[0] == want[0] and got[1] == want[1]
+    for a, b in zip(got[2:8], want[2:8]):
+        assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+    monkeypatch.setattr(apa_core, "_SHM_DIR", str(tmp_path / "missing"))
+    rec = apa_core._load_chunk_shm(path)
+    assert rec[0] == "inline"
+    got = apa_core._open_chunk(rec)
+    assert got[8] is None
+    for a, b in zip(got[2:8], want[2:8]):
+        assert np.array_equal(a, b, equal_nan=True)
+    # raw layout: every array starts 8-byte aligned whatever came before it
+    monkeypatch.setattr(apa_core, "_SHM_DIR", str(tmp_path))
+    arrays = [np.arange(5, dtype=np.int32), np.array([1.5, np.nan, -2.0]), np.arange(3, dtype=np.int16), np.zeros(0), np.arange(2, dtype=np.int64)]
+    name = apa_core._shm_write(arrays)
+    back = apa_core._shm_read(name, [(a.dtype.str, len(a)) for a in arrays])
+    os.unlink(name)
+    for a, b in zip(arrays, back):
+        assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
