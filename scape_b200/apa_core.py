@@ -455,7 +455,7 @@ def _load_chunk_shm(path):
         return ("inline", gene_infos, n_reads, x, l, r, pa, cb, rid)
     try:
         name = _shm_write([x, l, r, pa, cb, rid])
-    except OSError:                                       # tmpfs full: through the pipe after all
+    except Exception:                                     # tmpfs full or unusable: through the pipe after all
         return ("inline", gene_infos, n_reads, x, l, r, pa, cb, rid)
     return ("shm", gene_infos, n_reads, name, n, cb.dtype.str, rid.dtype.str)
 
@@ -744,7 +744,7 @@ def _infer_files_pooled_run(pool, paths, outs, devices, fixed, pre_para, shm_fil
                     label_file = _shm_write([np.asarray(out.label, dtype=np.int64)])
                     with flock:
                         shm_files.append(label_file)
-                except OSError:
+                except Exception:
                     label_file = None
             u0 = 0
             for f in mine:
